@@ -1,0 +1,262 @@
+/* wesep_b200 — C-ABI of the B200-native (sm_100a) target-speaker-extraction train-step kernels.
+ *
+ * This is the drop-in boundary: the reference (wenet-e2e/wesep) has no native
+ * code on its training path — it calls stock torch.nn modules.  Each entry point below replaces the
+ * ATen/cuDNN/cuBLAS work behind one reference nn.Module.forward (+ its autograd backward); the
+ * reference file:line is cited per function.  Host side = Python nn.Modules with the reference's
+ * class names / ctor kwargs / state_dict keys (wesep_b200/models, wesep_b200/modules) that bind
+ * these symbols with ctypes.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, POD argument structs, no torch types.
+ *   - every pointer is a DEVICE pointer unless named host_*; `stream` is a cudaStream_t.
+ *   - asynchronous on `stream`; no allocation, no host sync; caller owns all memory.
+ *   - activations are fp32 `[n][C][ld]`: time contiguous, row stride `ld` floats (ld % 4 == 0,
+ *     ld >= T, base 16-byte aligned), batch stride = C*ld.  Columns t in [T, ld) are padding:
+ *     never read as data; their contents are unspecified.
+ *   - return 0 on success, -1 bad shape/alignment, -2 unsupported configuration, -3 CUDA error
+ *     (text via wesep_b200_last_error()).
+ *   - gLN statistics buffers are `double[n][2]` = (sum, sum of squares) over (C,T) of the
+ *     normalised tensor; they must be zeroed by the caller before the producing call unless noted.
+ *   - parameter-gradient outputs ACCUMULATE (+=) into caller-zeroed buffers.
+ */
+#ifndef WESEP_B200_H_
+#define WESEP_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WESEP_B200_VERSION 100
+
+int wesep_b200_version(void);
+/* Last error text of the calling thread ("" if none). */
+const char* wesep_b200_last_error(void);
+/* Number of kernels launched by this library in this process (diagnostic; bench.py gpu_launches). */
+uint64_t wesep_b200_launch_count(void);
+/* GEMM precision: 0 = 3xTF32 split (fp32-grade, default), 1 = single-pass TF32. Process-wide. */
+int wesep_b200_set_gemm_mode(int mode);
+
+/* ------------------------------------------------------------------------------------------------
+ * SI-SDR loss (replaces auraloss.time.SISDRLoss used at wesep/utils/losses.py:24-25, called at
+ * wesep/utils/executor.py:115-122).  Up to 4 estimates share one target (Spex+ est1..3).
+ * loss_i = -(1/n) sum_rows 10 log10( |a t~|^2 / (|x~ - a t~|^2 + eps) + eps ),  zero-mean, eps=1e-8.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int n_est;             /* 1..4 */
+  int n;                 /* rows */
+  int L;                 /* samples per row */
+  const float* est[4];   /* [n][ld_est] */
+  int64_t ld_est[4];
+  const float* tgt;      /* [n][ld_tgt] */
+  int64_t ld_tgt;
+  double* sums;          /* workspace [n_est][n][5] (Sx,St,Sxt,Sxx,Stt); zeroed by the call */
+  float* sisdr_rows;     /* out [n_est][n] per-row SI-SDR in dB (positive = good) */
+  float* loss;           /* out [n_est] = -mean_rows(sisdr) */
+} WesepSisdrFwdArgs;
+int wesep_b200_sisdr_fwd(const WesepSisdrFwdArgs* a, void* stream);
+
+typedef struct {
+  int n_est, n, L;
+  const float* est[4];
+  int64_t ld_est[4];
+  const float* tgt;
+  int64_t ld_tgt;
+  const double* sums;    /* from the forward call */
+  const float* gloss;    /* [n_est] upstream d(total)/d(loss_i) (device) */
+  float* gest[4];        /* out [n][ld_gest] gradient wrt est_i (overwritten) */
+  int64_t ld_gest[4];
+} WesepSisdrBwdArgs;
+int wesep_b200_sisdr_bwd(const WesepSisdrBwdArgs* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Per-tensor gradient clip + Adam with coupled L2 decay over a flat fp32 arena (replaces
+ * clip_gradients wesep/utils/funcs.py:79-88 + torch.optim.Adam(weight_decay) wesep/bin/train.py:237).
+ * Tensors are segments [seg_off[i], seg_off[i+1]) of the arenas (offsets multiples of 4).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int64_t total;            /* arena length in floats */
+  int n_seg;
+  const int64_t* seg_off;   /* device [n_seg+1] */
+  const int32_t* chunk_seg; /* device [n_chunk]: segment of each 4096-float chunk (chunks never straddle) */
+  const int64_t* chunk_off; /* device [n_chunk]: first element of the chunk */
+  int n_chunk;
+  float* param;             /* [total] */
+  float* grad;              /* [total]  (scaled by grad_scale before clipping; modified in place when clipped) */
+  float* exp_avg;           /* [total] */
+  float* exp_avg_sq;        /* [total] */
+  double* sumsq;            /* workspace [n_seg]; zeroed by the call */
+  float* norms;             /* out [n_seg] per-tensor L2 norm (after grad_scale) */
+  float grad_scale;         /* e.g. 1/world_size after an all-reduce(sum) */
+  float clip;               /* <= 0 disables clipping */
+  float lr, beta1, beta2, eps, weight_decay;
+  int step;                 /* 1-based */
+} WesepClipAdamArgs;
+int wesep_b200_clip_adam(const WesepClipAdamArgs* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * 1x1-conv GEMM  Y[n][M][T] = W[M][Kd] * f(X[n][Kd][T]) (+ epilogue)  — the pointwise convs of
+ * wesep/modules/tasnet/{convs,encoder,decoder,speaker}.py.  Exposed for tests and for the host
+ * modules that are not fused TCN blocks.
+ *   pro:  0 identity | 1 prelu(alpha) | 2 scale_c*prelu(x; alpha)+shift_c with per-(row,channel)
+ *         scale/shift built from (ch_scale, ch_shift, row_stats): gLN-apply or BN-apply.
+ *   epi:  0 Y=acc+bias | 1 Y=relu(acc+bias) | 2 Y=acc+bias+R (residual) |
+ *         3 Y=aux*relu(acc+bias), Y2=relu(acc+bias) (decoder mask, decoder.py:96-102)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int n, M, Kd, T;
+  const float* W; int64_t ldw; int w_trans;   /* w_trans: W stored [Kd][M] (ldw >= M) */
+  const float* X; int64_t ldx;                /* [n][Kd][ldx] */
+  float* Y; int64_t ldy;                      /* [n][M][ldy] */
+  const float* bias;                          /* [M] or NULL */
+  const float* row_bias;                      /* [n][M] or NULL (added to bias) */
+  int pro;
+  const float* alpha;                         /* PReLU slope (device scalar) for pro 1/2; NULL = 1 */
+  const float* ch_scale; const float* ch_shift; /* [Kd] or NULL */
+  const double* row_stats; double stat_count; float stat_eps; /* gLN of X: [n][2], count=C*T */
+  int epi;
+  const float* R; int64_t ldr;                /* residual [n][M][ldr] (epi 2) / aux (epi 3) */
+  float* Y2; int64_t ldy2;                    /* second output (epi 3) */
+  double* out_stats;                          /* optional [n][2]: += sum / sumsq of prelu(Y; out_alpha) */
+  const float* out_alpha;
+  double* ch_stats;                           /* optional [M][2]: += per-channel sum / sumsq of Y (BatchNorm) */
+  int64_t bsx, bsy, bsr, bsy2;                /* batch strides in floats; 0 = dense (C*ld): channel-slices of wider tensors */
+} WesepGemmArgs;
+int wesep_b200_conv1x1(const WesepGemmArgs* a, void* stream);
+
+/* Weight-gradient GEMM  C[M][N] += sum_n sum_t fa(A[n][M][t]) * fb(B[n][N][t]);  per_row: C is
+ * [n][M][N] (no sum over n).  pro_* as above (row_stats give per-row mean/rstd: fb = (prelu(b)-mu)*r
+ * when ch_scale==NULL). */
+typedef struct {
+  int n, M, N, T;
+  const float* A; int64_t lda;  /* [n][M][lda] */
+  const float* B; int64_t ldb;  /* [n][N][ldb] */
+  float* C; int per_row;
+  int pro_b;
+  const float* alpha_b;
+  const float* ch_scale_b; const float* ch_shift_b;
+  const double* row_stats_b; double stat_count; float stat_eps;
+  int64_t bsa, bsb;             /* batch strides in floats; 0 = dense */
+  int64_t ldc;                  /* row stride of C; 0 = N */
+} WesepGemmDwArgs;
+int wesep_b200_conv1x1_dw(const WesepGemmDwArgs* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused TCN block (Conv1DBlock wesep/modules/tasnet/convs.py:43-104, skip_con False, non-causal,
+ * gLN; and Conv1DBlock4Fuse :107-160 when aux != NULL: the speaker half of conv1x1.weight is
+ * folded into a per-row bias).
+ *   u   = W1[:, :B] x + b1 (+ W1[:, B:] aux_n)       y1 = prelu(u, a1)      z1 = gLN1(y1)
+ *   d   = dwconv(z1; wd, bd, dilation)               y2 = prelu(d, a2)      z2 = gLN2(y2)
+ *   out = x + W3 z2 + b3
+ * Saved for backward: u, d (pre-activations), stats1, stats2.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int n, B, H, T, dil, E;       /* E = speaker-embedding dim (0 for plain block) */
+  int64_t ld;                   /* row stride of every activation below */
+  const float* x;               /* [n][B][ld] */
+  const float* aux;             /* [n][E] or NULL */
+  const float* W1; int64_t ldw1;/* [H][B+E] */
+  const float* b1;              /* [H] */
+  const float* a1;              /* [1] */
+  const float* g1; const float* be1; /* gLN1 weight/bias [H] */
+  const float* wd;              /* [H][3] */
+  const float* bd;              /* [H] */
+  const float* a2;
+  const float* g2; const float* be2;
+  const float* W3; int64_t ldw3;/* [B][H] */
+  const float* b3;              /* [B] */
+  float* u; float* d;           /* out [n][H][ld] */
+  float* out;                   /* out [n][B][ld] */
+  double* stats1; double* stats2; /* out [n][2] each (zeroed by the call) */
+  float* row_bias;              /* workspace [n][H] (fuse block only) */
+} WesepTcnFwdArgs;
+int wesep_b200_tcn_block_fwd(const WesepTcnFwdArgs* a, void* stream);
+
+typedef struct {
+  WesepTcnFwdArgs f;            /* same tensors as forward (out unused) */
+  const float* gout;            /* [n][B][ld] dL/d out */
+  float* dx;                    /* out [n][B][ld] */
+  /* parameter gradients (+=) */
+  float* dW1; float* db1; float* da1; float* dg1; float* dbe1;
+  float* dwd; float* dbd; float* da2; float* dg2; float* dbe2;
+  float* dW3; float* db3;
+  float* daux;                  /* [n][E] (overwritten) or NULL */
+  /* workspace */
+  float* dd; float* du;         /* [n][H][ld] each */
+  float* Gn;                    /* [n][B][H] */
+  float* sg;                    /* [n][B] */
+  float* sdu;                   /* [n][H] */
+  double* rowsc;                /* [n][8] */
+} WesepTcnBwdArgs;
+int wesep_b200_tcn_block_bwd(const WesepTcnBwdArgs* a, void* stream);
+/* bytes of the zero-initialised scratch the backward call needs are all caller-provided above. */
+
+/* ------------------------------------------------------------------------------------------------
+ * Channel-wise LayerNorm over C per frame (ChannelWiseLayerNorm wesep/modules/common/norm.py:51-66).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int n, C, T; int64_t ldx, ldy;
+  const float* x; float* y;
+  const float* gamma; const float* beta; float eps;
+  float* mean; float* rstd;     /* out [n][T] (saved for backward) */
+} WesepClnFwdArgs;
+int wesep_b200_cln_fwd(const WesepClnFwdArgs* a, void* stream);
+typedef struct {
+  int n, C, T; int64_t ldx, ldg, lddx;
+  const float* x; const float* gy; float* dx;
+  const float* gamma; const float* mean; const float* rstd;
+  float* dgamma; float* dbeta;  /* += [C] */
+} WesepClnBwdArgs;
+int wesep_b200_cln_bwd(const WesepClnBwdArgs* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Framing / overlap-add for the strided encoder / transposed decoder convs
+ * (MultiEncoder wesep/modules/tasnet/encoder.py:95-110, MultiDecoder decoder.py:104-108).
+ *   frames:      F[n][j][k] = x[n][k*hop + j]  (0 beyond the signal), j < J, k < K
+ *   overlap_add: y[n][s]    = bias + sum_{j,k: k*hop+j == s} F[n][j][k],  s < S
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int n, J, K, hop; int64_t S;
+  const float* x; int64_t ldx;  /* [n][ldx] signal of S valid samples */
+  float* F; int64_t ldf;        /* [n][J][ldf] */
+} WesepFrameArgs;
+int wesep_b200_frames(const WesepFrameArgs* a, void* stream);
+typedef struct {
+  int n, J, K, hop; int64_t S;
+  const float* F; int64_t ldf;
+  const float* bias;            /* device scalar or NULL */
+  float* y; int64_t ldy;
+} WesepOlaArgs;
+int wesep_b200_overlap_add(const WesepOlaArgs* a, void* stream);
+
+/* Elementwise helpers used by the host modules' backward passes. */
+typedef struct {
+  int n, C, T; int64_t ld;
+  const float* gS;              /* [n][C][ld] dL/dS, S = w * m, m = relu(mask conv) */
+  const float* w; const float* m;
+  float* gw;                    /* out dL/dw += ... (accumulate: w feeds three paths) or overwrite, see acc_w */
+  float* gm;                    /* out dL/d(pre-relu mask) */
+  int acc_w;
+} WesepMaskBwdArgs;
+int wesep_b200_mask_bwd(const WesepMaskBwdArgs* a, void* stream);
+
+typedef struct {
+  int n, C, T; int64_t ld;
+  const float* y;               /* relu output */
+  const float* gy; float* gx;   /* gx = gy * (y > 0) */
+} WesepReluBwdArgs;
+int wesep_b200_relu_bwd(const WesepReluBwdArgs* a, void* stream);
+
+/* Row sums over time: out[n][c] = sum_t x[n][c][t]  (bias gradients). */
+typedef struct {
+  int n, C, T; int64_t ld;
+  const float* x; float* out;   /* out [n][C] overwritten */
+} WesepRowSumArgs;
+int wesep_b200_rowsum(const WesepRowSumArgs* a, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WESEP_B200_H_ */

@@ -1,0 +1,146 @@
+"""GPU parity of the whole Spex+ path against (a) golden outputs of the REAL reference
+(tests/golden/*.npz) and (b) the oracle run in fp64, incl. the full train step."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import losses as olosses
+from oracle import optim as ooptim
+from oracle import spexplus as ospex
+from tests.util import cfg_from_args, fixture_inputs, load_fixture, rel_l2
+from wesep_b200 import synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def build_model(args, wseed):
+    from wesep_b200.models import get_model
+    m = get_model("ConvTasNet")(**args)
+    synth.fill_state_dict_(m.state_dict(), seed=wseed)
+    return m.to(DEV)
+
+
+def run_fixture(name, check_grads=True):
+    from wesep_b200.utils.executor import compute_loss
+    z, meta = load_fixture(name)
+    m = build_model(meta["args"], meta["wseed"])
+    m.train(meta["train"])
+    b = synth.make_batch(meta["n"], T=meta["T"], Te=meta["Te"], seed=meta["dseed"], device=DEV)
+    with torch.set_grad_enabled(meta["backward"]):
+        out = m(b["wav_mix"], b["spk_embeds"])
+        loss, rows = compute_loss(out, b["wav_targets"], b["spk_label"], multi_task=meta["args"].get("multi_task", True))
+    sub = meta["subsample"]
+    report = {}
+    for i in range(3):
+        ref = torch.from_numpy(z[f"out{i}"]).to(DEV)
+        got = out[i].detach()[..., ::sub]
+        assert got.shape == ref.shape, (name, i, got.shape, ref.shape)
+        report[f"out{i}"] = rel_l2(got, ref)
+        assert report[f"out{i}"] <= 2e-4, (name, f"out{i}", report[f"out{i}"])
+        d = float(np.max(np.abs(rows[i].detach().cpu().numpy() - z[f"sisdr_rows{i}"])))
+        report[f"dB{i}"] = d
+        assert d <= 0.01, (name, f"SI-SDR est{i + 1} differs by {d:.4f} dB (tolerance 0.01 dB)")
+    if len(out) > 3:
+        assert rel_l2(out[3].detach(), torch.from_numpy(z["out3"]).to(DEV)) <= 2e-4
+    assert abs(float(loss) - float(z["loss"])) <= 1e-3 * abs(float(z["loss"])) + 2e-3, (float(loss), float(z["loss"]))
+    if meta["backward"] and check_grads:
+        loss.backward()
+        worst = 0.0
+        for k, p in m.named_parameters():
+            ref = float(z["gnorm/" + k])
+            gn = float(p.grad.double().norm())
+            assert abs(gn - ref) <= 5e-3 * ref + 1e-6, (name, k, gn, ref)
+            if ("g/" + k) in z:
+                g = torch.from_numpy(z["g/" + k]).to(DEV)
+                e = float((p.grad - g).double().norm() / (g.double().norm() + 1e-12))
+                worst = max(worst, e)
+                assert e <= 5e-3, (name, k, e)
+        report["worst_small_grad_rel"] = worst
+    if meta["train"]:
+        for k, v in m.state_dict().items():
+            if k.endswith("running_mean") or k.endswith("running_var"):
+                assert torch.allclose(v.cpu(), torch.from_numpy(z["buf/" + k]), rtol=1e-3, atol=1e-5), (name, k)
+    return report
+
+
+@pytest.mark.parametrize("name", ["spex_small_train", "spex_small_eval", "spex_small_n1"])
+def test_golden_small(name):
+    run_fixture(name)
+
+
+def test_golden_full_cfg1_eval():
+    """BASELINE config 1: Spex+ forward + SI-SNR, one 2-speaker 4 s mixture, vs the real reference."""
+    run_fixture("spex_full_cfg1_eval")
+
+
+def test_golden_full_cfg1_train():
+    run_fixture("spex_full_cfg1_train")
+
+
+def test_full_model_vs_oracle_fp64_all_grads():
+    """Every output and EVERY parameter gradient of the small config vs the fp64 oracle."""
+    from wesep_b200.utils.executor import compute_loss
+    z, meta = load_fixture("spex_small_train")
+    m = build_model(meta["args"], meta["wseed"])
+    m.train()
+    b = synth.make_batch(meta["n"], T=meta["T"], Te=meta["Te"], seed=meta["dseed"], device=DEV)
+    out = m(b["wav_mix"], b["spk_embeds"])
+    loss, _ = compute_loss(out, b["wav_targets"], b["spk_label"])
+    loss.backward()
+    cfg, sd, _ = fixture_inputs(meta, dtype=torch.float64, device=DEV)
+    names = [k for k, _ in m.named_parameters()]
+    for k in names:
+        sd[k].requires_grad_(True)
+    o64 = ospex.convtasnet_forward(sd, cfg, b["wav_mix"].double(), b["spk_embeds"].double(), training=True)
+    l64, _ = olosses.train_loss(o64, b["wav_targets"].double(), b["spk_label"])
+    l64.backward()
+    assert abs(float(loss) - float(l64)) <= 2e-3
+    for i in range(4):
+        assert rel_l2(out[i].detach(), o64[i].detach()) <= 5e-5, i
+    bad = []
+    for k, p in m.named_parameters():
+        e = rel_l2(p.grad, sd[k].grad)
+        if e > 2e-3:
+            bad.append((k, e))
+    assert not bad, bad[:10]
+
+
+def test_train_steps_vs_oracle():
+    """3 full train steps (fwd, loss, bwd, per-tensor clip, Adam wd=1e-4, exp-decay lr) vs the oracle loop."""
+    from wesep_b200.utils.executor import train_step
+    from wesep_b200.utils.optim import FusedClipAdam
+    z, meta = load_fixture("spex_small_train")
+    m = build_model(meta["args"], meta["wseed"])
+    m.train()
+    opt = FusedClipAdam(m.parameters(), lr=1e-3, weight_decay=1e-4, clip=5.0)
+    cfg, sd, _ = fixture_inputs(meta, dtype=torch.float64, device=DEV)
+    names = [k for k, _ in m.named_parameters()]
+    P = [sd[k].requires_grad_(True) for k in names]
+    mom = [torch.zeros_like(p) for p in P]
+    var = [torch.zeros_like(p) for p in P]
+    losses, ref_losses = [], []
+    for step in range(3):
+        lr = ooptim.exponential_decrease_lr(step, 1000)
+        b = synth.make_batch(meta["n"], T=meta["T"], Te=meta["Te"], seed=100 + step, device=DEV)
+        opt.param_groups[0]["lr"] = lr
+        losses.append(float(train_step(m, b, opt)))
+        bufs = {}
+        o64 = ospex.convtasnet_forward(sd, cfg, b["wav_mix"].double(), b["spk_embeds"].double(), training=True,
+                                       buffers_out=bufs)
+        l64, _ = olosses.train_loss(o64, b["wav_targets"].double(), b["spk_label"])
+        grads = torch.autograd.grad(l64, P)
+        grads = [g.clone() for g in grads]
+        ooptim.clip_gradients(grads, 5.0)
+        with torch.no_grad():
+            ooptim.adam_step(P, grads, mom, var, step + 1, lr)
+            sd.update(bufs)
+        ref_losses.append(float(l64))
+    assert np.allclose(losses, ref_losses, rtol=2e-4, atol=2e-3), (losses, ref_losses)
+    # Adam's first steps move every element by ~lr*sign(g): elements with |g| ~ 0 may flip. Require 99.5 % agreement.
+    tot = bad = 0
+    for k, p in m.named_parameters():
+        d = (p.detach().double() - sd[k].detach()).abs()
+        tot += d.numel()
+        bad += int((d > 2e-4).sum())
+    assert bad <= 0.005 * tot, (bad, tot)

@@ -1,0 +1,444 @@
+// Fused TCN block (Conv1DBlock / Conv1DBlock4Fuse, wesep/modules/tasnet/convs.py:43-160):
+// HBM-bound depthwise-dilated stencil kernels + gLN bookkeeping, and the block-level C entry
+// points that chain them with the tensor-core 1x1-conv GEMMs (gemm_mma.cuh).
+// Math: SURVEY.md Appendix E.1.
+#include "gemm_mma.cuh"
+
+namespace wb {
+
+constexpr int ST_CH = 4;        // channel rows per CTA
+constexpr int ST_TT = 2048;     // time steps per CTA (forward)
+constexpr int ST_TTB = 1024;    // time steps per CTA (backward)
+constexpr int ST_THREADS = 256; // 64 threads per channel row
+constexpr float GLN_EPS = 1e-5f;
+
+// ------------------------------------------------------------------------------------ K3 forward
+// d[c][t] = sum_j wd[c][j] * z1[c][t + (j-1) dil] + bd[c],  z1 = g1*(prelu(u,a1)-mu1)*r1 + be1 inside
+// [0,T), zero outside (conv zero padding, convs.py:64-74).  Accumulates gLN2 stats of prelu(d,a2).
+struct StFwdP {
+  int n, H, T, dil; int64_t ld;
+  const float* u; float* d;
+  const float* a1; const float* g1; const float* be1;
+  const float* wd; const float* bd; const float* a2;
+  const double* stats1; double* stats2; double count;
+};
+
+__global__ void __launch_bounds__(ST_THREADS) tcn_dw_fwd_kernel(const StFwdP p) {
+  extern __shared__ float z[];  // [ST_CH][ST_TT + 2*dil]
+  __shared__ float red[2 * 32];
+  const int tid = threadIdx.x, sub = tid & 63, chl = tid >> 6;
+  const int t0 = blockIdx.x * ST_TT, c = blockIdx.y * ST_CH + chl, n = blockIdx.z;
+  const int dil = p.dil, W = ST_TT + 2 * dil;
+  float s = 0.f, q = 0.f;
+  if (c < p.H) {
+    float mu, r;
+    gln_mean_rstd(p.stats1 + 2 * n, p.count, GLN_EPS, mu, r);
+    const float a1 = __ldg(p.a1), gm = __ldg(p.g1 + c), bt = __ldg(p.be1 + c);
+    const float sc = gm * r, sh = bt - gm * mu * r;
+    const float* urow = p.u + ((int64_t)n * p.H + c) * p.ld;
+    float* zr = z + chl * W;
+    for (int i = sub; i < W; i += 64) {
+      int t = t0 - dil + i;
+      float v = 0.f;
+      if (t >= 0 && t < p.T) v = fmaf(sc, prelu_f(__ldg(urow + t), a1), sh);
+      zr[i] = v;
+    }
+  }
+  __syncthreads();
+  if (c < p.H) {
+    const float w0 = __ldg(p.wd + 3 * c), w1 = __ldg(p.wd + 3 * c + 1), w2 = __ldg(p.wd + 3 * c + 2);
+    const float bd = __ldg(p.bd + c), a2 = __ldg(p.a2);
+    const float* zr = z + chl * W + dil;
+    float* drow = p.d + ((int64_t)n * p.H + c) * p.ld;
+#pragma unroll 4
+    for (int i = sub; i < ST_TT; i += 64) {
+      int t = t0 + i;
+      if (t < p.T) {
+        float dv = fmaf(w0, zr[i - dil], fmaf(w1, zr[i], fmaf(w2, zr[i + dil], bd)));
+        drow[t] = dv;
+        float y = prelu_f(dv, a2);
+        s += y;
+        q += y * y;
+      }
+    }
+  }
+  float v[2] = {s, q};
+  block_sum<2>(v, red);
+  if (tid == 0) {
+    atomicAdd(p.stats2 + 2 * n, (double)v[0]);
+    atomicAdd(p.stats2 + 2 * n + 1, (double)v[1]);
+  }
+}
+
+// ------------------------------------------------------------------------------------ B3 backward
+// inputs dd = dL/d(d), u;  outputs du = dL/du and parameter-gradient partial sums.
+struct StBwdP {
+  int n, H, T, dil; int64_t ld;
+  const float* u; const float* dd; float* du;
+  const float* a1; const float* g1; const float* be1; const float* wd;
+  const double* stats1; double count;
+  const double* rowacc;          // [n][8]: [2]=P1 [3]=P2 [4]=P3
+  float* dg1; float* dbe1; float* dwd; float* dbd; float* da1;  // += [H],[H],[H][3],[H],[1]
+  float* sdu;                    // += [n][H] sum_t du
+};
+
+__global__ void __launch_bounds__(ST_THREADS) tcn_dw_bwd_kernel(const StBwdP p) {
+  extern __shared__ float sm[];  // dds[CH][W], z1s[CH][W], us[CH][TT]
+  __shared__ float red[32];
+  __shared__ float chred[ST_CH][2][8];
+  const int tid = threadIdx.x, sub = tid & 63, chl = tid >> 6, lane = tid & 31;
+  const int t0 = blockIdx.x * ST_TTB, c = blockIdx.y * ST_CH + chl, n = blockIdx.z;
+  const int dil = p.dil, W = ST_TTB + 2 * dil;
+  float* dds = sm + chl * W;
+  float* z1s = sm + ST_CH * W + chl * W;
+  float* us = sm + 2 * ST_CH * W + chl * ST_TTB;
+  float mu = 0.f, r = 1.f, a1 = 1.f, gm = 0.f;
+  if (c < p.H) {
+    gln_mean_rstd(p.stats1 + 2 * n, p.count, GLN_EPS, mu, r);
+    a1 = __ldg(p.a1);
+    gm = __ldg(p.g1 + c);
+    const float bt = __ldg(p.be1 + c);
+    const float sc = gm * r, sh = bt - gm * mu * r;
+    const float* urow = p.u + ((int64_t)n * p.H + c) * p.ld;
+    const float* drow = p.dd + ((int64_t)n * p.H + c) * p.ld;
+    for (int i = sub; i < W; i += 64) {
+      int t = t0 - dil + i;
+      float dv = 0.f, zv = 0.f;
+      if (t >= 0 && t < p.T) {
+        dv = __ldg(drow + t);
+        float uv = __ldg(urow + t);
+        zv = fmaf(sc, prelu_f(uv, a1), sh);
+        int j = i - dil;
+        if (j >= 0 && j < ST_TTB) us[j] = uv;
+      }
+      dds[i] = dv;
+      z1s[i] = zv;
+    }
+  }
+  __syncthreads();
+  float acc[8];  // 0 sdz(dbe1) 1 sdzy(dg1) 2..4 dw0..2 5 sdd(dbd) 6 sdu 7 unused
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  float dal = 0.f;
+  if (c < p.H) {
+    const double Mc = p.count;
+    const float m1 = (float)(p.rowacc[8 * n + 2] / Mc);
+    const float m2 = (float)((p.rowacc[8 * n + 3] - p.rowacc[8 * n + 4]) / Mc);
+    const float w0 = __ldg(p.wd + 3 * c), w1 = __ldg(p.wd + 3 * c + 1), w2 = __ldg(p.wd + 3 * c + 2);
+    float* durow = p.du + ((int64_t)n * p.H + c) * p.ld;
+    const float* dc = dds + dil;
+    const float* zc = z1s + dil;
+#pragma unroll 2
+    for (int i = sub; i < ST_TTB; i += 64) {
+      int t = t0 + i;
+      if (t < p.T) {
+        const float ddv = dc[i];
+        // dz1[t] = sum_j w[j] * dd[t - (j-1) dil]
+        const float dz = fmaf(w0, dc[i + dil], fmaf(w1, ddv, w2 * dc[i - dil]));
+        const float uv = us[i];
+        const float yh = (prelu_f(uv, a1) - mu) * r;
+        const float dy = r * (gm * dz - m1 - yh * m2);
+        const float duv = dy * (uv > 0.f ? 1.f : a1);
+        durow[t] = duv;
+        acc[0] += dz;
+        acc[1] += dz * yh;
+        acc[2] += ddv * zc[i - dil];
+        acc[3] += ddv * zc[i];
+        acc[4] += ddv * zc[i + dil];
+        acc[5] += ddv;
+        acc[6] += duv;
+        dal += uv > 0.f ? 0.f : dy * uv;
+      }
+    }
+  }
+  // per-channel reduction: the 64 threads (2 warps) of a channel row
+#pragma unroll
+  for (int i = 0; i < 7; ++i) acc[i] = warp_sum(acc[i]);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 7; ++i) chred[chl][(tid >> 5) & 1][i] = acc[i];
+  }
+  float v[1] = {dal};
+  block_sum<1>(v, red);  // contains __syncthreads (also publishes chred)
+  if (tid == 0 && v[0] != 0.f) atomicAdd(p.da1, v[0]);
+  if (sub == 0 && c < p.H) {
+    float r7[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) r7[i] = chred[chl][0][i] + chred[chl][1][i];
+    atomicAdd(p.dbe1 + c, r7[0]);
+    atomicAdd(p.dg1 + c, r7[1]);
+    atomicAdd(p.dwd + 3 * c + 0, r7[2]);
+    atomicAdd(p.dwd + 3 * c + 1, r7[3]);
+    atomicAdd(p.dwd + 3 * c + 2, r7[4]);
+    atomicAdd(p.dbd + c, r7[5]);
+    atomicAdd(p.sdu + (int64_t)n * p.H + c, r7[6]);
+  }
+}
+
+// ------------------------------------------------------------------------------------ small kernels
+// out[n][c] = sum_t x[n][c][t]; one warp per row.
+__global__ void rowsum_kernel(const float* x, int64_t ld, int rows, int T, float* out) {
+  int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= rows) return;
+  const float* r = x + (int64_t)w * ld;
+  float s = 0.f;
+  int T4 = T & ~3;
+  for (int t = lane * 4; t < T4; t += 128) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(r + t));
+    s += (v.x + v.y) + (v.z + v.w);
+  }
+  for (int t = T4 + lane; t < T; t += 32) s += __ldg(r + t);
+  s = warp_sum(s);
+  if (lane == 0) out[w] = s;
+}
+
+// gLN2 backward, step 1 (per row): means of h and h*yhat2 from Gn = sum_t g y2^T and sg = sum_t g.
+struct F2P {
+  int n, B, H; double count;  // count = H*T
+  const float* Gn; const float* sg; const float* W3; int64_t ldw3;
+  const float* g2; const float* be2; const double* stats2;
+  double* rowsc;  // [n][8]: out [0]=mean(h) [1]=mean(h yhat2) [6]=mu2 [7]=r2
+  float* dW3; float* dg2; float* dbe2; float* db3;
+};
+__global__ void __launch_bounds__(256) tcn_f2a_kernel(const F2P p) {
+  __shared__ float red[2 * 32];
+  const int n = blockIdx.x, tid = threadIdx.x;
+  float mu, r;
+  gln_mean_rstd(p.stats2 + 2 * n, p.count, GLN_EPS, mu, r);
+  const float* G = p.Gn + (int64_t)n * p.B * p.H;
+  const float* sg = p.sg + (int64_t)n * p.B;
+  float s1 = 0.f, s2 = 0.f;
+  for (int c = tid; c < p.H; c += 256) {
+    const float gm = __ldg(p.g2 + c);
+    float a = 0.f, b = 0.f;
+    for (int o = 0; o < p.B; ++o) {
+      const float w = __ldg(p.W3 + (int64_t)o * p.ldw3 + c);
+      const float sgo = sg[o];
+      a = fmaf(w, sgo, a);
+      b = fmaf(w, r * (G[(int64_t)o * p.H + c] - mu * sgo), b);
+    }
+    s1 = fmaf(gm, a, s1);
+    s2 = fmaf(gm, b, s2);
+  }
+  float v[2] = {s1, s2};
+  block_sum<2>(v, red);
+  if (tid == 0) {
+    p.rowsc[8 * n + 0] = (double)v[0] / p.count;
+    p.rowsc[8 * n + 1] = (double)v[1] / p.count;
+    p.rowsc[8 * n + 6] = (double)mu;
+    p.rowsc[8 * n + 7] = (double)r;
+  }
+}
+// step 2 (per weight element): dW3, dgamma2, dbeta2, db3. grid (H/128, B/8), block 128: thread <-> c.
+__global__ void __launch_bounds__(128) tcn_f2b_kernel(const F2P p) {
+  const int c = blockIdx.x * 128 + threadIdx.x;
+  const int o0 = blockIdx.y * 8;
+  if (c >= p.H) return;
+  const float gm = __ldg(p.g2 + c), bt = __ldg(p.be2 + c);
+  float dg = 0.f, db = 0.f;
+  for (int o = o0; o < min(o0 + 8, p.B); ++o) {
+    float a1 = 0.f, a2 = 0.f;
+    for (int n = 0; n < p.n; ++n) {
+      const float mu = (float)p.rowsc[8 * n + 6], r = (float)p.rowsc[8 * n + 7];
+      const float sgo = __ldg(p.sg + (int64_t)n * p.B + o);
+      a1 += r * (__ldg(p.Gn + ((int64_t)n * p.B + o) * p.H + c) - mu * sgo);
+      a2 += sgo;
+    }
+    const float w = __ldg(p.W3 + (int64_t)o * p.ldw3 + c);
+    atomicAdd(p.dW3 + (int64_t)o * p.ldw3 + c, gm * a1 + bt * a2);   // sole writer of this element in this call
+    dg = fmaf(w, a1, dg);
+    db = fmaf(w, a2, db);
+    if (c == 0) atomicAdd(p.db3 + o, a2);
+  }
+  atomicAdd(p.dg2 + c, dg);
+  atomicAdd(p.dbe2 + c, db);
+}
+
+// speaker fold of the fuse block: row_bias[n][h] = sum_e W1[h][B+e] aux[n][e]; one warp per (n,h)
+__global__ void fuse_rowbias_kernel(const float* W1, int64_t ldw1, int B, int E, int H, int n, const float* aux,
+                                    float* row_bias) {
+  int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= n * H) return;
+  int r = w / H, h = w % H;
+  const float* wr = W1 + (int64_t)h * ldw1 + B;
+  const float* a = aux + (int64_t)r * E;
+  float s = 0.f;
+  for (int e = lane; e < E; e += 32) s = fmaf(__ldg(wr + e), __ldg(a + e), s);
+  s = warp_sum(s);
+  if (lane == 0) row_bias[w] = s;
+}
+
+// tail of the backward: db1, da2 and (fuse block) daux, dW1[:, B:]
+struct TailP {
+  int n, B, H, E; int64_t ldw1;
+  const float* sdu; const double* rowacc; const float* W1; const float* aux;
+  float* db1; float* da2; float* daux; float* dW1;
+};
+__global__ void tcn_bwd_tail_kernel(const TailP p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < p.H) {
+    float s = 0.f;
+    for (int n = 0; n < p.n; ++n) s += p.sdu[(int64_t)n * p.H + i];
+    atomicAdd(p.db1 + i, s);
+  }
+  if (i == 0) {
+    double s = 0.0;
+    for (int n = 0; n < p.n; ++n) s += p.rowacc[8 * n + 5];
+    atomicAdd(p.da2, (float)s);
+  }
+  if (p.E > 0) {
+    if (i < p.n * p.E) {  // daux[n][e] = sum_h W1[h][B+e] sdu[n][h]
+      int n = i / p.E, e = i % p.E;
+      float s = 0.f;
+      for (int h = 0; h < p.H; ++h) s = fmaf(__ldg(p.W1 + (int64_t)h * p.ldw1 + p.B + e), p.sdu[(int64_t)n * p.H + h], s);
+      p.daux[i] = s;
+    }
+    if (i < p.H * p.E) {  // dW1[h][B+e] += sum_n sdu[n][h] aux[n][e]
+      int h = i / p.E, e = i % p.E;
+      float s = 0.f;
+      for (int n = 0; n < p.n; ++n) s = fmaf(p.sdu[(int64_t)n * p.H + h], __ldg(p.aux + (int64_t)n * p.E + e), s);
+      atomicAdd(p.dW1 + (int64_t)h * p.ldw1 + p.B + e, s);
+    }
+  }
+}
+
+static int check_tcn(const WesepTcnFwdArgs& a) {
+  if (a.n <= 0 || a.B <= 0 || a.H <= 0 || a.T <= 0 || a.dil <= 0) return fail(-1, "tcn: empty shape");
+  if ((a.ld & 3) || a.ld < a.T) return fail(-1, "tcn: ld must be a multiple of 4 and >= T");
+  if ((a.B & 3) || (a.H & 3)) return fail(-1, "tcn: B and H must be multiples of 4");
+  if (a.dil > 4096) return fail(-2, "tcn: dilation too large");
+  if ((a.E > 0) != (a.aux != nullptr)) return fail(-1, "tcn: aux and E must be given together");
+  if (a.ldw1 < a.B + a.E || (a.ldw1 & 3) || (a.ldw3 & 3)) return fail(-1, "tcn: weight strides");
+  return 0;
+}
+
+}  // namespace wb
+
+using namespace wb;
+
+extern "C" int wesep_b200_tcn_block_fwd(const WesepTcnFwdArgs* ap, void* stream) {
+  const WesepTcnFwdArgs& a = *ap;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = check_tcn(a)) return rc;
+  const double count = (double)a.H * (double)a.T;
+  WB_CUDA(cudaMemsetAsync(a.stats1, 0, sizeof(double) * 2 * a.n, st));
+  WB_CUDA(cudaMemsetAsync(a.stats2, 0, sizeof(double) * 2 * a.n, st));
+  if (a.aux) {
+    int warps = a.n * a.H;
+    fuse_rowbias_kernel<<<cdiv((int64_t)warps * 32, 256), 256, 0, st>>>(a.W1, a.ldw1, a.B, a.E, a.H, a.n, a.aux, a.row_bias);
+    WB_LAUNCH_CHECK("fuse_rowbias");
+  }
+  {  // K2: u = W1 x + b1 (+ row bias); gLN1 statistics of prelu(u)
+    GemmWxP p{};
+    p.n = a.n; p.M = a.H; p.Kd = a.B; p.T = a.T;
+    p.W = a.W1; p.ldw = a.ldw1; p.X = a.x; p.ldx = a.ld; p.bsx = (int64_t)a.B * a.ld;
+    p.ep.Y = a.u; p.ep.ldy = a.ld; p.ep.bsy = (int64_t)a.H * a.ld;
+    p.ep.bias = a.b1; p.ep.row_bias = a.aux ? a.row_bias : nullptr;
+    p.ep.out_stats = a.stats1; p.ep.out_alpha = a.a1;
+    if (int rc = launch_gemm_wx(p, false, 0, 0, st)) return rc;
+  }
+  {  // K3: depthwise dilated conv on gLN1(prelu(u)); gLN2 statistics
+    StFwdP p{a.n, a.H, a.T, a.dil, a.ld, a.u, a.d, a.a1, a.g1, a.be1, a.wd, a.bd, a.a2, a.stats1, a.stats2, count};
+    dim3 grid(cdiv(a.T, ST_TT), cdiv(a.H, ST_CH), a.n);
+    size_t smem = (size_t)ST_CH * (ST_TT + 2 * a.dil) * sizeof(float);
+    WB_CUDA(cudaFuncSetAttribute(tcn_dw_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tcn_dw_fwd_kernel<<<grid, ST_THREADS, smem, st>>>(p);
+    WB_LAUNCH_CHECK("tcn_dw_fwd");
+  }
+  {  // K4: out = x + W3 gLN2(prelu(d)) + b3
+    GemmWxP p{};
+    p.n = a.n; p.M = a.B; p.Kd = a.H; p.T = a.T;
+    p.W = a.W3; p.ldw = a.ldw3; p.X = a.d; p.ldx = a.ld; p.bsx = (int64_t)a.H * a.ld;
+    p.xf = XformP{a.a2, a.g2, a.be2, a.stats2, count, GLN_EPS};
+    p.ep.Y = a.out; p.ep.ldy = a.ld; p.ep.bsy = (int64_t)a.B * a.ld;
+    p.ep.bias = a.b3;
+    p.ep.R = a.x; p.ep.ldr = a.ld; p.ep.bsr = (int64_t)a.B * a.ld;
+    if (int rc = launch_gemm_wx(p, false, 2, 2, st)) return rc;
+  }
+  return 0;
+}
+
+extern "C" int wesep_b200_tcn_block_bwd(const WesepTcnBwdArgs* bp, void* stream) {
+  const WesepTcnBwdArgs& b = *bp;
+  const WesepTcnFwdArgs& a = b.f;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = check_tcn(a)) return rc;
+  const double count = (double)a.H * (double)a.T;
+  WB_CUDA(cudaMemsetAsync(b.Gn, 0, sizeof(float) * (size_t)a.n * a.B * a.H, st));
+  WB_CUDA(cudaMemsetAsync(b.sdu, 0, sizeof(float) * (size_t)a.n * a.H, st));
+  WB_CUDA(cudaMemsetAsync(b.rowsc, 0, sizeof(double) * 8 * a.n, st));
+  {  // sg[n][o] = sum_t g
+    int rows = a.n * a.B;
+    rowsum_kernel<<<cdiv((int64_t)rows * 32, 256), 256, 0, st>>>(b.gout, a.ld, rows, a.T, b.sg);
+    WB_LAUNCH_CHECK("rowsum");
+  }
+  {  // Gn[n][o][c] = sum_t g[o][t] * prelu(d[c][t], a2)
+    GemmDwP p{};
+    p.n = a.n; p.M = a.B; p.N = a.H; p.T = a.T;
+    p.A = b.gout; p.lda = a.ld; p.bsa = (int64_t)a.B * a.ld;
+    p.B = a.d; p.ldb = a.ld; p.bsb = (int64_t)a.H * a.ld;
+    p.C = b.Gn; p.ldc = a.H; p.per_row = 1;
+    p.xb = XformP{a.a2, nullptr, nullptr, nullptr, 1.0, 0.f};
+    if (int rc = launch_gemm_dw(p, 1, st)) return rc;
+  }
+  {
+    F2P p{a.n, a.B, a.H, count, b.Gn, b.sg, a.W3, a.ldw3, a.g2, a.be2, a.stats2, b.rowsc, b.dW3, b.dg2, b.dbe2, b.db3};
+    tcn_f2a_kernel<<<a.n, 256, 0, st>>>(p);
+    WB_LAUNCH_CHECK("tcn_f2a");
+    tcn_f2b_kernel<<<dim3(cdiv(a.H, 128), cdiv(a.B, 8)), 128, 0, st>>>(p);
+    WB_LAUNCH_CHECK("tcn_f2b");
+  }
+  {  // B2: dd = dL/d(d) from h = g2 * (W3^T g), gLN2 + PReLU_2 backward fused in the epilogue
+    GemmWxP p{};
+    p.n = a.n; p.M = a.H; p.Kd = a.B; p.T = a.T;
+    p.W = a.W3; p.ldw = a.ldw3; p.X = b.gout; p.ldx = a.ld; p.bsx = (int64_t)a.B * a.ld;
+    EpiP& e = p.ep;
+    e.Y = b.dd; e.ldy = a.ld; e.bsy = (int64_t)a.H * a.ld;
+    e.d = a.d; e.ldd = a.ld; e.bsd = (int64_t)a.H * a.ld;
+    e.a2 = a.a2; e.g2 = a.g2; e.stats2 = a.stats2; e.count2 = count; e.eps2 = GLN_EPS;
+    e.rowsc = b.rowsc; e.rowacc = b.rowsc;
+    e.g1 = a.g1; e.be1 = a.be1; e.bd = a.bd; e.wd = a.wd; e.dil = a.dil;
+    if (int rc = launch_gemm_wx(p, true, 0, 10, st)) return rc;
+  }
+  {  // B3: depthwise conv + gLN1 + PReLU_1 backward
+    StBwdP p{a.n, a.H, a.T, a.dil, a.ld, a.u, b.dd, b.du, a.a1, a.g1, a.be1, a.wd, a.stats1, count, b.rowsc,
+             b.dg1, b.dbe1, b.dwd, b.dbd, b.da1, b.sdu};
+    dim3 grid(cdiv(a.T, ST_TTB), cdiv(a.H, ST_CH), a.n);
+    size_t smem = (size_t)ST_CH * (2 * (ST_TTB + 2 * a.dil) + ST_TTB) * sizeof(float);
+    WB_CUDA(cudaFuncSetAttribute(tcn_dw_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tcn_dw_bwd_kernel<<<grid, ST_THREADS, smem, st>>>(p);
+    WB_LAUNCH_CHECK("tcn_dw_bwd");
+  }
+  {  // B4: dx = g + W1[:, :B]^T du
+    GemmWxP p{};
+    p.n = a.n; p.M = a.B; p.Kd = a.H; p.T = a.T;
+    p.W = a.W1; p.ldw = a.ldw1; p.X = b.du; p.ldx = a.ld; p.bsx = (int64_t)a.H * a.ld;
+    p.ep.Y = b.dx; p.ep.ldy = a.ld; p.ep.bsy = (int64_t)a.B * a.ld;
+    p.ep.R = b.gout; p.ep.ldr = a.ld; p.ep.bsr = (int64_t)a.B * a.ld;
+    if (int rc = launch_gemm_wx(p, true, 0, 2, st)) return rc;
+  }
+  {  // dW1[:, :B] += sum_n sum_t du x^T
+    GemmDwP p{};
+    p.n = a.n; p.M = a.H; p.N = a.B; p.T = a.T;
+    p.A = b.du; p.lda = a.ld; p.bsa = (int64_t)a.H * a.ld;
+    p.B = a.x; p.ldb = a.ld; p.bsb = (int64_t)a.B * a.ld;
+    p.C = b.dW1; p.ldc = a.ldw1; p.per_row = 0;
+    if (int rc = launch_gemm_dw(p, 0, st)) return rc;
+  }
+  {
+    TailP p{a.n, a.B, a.H, a.E, a.ldw1, b.sdu, b.rowsc, a.W1, a.aux, b.db1, b.da2, b.daux, b.dW1};
+    int work = a.H;
+    if (a.E > 0) work = max(work, max(a.n * a.E, a.H * a.E));
+    tcn_bwd_tail_kernel<<<cdiv(work, 256), 256, 0, st>>>(p);
+    WB_LAUNCH_CHECK("tcn_bwd_tail");
+  }
+  return 0;
+}
+
+extern "C" int wesep_b200_rowsum(const WesepRowSumArgs* a, void* stream) {
+  if ((a->ld & 3) || !aligned16(a->x)) return fail(-1, "rowsum: alignment");
+  int rows = a->n * a->C;
+  rowsum_kernel<<<cdiv((int64_t)rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(a->x, a->ld, rows, a->T, a->out);
+  WB_LAUNCH_CHECK("rowsum");
+  return 0;
+}

@@ -1,0 +1,64 @@
+"""Data-parallel plumbing: one process per GPU, ONE collective on the data path — the gradient
+all-reduce (reference: torch DDP at wesep/bin/train.py:227-228).  The flat gradient arena is reduced
+in place with NCCL over NVLink/NVSwitch (SUM); the 1/world_size average is folded into the fused
+clip+Adam kernel (`grad_scale`).  Works with the gloo backend on CPU tensors for the host-logic tests."""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend=None):
+    """torchrun-style rendezvous (RANK / WORLD_SIZE / LOCAL_RANK / MASTER_*). Returns (rank, world, local_rank)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+        dist.init_process_group(backend=backend)
+    return rank, world, local
+
+
+def shard_rows(n_total, rank, world):
+    """Utterance sharding: rank r owns rows [lo, hi) (reference partitions shard files data[rank::world],
+    wesep/dataset/dataset.py:98-102; the synthetic bench uses contiguous blocks)."""
+    base, rem = divmod(n_total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class GradAllReducer:
+    """All-reduce(SUM) of a flat gradient buffer, in `n_buckets` contiguous pieces (reverse order, like
+    DDP's reverse-registration buckets) so later rounds can overlap them with the backward pass."""
+
+    def __init__(self, flat_grad, group=None, n_buckets=1):
+        self.flat = flat_grad
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        n = flat_grad.numel()
+        step = (n + n_buckets - 1) // n_buckets
+        step = (step + 3) // 4 * 4
+        self.bounds = [(lo, min(lo + step, n)) for lo in range(0, n, step)]
+
+    def all_reduce(self, async_op=False):
+        if self.world == 1:
+            return []
+        works = []
+        for lo, hi in reversed(self.bounds):
+            w = dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=async_op)
+            if async_op:
+                works.append(w)
+        return works
+
+    @property
+    def grad_scale(self):
+        return 1.0 / self.world
+
+
+def broadcast_params(flat_param, src=0, group=None):
+    """DDP constructor semantics (train.py:227): every rank starts from rank 0's parameters."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.broadcast(flat_param, src=src, group=group)

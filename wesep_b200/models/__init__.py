@@ -1,0 +1,12 @@
+"""Model registry — reference wesep/models/__init__.py:10-27 (prefix dispatch by name)."""
+import wesep_b200.models.convtasnet as convtasnet
+
+
+def get_model(model_name: str):
+    if model_name.startswith("ConvTasNet"):
+        return getattr(convtasnet, model_name)
+    for prefix in ("BSRNN_Multi", "BSRNN_Feats", "BSRNN", "DPCCN", "TFGridNet", "CMGAN"):
+        if model_name.startswith(prefix):
+            raise NotImplementedError(model_name + " is not built yet in wesep_b200 (Spex+/ConvTasNet only so far)")
+    print(model_name + " not found !!!")
+    exit(1)

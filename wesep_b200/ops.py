@@ -1,0 +1,494 @@
+"""torch.autograd.Function wrappers over the C-ABI kernels (include/wesep_b200.h).
+
+PyTorch here is plumbing only: device memory (caching allocator), streams and the autograd
+tape.  All arithmetic on the hot path runs in libwesep_b200.so; there is no fallback.
+
+Activation layout ("act"): fp32 ``[n, C, T]`` views of ``[n, C, ld]`` storage with the time
+axis contiguous and ``ld = ceil4(T)`` so every row starts 16-byte aligned (6399 frames -> 6400).
+"""
+import torch
+
+from . import _lib
+from ._lib import STRUCTS
+
+
+# --------------------------------------------------------------------------- helpers
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _args(name, **kw):
+    s = STRUCTS[name]()
+    for k, v in kw.items():
+        if isinstance(v, torch.Tensor):
+            v = v.data_ptr()
+        elif v is None:
+            v = 0
+        setattr(s, k, v)
+    return s
+
+
+def _check_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("wesep_b200 kernels need CUDA tensors (no CPU fallback)")
+
+
+def ceil4(T):
+    return (T + 3) // 4 * 4
+
+
+def new_act(n, C, T, device, zero=False):
+    ld = ceil4(T)
+    buf = (torch.zeros if zero else torch.empty)((n, C, ld), dtype=torch.float32, device=device)
+    return buf[:, :, :T] if ld != T else buf
+
+
+def is_act(x):
+    return (x.dim() == 3 and x.dtype == torch.float32 and x.is_cuda and x.stride(2) == 1
+            and x.stride(1) == ceil4(x.shape[2]) and x.stride(0) == x.shape[1] * x.stride(1) and x.data_ptr() % 16 == 0)
+
+
+def is_act_slice(x):
+    """act layout, or a channel slice of one (batch stride larger than C*ld)."""
+    return (x.dim() == 3 and x.dtype == torch.float32 and x.is_cuda and x.stride(2) == 1
+            and x.stride(1) == ceil4(x.shape[2]) and x.stride(0) % 4 == 0 and x.stride(0) >= x.shape[1] * x.stride(1)
+            and x.data_ptr() % 16 == 0)
+
+
+def as_act(x):
+    """Return x in act layout (copy only if its strides do not qualify)."""
+    _check_cuda(x)
+    if x.dim() != 3:
+        raise RuntimeError("expected a 3-D [n, C, T] tensor")
+    if is_act(x):
+        return x
+    y = new_act(x.shape[0], x.shape[1], x.shape[2], x.device)
+    y.copy_(x)
+    return y
+
+
+def _w2d(w):
+    """conv weight (O, I, 1) / linear weight (O, I) -> contiguous 2-D view."""
+    w2 = w.reshape(w.shape[0], -1)
+    return w2 if w2.is_contiguous() else w2.contiguous()
+
+
+def _vec(p):
+    v = p.reshape(-1)
+    return v if v.is_contiguous() else v.contiguous()
+
+
+def _sig(x):
+    """[n, L] signal with contiguous samples -> (tensor, ld)."""
+    if x.dim() != 2 or x.dtype != torch.float32:
+        raise RuntimeError("expected a float32 [n, L] signal")
+    if x.stride(1) != 1:
+        x = x.contiguous()
+    return x, x.stride(0)
+
+
+# --------------------------------------------------------------------------- raw calls
+def conv1x1_raw(x, W2d, w_trans, M, *, bias=None, row_bias=None, pro=0, alpha=None, ch_scale=None, ch_shift=None,
+                row_stats=None, stat_count=1.0, stat_eps=0.0, epi=0, R=None, Y=None, Y2=None, out_stats=None,
+                out_alpha=None, ch_stats=None):
+    n, Kd, T = x.shape
+    if Y is None:
+        Y = new_act(n, M, T, x.device)
+    a = _args("WesepGemmArgs", n=n, M=M, Kd=Kd, T=T, W=W2d, ldw=W2d.stride(0), w_trans=int(w_trans), X=x, ldx=x.stride(1),
+              Y=Y, ldy=Y.stride(1), bias=bias, row_bias=row_bias, pro=pro, alpha=alpha, ch_scale=ch_scale,
+              ch_shift=ch_shift, row_stats=row_stats, stat_count=float(stat_count), stat_eps=float(stat_eps), epi=epi,
+              R=R, ldr=0 if R is None else R.stride(1), Y2=Y2, ldy2=0 if Y2 is None else Y2.stride(1),
+              out_stats=out_stats, out_alpha=out_alpha, ch_stats=ch_stats, bsx=x.stride(0), bsy=Y.stride(0),
+              bsr=0 if R is None else R.stride(0), bsy2=0 if Y2 is None else Y2.stride(0))
+    for t_ in (x, Y, R, Y2):
+        if t_ is not None and not is_act_slice(t_):
+            raise RuntimeError("conv1x1: operand is not in act layout")
+    _lib.call("wesep_b200_conv1x1", a, _stream())
+    return Y
+
+
+def conv1x1_dw_raw(A, B, C, *, per_row=False, pro_b=0, alpha_b=None, ch_scale_b=None, ch_shift_b=None,
+                   row_stats_b=None, stat_count=1.0, stat_eps=0.0):
+    """C[M][N] += sum_n sum_t A[n][M][t] * f(B[n][N][t])  (C dense, zero-initialised by the caller)."""
+    n, M, T = A.shape
+    N = B.shape[1]
+    a = _args("WesepGemmDwArgs", n=n, M=M, N=N, T=T, A=A, lda=A.stride(1), B=B, ldb=B.stride(1), C=C, per_row=int(per_row),
+              pro_b=pro_b, alpha_b=alpha_b, ch_scale_b=ch_scale_b, ch_shift_b=ch_shift_b, row_stats_b=row_stats_b,
+              stat_count=float(stat_count), stat_eps=float(stat_eps), bsa=A.stride(0), bsb=B.stride(0),
+              ldc=C.stride(0) if C.dim() == 2 else C.stride(1))
+    if not (is_act_slice(A) and is_act_slice(B)) or C.stride(-1) != 1:
+        raise RuntimeError("conv1x1_dw: operand layout")
+    _lib.call("wesep_b200_conv1x1_dw", a, _stream())
+    return C
+
+
+def rowsum_raw(x):
+    n, C, T = x.shape
+    out = torch.empty((n, C), dtype=torch.float32, device=x.device)
+    _lib.call("wesep_b200_rowsum", _args("WesepRowSumArgs", n=n, C=C, T=T, ld=x.stride(1), x=x, out=out), _stream())
+    return out
+
+
+def frames_raw(sig, J, K, hop):
+    sig, ldx = _sig(sig)
+    n, S = sig.shape
+    F = new_act(n, J, K, sig.device)
+    _lib.call("wesep_b200_frames", _args("WesepFrameArgs", n=n, J=J, K=K, hop=hop, S=S, x=sig, ldx=ldx, F=F,
+                                         ldf=F.stride(1)), _stream())
+    return F
+
+
+# --------------------------------------------------------------------------- fused TCN block
+class TCNBlockFn(torch.autograd.Function):
+    """Conv1DBlock / Conv1DBlock4Fuse (wesep/modules/tasnet/convs.py:43-160) as one fused op."""
+
+    @staticmethod
+    def forward(ctx, x, aux, W1, b1, a1, g1, be1, wd, bd, a2, g2, be2, W3, b3, dil):
+        x = as_act(x)
+        n, B, T = x.shape
+        W1c, W3c = _w2d(W1), _w2d(W3)
+        H = W1c.shape[0]
+        E = 0
+        auxc = None
+        if aux is not None:
+            auxc = aux.reshape(n, -1).contiguous()
+            E = auxc.shape[1]
+        if W1c.shape[1] != B + E or W3c.shape != (B, H):
+            raise RuntimeError("TCN block: weight shapes do not match the input")
+        dev = x.device
+        u = new_act(n, H, T, dev)
+        d = new_act(n, H, T, dev)
+        out = new_act(n, B, T, dev)
+        stats = torch.empty((2, n, 2), dtype=torch.float64, device=dev)
+        row_bias = torch.empty((n, H), dtype=torch.float32, device=dev) if E else None
+        P = dict(b1=_vec(b1), a1=_vec(a1), g1=_vec(g1), be1=_vec(be1), wd=_vec(wd), bd=_vec(bd), a2=_vec(a2),
+                 g2=_vec(g2), be2=_vec(be2), b3=_vec(b3))
+        fa = _args("WesepTcnFwdArgs", n=n, B=B, H=H, T=T, dil=int(dil), E=E, ld=x.stride(1), x=x, aux=auxc, W1=W1c,
+                   ldw1=W1c.stride(0), W3=W3c, ldw3=W3c.stride(0), u=u, d=d, out=out, stats1=stats[0], stats2=stats[1],
+                   row_bias=row_bias, **P)
+        if u.stride(1) != x.stride(1):
+            raise RuntimeError("TCN block: inconsistent row strides")
+        _lib.call("wesep_b200_tcn_block_fwd", fa, _stream())
+        ctx.dil = int(dil)
+        ctx.has_aux = aux is not None
+        ctx.shapes = (W1.shape, W3.shape, None if aux is None else aux.shape)
+        ctx.save_for_backward(x, auxc, W1c, W3c, u, d, stats, *[P[k] for k in ("b1", "a1", "g1", "be1", "wd", "bd", "a2",
+                                                                            "g2", "be2", "b3")])
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, auxc, W1c, W3c, u, d, stats, b1, a1, g1, be1, wd, bd, a2, g2, be2, b3 = ctx.saved_tensors
+        n, B, T = x.shape
+        H = W1c.shape[0]
+        E = 0 if auxc is None else auxc.shape[1]
+        dev = x.device
+        gout = as_act(gout)
+        if gout.stride(1) != x.stride(1):
+            g2_ = new_act(n, B, T, dev)
+            g2_.copy_(gout)
+            gout = g2_
+        dx = new_act(n, B, T, dev)
+        dd = new_act(n, H, T, dev)
+        du = new_act(n, H, T, dev)
+        sizes = [H * (B + E), H, 1, H, H, 3 * H, H, 1, H, H, B * H, B]
+        flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        parts = list(torch.split(flat, sizes))
+        dW1, db1, da1, dg1, dbe1, dwd, dbd, da2, dg2, dbe2, dW3, db3 = parts
+        daux = torch.empty((n, E), dtype=torch.float32, device=dev) if E else None
+        Gn = torch.empty((n, B, H), dtype=torch.float32, device=dev)
+        sg = torch.empty((n, B), dtype=torch.float32, device=dev)
+        sdu = torch.empty((n, H), dtype=torch.float32, device=dev)
+        rowsc = torch.empty((n, 8), dtype=torch.float64, device=dev)
+        fa = _args("WesepTcnFwdArgs", n=n, B=B, H=H, T=T, dil=ctx.dil, E=E, ld=x.stride(1), x=x, aux=auxc, W1=W1c,
+                   ldw1=W1c.stride(0), b1=b1, a1=a1, g1=g1, be1=be1, wd=wd, bd=bd, a2=a2, g2=g2, be2=be2, W3=W3c,
+                   ldw3=W3c.stride(0), b3=b3, u=u, d=d, out=None, stats1=stats[0], stats2=stats[1], row_bias=None)
+        ba = _args("WesepTcnBwdArgs", gout=gout, dx=dx, dW1=dW1, db1=db1, da1=da1, dg1=dg1, dbe1=dbe1, dwd=dwd, dbd=dbd,
+                   da2=da2, dg2=dg2, dbe2=dbe2, dW3=dW3, db3=db3, daux=daux, dd=dd, du=du, Gn=Gn, sg=sg, sdu=sdu,
+                   rowsc=rowsc)
+        ba.f = fa
+        _lib.call("wesep_b200_tcn_block_bwd", ba, _stream())
+        W1s, W3s, auxs = ctx.shapes
+        g_aux = None if daux is None else daux.reshape(auxs)
+        return (dx, g_aux, dW1.view(W1s), db1, da1, dg1.view(H, 1), dbe1.view(H, 1), dwd.view(H, 1, 3), dbd, da2,
+                dg2.view(H, 1), dbe2.view(H, 1), dW3.view(W3s), db3, None)
+
+
+def tcn_block(x, aux, W1, b1, a1, g1, be1, wd, bd, a2, g2, be2, W3, b3, dil):
+    return TCNBlockFn.apply(x, aux, W1, b1, a1, g1, be1, wd, bd, a2, g2, be2, W3, b3, dil)
+
+
+# --------------------------------------------------------------------------- generic 1x1 conv
+class Conv1x1Fn(torch.autograd.Function):
+    """y = act(W x + b) for x [n, I, T]; W given 2-D as (O, I) or, w_trans, as (I, O). act in {None, 'relu'}."""
+
+    @staticmethod
+    def forward(ctx, x, W2d, bias, w_trans, act):
+        x = as_act(x)
+        W2d = W2d if W2d.is_contiguous() else W2d.contiguous()
+        M = W2d.shape[1] if w_trans else W2d.shape[0]
+        Kd = W2d.shape[0] if w_trans else W2d.shape[1]
+        if Kd != x.shape[1]:
+            raise RuntimeError("conv1x1: channel mismatch")
+        y = conv1x1_raw(x, W2d, w_trans, M, bias=None if bias is None else _vec(bias), epi=1 if act == "relu" else 0)
+        ctx.w_trans, ctx.act, ctx.has_bias = bool(w_trans), act, bias is not None
+        ctx.save_for_backward(x, W2d, y if act == "relu" else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, W2d, y = ctx.saved_tensors
+        n, Kd, T = x.shape
+        g = as_act(gy)
+        if ctx.act == "relu":
+            g2 = new_act(n, g.shape[1], T, g.device)
+            if g.stride(1) != y.stride(1):
+                raise RuntimeError("conv1x1 backward: stride mismatch")
+            _lib.call("wesep_b200_relu_bwd", _args("WesepReluBwdArgs", n=n, C=g.shape[1], T=T, ld=g.stride(1), y=y, gy=g,
+                                                   gx=g2), _stream())
+            g = g2
+        M = g.shape[1]
+        dW = torch.zeros_like(W2d)
+        if ctx.w_trans:   # W stored [Kd][M]: dW[k][m] = sum x[k,t] g[m,t]
+            conv1x1_dw_raw(x, g, dW)
+        else:
+            conv1x1_dw_raw(g, x, dW)
+        db = rowsum_raw(g).sum(0) if ctx.has_bias else None
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = conv1x1_raw(g, W2d, not ctx.w_trans, Kd)
+        return dx, dW, db, None, None
+
+
+def conv1x1(x, W2d, bias=None, w_trans=False, act=None):
+    return Conv1x1Fn.apply(x, W2d, bias, w_trans, act)
+
+
+# --------------------------------------------------------------------------- cLN
+class ClnFn(torch.autograd.Function):
+    """ChannelWiseLayerNorm (wesep/modules/common/norm.py:51-66)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        x = as_act(x)
+        n, C, T = x.shape
+        y = new_act(n, C, T, x.device)
+        mean = torch.empty((n, T), dtype=torch.float32, device=x.device)
+        rstd = torch.empty((n, T), dtype=torch.float32, device=x.device)
+        gamma, beta = _vec(gamma), _vec(beta)
+        _lib.call("wesep_b200_cln_fwd", _args("WesepClnFwdArgs", n=n, C=C, T=T, ldx=x.stride(1), ldy=y.stride(1), x=x, y=y,
+                                              gamma=gamma, beta=beta, eps=float(eps), mean=mean, rstd=rstd), _stream())
+        ctx.save_for_backward(x, gamma, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, gamma, mean, rstd = ctx.saved_tensors
+        n, C, T = x.shape
+        g = as_act(gy)
+        dx = new_act(n, C, T, x.device)
+        dgb = torch.zeros((2, C), dtype=torch.float32, device=x.device)
+        _lib.call("wesep_b200_cln_bwd", _args("WesepClnBwdArgs", n=n, C=C, T=T, ldx=x.stride(1), ldg=g.stride(1),
+                                              lddx=dx.stride(1), x=x, gy=g, dx=dx, gamma=gamma, mean=mean, rstd=rstd,
+                                              dgamma=dgb[0], dbeta=dgb[1]), _stream())
+        return dx, dgb[0], dgb[1], None
+
+
+def cln(x, gamma, beta, eps=1e-5):
+    return ClnFn.apply(x, gamma, beta, eps)
+
+
+# --------------------------------------------------------------------------- encoder / decoder
+def _relu_bwd(y, g):
+    n, C, T = y.shape
+    g = as_act(g)
+    out = new_act(n, C, T, y.device)
+    if not (is_act(y) and g.stride(1) == y.stride(1) == out.stride(1)):
+        raise RuntimeError("relu backward: layout mismatch")
+    _lib.call("wesep_b200_relu_bwd", _args("WesepReluBwdArgs", n=n, C=C, T=T, ld=y.stride(1), y=y, gy=g, gx=out), _stream())
+    return out
+
+
+class MultiEncoderConvFn(torch.autograd.Function):
+    """cat_i relu(conv1d(x, w_i, b_i, stride=hop)) for the three filter lengths of MultiEncoder
+    (wesep/modules/tasnet/encoder.py:95-110): framing + three GEMMs writing one [n, 3N, K] tensor.
+    The right zero-padding of the input (encoder.py:103-109) is the zero fill of the framing."""
+
+    @staticmethod
+    def forward(ctx, x, hop, *wb):
+        ws, bs = wb[0::2], wb[1::2]
+        _check_cuda(x, *ws)
+        n, T = x.shape
+        N = ws[0].shape[0]
+        Ls = [w.shape[-1] for w in ws]
+        if any(L % 4 for L in Ls) or T < Ls[0]:
+            raise RuntimeError("MultiEncoder: filter lengths must be multiples of 4 and <= signal length")
+        K = (T - Ls[0]) // hop + 1
+        F = frames_raw(x, max(Ls), K, hop)
+        w_cat = new_act(n, len(ws) * N, K, x.device)
+        W2 = [_w2d(w) for w in ws]
+        for i, (W, b, L) in enumerate(zip(W2, bs, Ls)):
+            conv1x1_raw(F[:, :L], W, False, N, bias=_vec(b), epi=1, Y=w_cat[:, i * N:(i + 1) * N])
+        ctx.N, ctx.Ls = N, Ls
+        ctx.wshapes = [w.shape for w in ws]
+        ctx.save_for_backward(F, w_cat)
+        return w_cat
+
+    @staticmethod
+    def backward(ctx, g_cat):
+        F, w_cat = ctx.saved_tensors
+        N, Ls = ctx.N, ctx.Ls
+        g = _relu_bwd(w_cat, g_cat)
+        rs = rowsum_raw(g).sum(0)
+        outs = []
+        for i, L in enumerate(Ls):
+            dW = torch.zeros((N, L), dtype=torch.float32, device=g.device)
+            conv1x1_dw_raw(g[:, i * N:(i + 1) * N], F[:, :L], dW)
+            outs += [dW.view(ctx.wshapes[i]), rs[i * N:(i + 1) * N]]
+        return (None, None, *outs)
+
+
+class DecoderMasksFn(torch.autograd.Function):
+    """S_i = w_i * relu(mask_i(e)) for i = 1..3 as ONE GEMM over concatenated mask weights
+    (MultiDecoder.forward, wesep/modules/tasnet/decoder.py:96-102)."""
+
+    @staticmethod
+    def forward(ctx, e, w_cat, *wb):
+        ws, bs = wb[0::2], wb[1::2]
+        e, w_cat = as_act(e), as_act(w_cat)
+        Wc = torch.cat([_w2d(w) for w in ws], 0).contiguous()
+        bc = torch.cat([_vec(b) for b in bs], 0).contiguous()
+        n, _, T = e.shape
+        M = Wc.shape[0]
+        if w_cat.shape[1] != M:
+            raise RuntimeError("decoder masks: encoder output / mask width mismatch")
+        m = new_act(n, M, T, e.device)
+        S = conv1x1_raw(e, Wc, False, M, bias=bc, epi=3, R=w_cat, Y2=m)
+        ctx.wshapes = [w.shape for w in ws]
+        ctx.save_for_backward(e, w_cat, Wc, m)
+        return S
+
+    @staticmethod
+    def backward(ctx, gS):
+        e, w_cat, Wc, m = ctx.saved_tensors
+        n, B, T = e.shape
+        M = Wc.shape[0]
+        gS = as_act(gS)
+        gw = new_act(n, M, T, e.device)
+        gm = new_act(n, M, T, e.device)
+        if not (gS.stride(1) == w_cat.stride(1) == m.stride(1) == gw.stride(1)):
+            raise RuntimeError("decoder masks backward: stride mismatch")
+        _lib.call("wesep_b200_mask_bwd", _args("WesepMaskBwdArgs", n=n, C=M, T=T, ld=gw.stride(1), gS=gS, w=w_cat, m=m,
+                                               gw=gw, gm=gm, acc_w=0), _stream())
+        dW = torch.zeros_like(Wc)
+        conv1x1_dw_raw(gm, e, dW)
+        db = rowsum_raw(gm).sum(0)
+        de = conv1x1_raw(gm, Wc, True, B)
+        k = len(ctx.wshapes)
+        Ni = M // k
+        outs = []
+        for i in range(k):
+            outs += [dW[i * Ni:(i + 1) * Ni].reshape(ctx.wshapes[i]), db[i * Ni:(i + 1) * Ni]]
+        return (de, gw, *outs)
+
+
+class DecoderBasisFn(torch.autograd.Function):
+    """est_i = ConvTranspose1d(N, 1, L_i, stride=hop)(S_i)[:, :xlen]  (decoder.py:104-108) as a basis
+    GEMM F_i = D_i^T S_i followed by a gather-form overlap-add (no atomics)."""
+
+    @staticmethod
+    def forward(ctx, S_cat, hop, xlen, *db):
+        Ds, cs = db[0::2], db[1::2]
+        S_cat = as_act(S_cat)
+        n, M, K = S_cat.shape
+        k = len(Ds)
+        N = M // k
+        D2 = [_w2d(D) for D in Ds]          # (N, 1, L) -> [N, L]
+        ests = []
+        for i, (D, c) in enumerate(zip(D2, cs)):
+            L = D.shape[1]
+            if L % 4:
+                raise RuntimeError("MultiDecoder: filter lengths must be multiples of 4")
+            Fi = conv1x1_raw(S_cat[:, i * N:(i + 1) * N], D, True, L)
+            y = torch.empty((n, xlen), dtype=torch.float32, device=S_cat.device)
+            _lib.call("wesep_b200_overlap_add", _args("WesepOlaArgs", n=n, J=L, K=K, hop=hop, S=xlen, F=Fi, ldf=Fi.stride(1),
+                                                      bias=_vec(c), y=y, ldy=y.stride(0)), _stream())
+            ests.append(y)
+        ctx.hop, ctx.N = hop, N
+        ctx.dshapes = [D.shape for D in Ds]
+        ctx.save_for_backward(S_cat, *D2)
+        return tuple(ests)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        S_cat, *D2 = ctx.saved_tensors
+        n, M, K = S_cat.shape
+        N, hop = ctx.N, ctx.hop
+        dS = new_act(n, M, K, S_cat.device)
+        outs = []
+        for i, (D, g) in enumerate(zip(D2, gs)):
+            L = D.shape[1]
+            if g is None:
+                dS[:, i * N:(i + 1) * N].zero_()
+                outs += [None, None]
+                continue
+            g = g.contiguous()
+            dF = frames_raw(g, L, K, hop)
+            conv1x1_raw(dF, D, False, N, Y=dS[:, i * N:(i + 1) * N])
+            dD = torch.zeros_like(D)
+            conv1x1_dw_raw(S_cat[:, i * N:(i + 1) * N], dF, dD)
+            outs += [dD.view(ctx.dshapes[i]), g.sum().reshape(1)]
+        return (dS, None, None, *outs)
+
+
+# --------------------------------------------------------------------------- SI-SDR
+class SisdrFn(torch.autograd.Function):
+    """losses[i] = SISDRLoss()(est_i, tgt) for up to 4 estimates sharing one target
+    (auraloss.time.SISDRLoss as used at wesep/utils/losses.py:24-25)."""
+
+    @staticmethod
+    def forward(ctx, tgt, *ests):
+        k = len(ests)
+        if not 1 <= k <= 4:
+            raise RuntimeError("sisdr: 1..4 estimates")
+        _check_cuda(tgt, *ests)
+        tgt, ldt = _sig(tgt)
+        n, L = tgt.shape
+        es = [_sig(e) for e in ests]
+        for e, _ in es:
+            if e.shape != (n, L):
+                raise RuntimeError("sisdr: estimate/target shape mismatch")
+        dev = tgt.device
+        sums = torch.empty((k, n, 5), dtype=torch.float64, device=dev)
+        rows = torch.empty((k, n), dtype=torch.float32, device=dev)
+        loss = torch.empty((k,), dtype=torch.float32, device=dev)
+        a = _args("WesepSisdrFwdArgs", n_est=k, n=n, L=L, tgt=tgt, ld_tgt=ldt, sums=sums, sisdr_rows=rows, loss=loss)
+        for i, (e, ld) in enumerate(es):
+            a.est[i] = e.data_ptr()
+            a.ld_est[i] = ld
+        _lib.call("wesep_b200_sisdr_fwd", a, _stream())
+        ctx.save_for_backward(tgt, sums, *[e for e, _ in es])
+        ctx.mark_non_differentiable(rows)
+        return loss, rows
+
+    @staticmethod
+    def backward(ctx, gloss, _grows):
+        tgt, sums, *es = ctx.saved_tensors
+        k = len(es)
+        n, L = tgt.shape
+        gloss = gloss.contiguous().float()
+        gs = [torch.empty((n, L), dtype=torch.float32, device=tgt.device) for _ in range(k)]
+        a = _args("WesepSisdrBwdArgs", n_est=k, n=n, L=L, tgt=tgt, ld_tgt=tgt.stride(0), sums=sums, gloss=gloss)
+        for i in range(k):
+            a.est[i] = es[i].data_ptr()
+            a.ld_est[i] = es[i].stride(0)
+            a.gest[i] = gs[i].data_ptr()
+            a.ld_gest[i] = L
+        _lib.call("wesep_b200_sisdr_bwd", a, _stream())
+        return (None, *gs)
+
+
+def sisdr_losses(ests, tgt):
+    """Returns (losses [k], per-row SI-SDR [k, n] in dB)."""
+    return SisdrFn.apply(tgt, *ests)

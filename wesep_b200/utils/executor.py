@@ -1,0 +1,74 @@
+"""Train-step driver — mirrors the loop body of the reference Executor.train
+(wesep/utils/executor.py:70-134): forward, weighted SI-SDR (+CE) loss, backward, gradient
+all-reduce, per-tensor clip + Adam.  Host syncs per step: only the caller's optional loss read."""
+import torch
+import torch.nn.functional as F
+
+from wesep_b200 import ops
+
+
+def compute_loss(outputs, targets, spk_label, loss_posi=((0, 1, 2), (3,)), loss_weight=((0.8, 0.1, 0.1), (0.5,)),
+                 multi_task=True):
+    """loss = sum_j w0[j] * SISDR(outputs[posi0[j]], targets) (+ w1[j] * CE(outputs[posi1[j]], spk_label))
+    — executor.py:105-122 with criterion = [SISDR, CE]; all SI-SDR terms in one fused kernel."""
+    if not isinstance(outputs, (list, tuple)):
+        outputs = [outputs]
+    ests = [outputs[p] for p in loss_posi[0]]
+    L = ests[0].shape[-1]
+    tgt = targets if targets.shape[-1] == L else targets[:, :L]
+    losses, rows = ops.sisdr_losses(ests, tgt)
+    w = torch.tensor(list(loss_weight[0]), dtype=torch.float32, device=losses.device)
+    loss = (losses * w).sum()
+    if multi_task and len(loss_posi) > 1:
+        for j, p in enumerate(loss_posi[1]):
+            loss = loss + loss_weight[1][j] * F.cross_entropy(outputs[p], spk_label)
+    return loss, rows
+
+
+def train_step(model, batch, optimizer, reducer=None, loss_posi=((0, 1, 2), (3,)), loss_weight=((0.8, 0.1, 0.1), (0.5,)),
+               multi_task=True, device=None):
+    """One iteration of Executor.train. `batch` holds wav_mix / wav_targets / spk_embeds / spk_label
+    (host pinned or device tensors). Returns the (device) loss tensor; no host sync here."""
+    if device is None:
+        device = next(model.parameters()).device
+    features = batch["wav_mix"].to(device, non_blocking=True).float()
+    targets = batch["wav_targets"].to(device, non_blocking=True).float()
+    enroll = batch["spk_embeds"].to(device, non_blocking=True).float()
+    spk_label = batch["spk_label"].to(device, non_blocking=True)
+    optimizer.zero_grad()
+    outputs = model(features, enroll)
+    loss, _ = compute_loss(outputs, targets, spk_label, loss_posi, loss_weight, multi_task)
+    loss.backward()
+    if reducer is not None:
+        reducer.all_reduce()
+        optimizer.grad_scale = reducer.grad_scale
+    optimizer.step()
+    return loss
+
+
+class Executor:
+    """reference wesep/utils/executor.py:27-152 (train only; logging left to the caller)."""
+
+    def __init__(self):
+        self.step = 0
+
+    def train(self, dataloader, models, epoch_iter, optimizers, criterion, schedulers, scaler, epoch, enable_amp,
+              logger, clip_grad=5.0, log_batch_interval=100, device=torch.device("cuda"), se_loss_weight=1.0,
+              multi_task=False, reducer=None, **_unused):
+        if enable_amp:
+            raise NotImplementedError("AMP is off in every recipe (fp32 path only)")
+        model, optimizer, scheduler = models[0], optimizers[0], schedulers[0]
+        model.train()
+        optimizer.param_groups[0]["clip"] = clip_grad or 0.0
+        losses = []
+        for i, batch in enumerate(dataloader):
+            cur_iter = (epoch - 1) * epoch_iter + i
+            scheduler.step(cur_iter)
+            loss = train_step(model, batch, optimizer, reducer, se_loss_weight[0], se_loss_weight[1], multi_task, device)
+            losses.append(loss.item())
+            if logger is not None and (i + 1) % log_batch_interval == 0:
+                logger.info("TRAIN epoch %d iter %d loss %.4f lr %.3e" % (epoch, i + 1, sum(losses) / len(losses),
+                                                                           optimizer.param_groups[0]["lr"]))
+            if (i + 1) == epoch_iter:
+                break
+        return sum(losses) / len(losses), 0
