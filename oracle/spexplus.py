@@ -34,19 +34,20 @@ def prelu(x, a):
 
 
 # --------------------------------------------------------------------------- encoder
-def multi_encoder(sd, pre, x, L1=20, stride=10, L2=80, L3=160, only_w=False):
-    """MultiEncoder.forward — wesep/modules/tasnet/encoder.py:95-114."""
+def multi_encoder(sd, pre, x, L1=20, stride=10, L2=80, L3=160, only_w=False, relu=F.relu):
+    """MultiEncoder.forward — wesep/modules/tasnet/encoder.py:95-114.  (`relu` overridable by tests to pin the
+    branch at |x| ~ 0, like `prelu` in conv1d_block.)"""
     if x.dim() == 2:
         x = x.unsqueeze(1)  # Conv1D.forward, convs.py:19
-    w1 = F.relu(F.conv1d(x, sd[pre + "encoder_1d_short.weight"], sd[pre + "encoder_1d_short.bias"], stride=stride))
+    w1 = relu(F.conv1d(x, sd[pre + "encoder_1d_short.weight"], sd[pre + "encoder_1d_short.bias"], stride=stride))
     T = w1.shape[-1]
     xlen1 = x.shape[-1]
     xlen2 = (T - 1) * stride + L2
     xlen3 = (T - 1) * stride + L3
-    w2 = F.relu(F.conv1d(F.pad(x, (0, xlen2 - xlen1)), sd[pre + "encoder_1d_middle.weight"],
-                         sd[pre + "encoder_1d_middle.bias"], stride=stride))
-    w3 = F.relu(F.conv1d(F.pad(x, (0, xlen3 - xlen1)), sd[pre + "encoder_1d_long.weight"],
-                         sd[pre + "encoder_1d_long.bias"], stride=stride))
+    w2 = relu(F.conv1d(F.pad(x, (0, xlen2 - xlen1)), sd[pre + "encoder_1d_middle.weight"],
+                       sd[pre + "encoder_1d_middle.bias"], stride=stride))
+    w3 = relu(F.conv1d(F.pad(x, (0, xlen3 - xlen1)), sd[pre + "encoder_1d_long.weight"],
+                       sd[pre + "encoder_1d_long.bias"], stride=stride))
     if only_w:
         return None, w1, w2, w3
     e = cln(torch.cat([w1, w2, w3], 1), sd[pre + "ln.weight"], sd[pre + "ln.bias"])
@@ -55,8 +56,10 @@ def multi_encoder(sd, pre, x, L1=20, stride=10, L2=80, L3=160, only_w=False):
 
 
 # --------------------------------------------------------------------------- TCN blocks
-def conv1d_block(sd, pre, x, dilation, P=3):
-    """Conv1DBlock.forward (skip_con False, non-causal) — wesep/modules/tasnet/convs.py:84-104."""
+def conv1d_block(sd, pre, x, dilation, P=3, prelu=prelu):
+    """Conv1DBlock.forward (skip_con False, non-causal) — wesep/modules/tasnet/convs.py:84-104.
+    `prelu` may be overridden by tests to pin the branch taken at |x| ~ 0 (PReLU's derivative is
+    discontinuous there, so fp32 and fp64 runs legitimately disagree on isolated elements)."""
     H = sd[pre + "dwconv.weight"].shape[0]
     c = F.conv1d(x, sd[pre + "conv1x1.weight"], sd[pre + "conv1x1.bias"])
     c = prelu(c, sd[pre + "PReLU_1.weight"])
@@ -69,7 +72,7 @@ def conv1d_block(sd, pre, x, dilation, P=3):
     return x + c
 
 
-def conv1d_block4fuse(sd, pre, x, aux, dilation=1, P=3):
+def conv1d_block4fuse(sd, pre, x, aux, dilation=1, P=3, prelu=prelu):
     """Conv1DBlock4Fuse.forward — wesep/modules/tasnet/convs.py:148-160 (aux [n,E,1])."""
     H = sd[pre + "dconv.weight"].shape[0]
     T = x.shape[-1]

@@ -19,6 +19,7 @@ int launch_gemm_wx(const GemmWxP& p, bool a_trans, int pro, int epi, cudaStream_
   WB_CASE(false, 2, 0)
   WB_CASE(false, 2, 2)
   WB_CASE(true, 0, 0)
+  WB_CASE(true, 0, 1)
   WB_CASE(true, 0, 2)
   WB_CASE(true, 0, 10)
   WB_CASE(true, 2, 0)

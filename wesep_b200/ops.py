@@ -12,6 +12,9 @@ from . import _lib
 from ._lib import STRUCTS
 
 
+DEBUG_STASH = None   # tests may set this to a dict to inspect the TCN backward workspaces
+
+
 # --------------------------------------------------------------------------- helpers
 def _stream():
     return torch.cuda.current_stream().cuda_stream
@@ -209,6 +212,8 @@ class TCNBlockFn(torch.autograd.Function):
                    rowsc=rowsc)
         ba.f = fa
         _lib.call("wesep_b200_tcn_block_bwd", ba, _stream())
+        if DEBUG_STASH is not None:
+            DEBUG_STASH.update(dd=dd, du=du, Gn=Gn, sg=sg, sdu=sdu, rowsc=rowsc, u=u, d=d, stats=stats)
         W1s, W3s, auxs = ctx.shapes
         g_aux = None if daux is None else daux.reshape(auxs)
         return (dx, g_aux, dW1.view(W1s), db1, da1, dg1.view(H, 1), dbe1.view(H, 1), dwd.view(H, 1, 3), dbd, da2,
