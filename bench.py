@@ -268,12 +268,12 @@ def run_ours(args, rank, world, local):
         config=dict(workload="Spex+ (ConvTasNet, examples/librimix/tse/v2/confs/spexplus.yaml) full train step, "
                              "4s@16kHz, %d model rows per GPU" % n,
                     rows_per_gpu=n, global_rows=n * world, samples=T_SAMPLES, parallelism="dp%d" % world,
-                    gemm_mode="3xTF32 split (fp32-grade) on mma.sync", l2="inputs and activations >> L2 (126 MB)",
+                    gemm_mode="3xTF32 split (fp32-grade); tcgen05.mma kind::tf32 + TMA + TMEM for the TCN GEMMs, mma.sync elsewhere", l2="inputs and activations >> L2 (126 MB)",
                     loss="0.8/0.1/0.1 SI-SDR + 0.5 CE", optimizer="per-tensor clip 5.0 + Adam(wd 1e-4), exp-decay lr"),
         e2e=dict(value=e2e, unit="utterances/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
                  ms_per_step=ms_e2e / args.steps),
         gpu_launches=launches, clocks=clocks, loss=loss_res, loss_e2e=loss_e2e,
-        roofline=dict(kernel="gemm_wx_kernel (K2 shape 256->512, n=%d, K=6399)" % n, bound="tensor",
+        roofline=dict(kernel="gemm_wx_tc_kernel<0,0> (tcgen05; K2 shape 256->512, n=%d, K=6399)" % n, bound="tensor",
                       achieved=dom["exec_tflops"], peak=pk["tf_burst"], unit="TFLOP/s",
                       frac=dom["exec_tflops"] / pk["tf_burst"], traffic=None,
                       note="executed = 3x algorithmic flops (3xTF32); peak = measured bf16 burst (%s); TF32 "

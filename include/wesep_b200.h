@@ -38,6 +38,14 @@ const char* wesep_b200_last_error(void);
 uint64_t wesep_b200_launch_count(void);
 /* GEMM precision: 0 = 3xTF32 split (fp32-grade, default), 1 = single-pass TF32. Process-wide. */
 int wesep_b200_set_gemm_mode(int mode);
+/* GEMM backend: 0 = legacy tensor path (mma.sync), 1 (default) = tcgen05/UMMA + TMA + TMEM where the shape is eligible
+ * (M % 128 == 0, Kd % 16 == 0, Kd <= 512, a workspace is supplied); other shapes stay on backend 0. Process-wide. */
+int wesep_b200_set_gemm_backend(int backend);
+/* tcgen05 debug flags. bit 0: also store the explicitly truncated "hi" operand tile (default off: the tensor core
+ * ignores the 13 low mantissa bits of tf32 inputs — measured identical results — so the raw tile serves as hi). */
+int wesep_b200_set_tc_flags(int flags);
+/* Workspace bytes the tcgen05 GEMM needs for an [M x Kd] weight (split hi/lo copies). */
+int64_t wesep_b200_gemm_ws_bytes(int M, int Kd);
 
 /* ------------------------------------------------------------------------------------------------
  * SI-SDR loss (replaces auraloss.time.SISDRLoss used at wesep/utils/losses.py:24-25, called at
@@ -123,6 +131,7 @@ typedef struct {
   const float* out_alpha;
   double* ch_stats;                           /* optional [M][2]: += per-channel sum / sumsq of Y (BatchNorm) */
   int64_t bsx, bsy, bsr, bsy2;                /* batch strides in floats; 0 = dense (C*ld): channel-slices of wider tensors */
+  void* ws; int64_t ws_bytes;                 /* optional workspace (>= wesep_b200_gemm_ws_bytes(M, Kd)) enabling backend 1 */
 } WesepGemmArgs;
 int wesep_b200_conv1x1(const WesepGemmArgs* a, void* stream);
 
@@ -171,6 +180,7 @@ typedef struct {
   float* out;                   /* out [n][B][ld] */
   double* stats1; double* stats2; /* out [n][2] each (zeroed by the call) */
   float* row_bias;              /* workspace [n][H] (fuse block only) */
+  void* ws; int64_t ws_bytes;   /* optional GEMM workspace (>= wesep_b200_gemm_ws_bytes(H, max(B,H))) enabling backend 1 */
 } WesepTcnFwdArgs;
 int wesep_b200_tcn_block_fwd(const WesepTcnFwdArgs* a, void* stream);
 

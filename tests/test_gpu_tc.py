@@ -1,0 +1,84 @@
+"""GPU: the tcgen05/TMA/TMEM GEMM backend (default) vs the legacy mma.sync backend and the fp64 oracle."""
+import math
+
+import pytest
+import torch
+
+from tests.test_gpu_kernels import _block_case, check, rnd
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(params=[0, 1], ids=["mma_sync", "tcgen05"])
+def backend(request):
+    from wesep_b200 import _lib
+    _lib.set_gemm_backend(request.param)
+    yield request.param
+    _lib.set_gemm_backend(1)
+
+
+@pytest.mark.parametrize("n,Kd,M,T,w_trans", [(1, 128, 128, 256, False), (2, 256, 512, 6399, False), (2, 512, 256, 6399, True),
+                                              (3, 64, 128, 100, False), (2, 256, 384, 517, True)])
+def test_conv1x1_backends(backend, n, Kd, M, T, w_trans):
+    from wesep_b200 import ops
+    x = ops.new_act(n, Kd, T, DEV)
+    x.copy_(rnd(n, Kd, T, seed=1))
+    W = rnd(Kd, M, seed=2, scale=1 / math.sqrt(Kd)) if w_trans else rnd(M, Kd, seed=2, scale=1 / math.sqrt(Kd))
+    b = rnd(M, seed=3)
+    R = ops.new_act(n, M, T, DEV)
+    R.copy_(rnd(n, M, T, seed=4))
+    y = ops.conv1x1_raw(x, W, w_trans, M, bias=b, epi=2, R=R)
+    Wm = W.double().t() if w_trans else W.double()
+    ref = torch.einsum("mk,nkt->nmt", Wm, x.double()) + b.double()[None, :, None] + R.double()
+    check("y", y, ref, 1e-5)
+
+
+def test_tc_is_used_and_counts_launches():
+    """With the default backend an eligible shape must go through the tcgen05 kernel (split_w + gemm = 2 launches)."""
+    from wesep_b200 import _lib, ops
+    _lib.set_gemm_backend(1)
+    x = ops.new_act(1, 128, 512, DEV)
+    x.normal_()
+    W = rnd(128, 128, seed=1)
+    before = _lib.launch_count()
+    ops.conv1x1_raw(x, W, False, 128)
+    assert _lib.launch_count() - before == 2
+    _lib.set_gemm_backend(0)
+    before = _lib.launch_count()
+    ops.conv1x1_raw(x, W, False, 128)
+    assert _lib.launch_count() - before == 1
+    _lib.set_gemm_backend(1)
+
+
+def test_tcn_block_full_size_backends(backend):
+    _block_case(False, n=2, B=256, H=512, T=6399, dil=16, seed=21)
+
+
+def test_tcn_fuse_block_full_size_backends(backend):
+    _block_case(True, n=3, B=256, H=512, T=4799, dil=1, seed=22, E=256)
+
+
+def test_tcn_block_small_mixed_backends(backend):
+    # H=128 is eligible for tcgen05 (M=128), B=64 is not: the block mixes both kernels
+    _block_case(False, n=2, B=64, H=128, T=700, dil=8, seed=23)
+
+
+@pytest.mark.parametrize("n,M,N,T,pro,per_row", [(2, 256, 512, 6399, 1, True), (3, 512, 256, 1000, 0, False),
+                                                   (1, 128, 256, 50, 0, False), (32, 512, 256, 6399, 0, False)])
+def test_conv1x1_dw_backends(backend, n, M, N, T, pro, per_row):
+    from wesep_b200 import ops
+    A = ops.new_act(n, M, T, DEV)
+    A.copy_(rnd(n, M, T, seed=1))
+    B = ops.new_act(n, N, T, DEV)
+    B.copy_(rnd(n, N, T, seed=2))
+    alpha = torch.tensor([0.3], device=DEV)
+    C = torch.zeros((n, M, N) if per_row else (M, N), device=DEV)
+    ops.conv1x1_dw_raw(A, B, C, per_row=per_row, pro_b=pro, alpha_b=alpha if pro else None)
+    Bd = B.double()
+    if pro:
+        Bd = torch.where(Bd > 0, Bd, 0.3 * Bd)
+    ref = torch.einsum("nmt,nkt->nmk", A.double(), Bd)
+    if not per_row:
+        ref = ref.sum(0)
+    check("C", C, ref, 1e-4 if n * T > 100000 else 1e-5)   # 2e5-term fp32 sums (tensor-core accumulation truncates)

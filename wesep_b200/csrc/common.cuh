@@ -13,6 +13,7 @@ namespace wb {
 extern thread_local char g_err[512];
 extern std::atomic<uint64_t> g_launches;
 extern int g_gemm_mode;
+extern int g_gemm_backend;
 
 inline int fail(int code, const char* msg) {
   snprintf(g_err, sizeof(g_err), "%s", msg);

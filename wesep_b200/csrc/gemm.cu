@@ -5,6 +5,9 @@ namespace wb {
 
 int launch_gemm_wx(const GemmWxP& p, bool a_trans, int pro, int epi, cudaStream_t st) {
   if (p.n <= 0 || p.M <= 0 || p.Kd <= 0 || p.T <= 0) return fail(-1, "gemm_wx: empty shape");
+  if (g_gemm_backend == 1 && g_gemm_mode == 0 && p.ws && (size_t)p.ws_bytes >= gemm_wx_tc_ws_bytes(p.M, p.Kd) &&
+      gemm_wx_tc_eligible(p, pro, epi))
+    return launch_gemm_wx_tc(p, a_trans, pro, epi, p.ws, st);
   if ((p.ldx & 3) || (p.ldw & 3) || !aligned16(p.X) || !aligned16(p.W)) return fail(-1, "gemm_wx: ldx/ldw/base alignment");
   if ((p.Kd & 3) || (a_trans && (p.M & 3))) return fail(-1, "gemm_wx: Kd (and M when transposed) must be multiples of 4");
   if (p.ep.ldy & 1) return fail(-1, "gemm_wx: ldy must be even");
@@ -188,6 +191,7 @@ int launch_gemm_dw(const GemmDwP& pin, int pro_b, cudaStream_t st) {
   if (p.n <= 0 || p.M <= 0 || p.N <= 0 || p.T <= 0) return fail(-1, "gemm_dw: empty shape");
   if ((p.lda & 3) || (p.ldb & 3) || !aligned16(p.A) || !aligned16(p.B)) return fail(-1, "gemm_dw: lda/ldb/base alignment");
   if (p.ldc < p.N) return fail(-1, "gemm_dw: ldc < N");
+  if (g_gemm_backend == 1 && g_gemm_mode == 0 && gemm_dw_tc_eligible(p, pro_b)) return launch_gemm_dw_tc(p, pro_b, st);
   if (p.t_chunk <= 0) {
     // aim for >= ~2 waves of CTAs (296 resident) without making chunks tiny
     int tiles = cdiv(p.M, G_BM) * cdiv(p.N, G_BN) * p.n;
@@ -220,6 +224,7 @@ extern "C" int wesep_b200_conv1x1(const WesepGemmArgs* a, void* stream) {
   e.R = a->R; e.ldr = a->ldr; e.bsr = a->bsr ? a->bsr : (int64_t)a->M * a->ldr;
   e.Y2 = a->Y2; e.ldy2 = a->ldy2; e.bsy2 = a->bsy2 ? a->bsy2 : (int64_t)a->M * a->ldy2;
   e.out_stats = a->out_stats; e.out_alpha = a->out_alpha; e.ch_stats = a->ch_stats;
+  p.ws = a->ws; p.ws_bytes = a->ws_bytes;
   if (a->epi < 0 || a->epi > 3) return fail(-2, "conv1x1: epi must be 0..3");
   if ((a->epi == 2 || a->epi == 3) && (!a->R || (a->ldr & 1))) return fail(-1, "conv1x1: residual/aux missing or odd ldr");
   if (a->epi == 3 && (!a->Y2 || (a->ldy2 & 1))) return fail(-1, "conv1x1: Y2 missing");

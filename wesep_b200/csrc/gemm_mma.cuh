@@ -67,7 +67,14 @@ struct GemmWxP {
   const float* X; int64_t ldx; int64_t bsx;
   XformP xf;
   EpiP ep;
+  void* ws; int64_t ws_bytes;   // optional workspace for the tcgen05 backend
 };
+
+// tcgen05 backend (gemm_tc.cu)
+bool gemm_wx_tc_eligible(const GemmWxP& p, int pro, int epi);
+size_t gemm_wx_tc_ws_bytes(int M, int Kd);
+int launch_gemm_wx_tc(const GemmWxP& p, bool a_trans, int pro, int epi, void* ws, cudaStream_t st);
+extern int g_gemm_backend;
 
 // ------------------------------------------------------------------------------------ epilogues
 template <int EPI>
@@ -406,5 +413,7 @@ struct GemmDwP {
   int t_chunk; // time steps per CTA (multiple of G_BK)
 };
 int launch_gemm_dw(const GemmDwP& p, int pro_b, cudaStream_t st);
+bool gemm_dw_tc_eligible(const GemmDwP& p, int pro_b);
+int launch_gemm_dw_tc(const GemmDwP& p, int pro_b, cudaStream_t st);
 
 }  // namespace wb

@@ -1,0 +1,775 @@
+// tcgen05 (UMMA) pointwise-conv GEMM for sm_100a:  Y[n][o][t] = sum_k W[o][k] * f(X[n][k][t])  (+ epilogue)
+//
+//   D[M = 128 output channels][N = 256 time steps] accumulates in TMEM (fp32), operands in shared memory:
+//     A = W^T tile  [k][o]  (MN-major, 32 o = 128 B per row)   pre-split into hi / lo by a prep kernel
+//     B = X   tile  [k][t]  (MN-major, 32 t = 128 B per row)   TMA'd raw, split into hi / lo by transform warps
+//   both with the 128-byte TMA/UMMA swizzle, so ONE layout rule covers both operands and the transform pass is a
+//   layout-agnostic elementwise sweep (the swizzle only permutes 16-byte chunks inside a 128-byte row).
+//   3xTF32: D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  (kind::tf32, K = 8 per instruction), fp32-grade accuracy.
+//
+//   Warp roles (448 threads, 1 CTA/SM, persistent over tiles):
+//     warps 0-7   epilogue   TMEM -> registers (tcgen05.ld 32x32b) -> fused epilogue -> global (lane = channel;
+//                            warp w owns TMEM lanes 32*(w%4).. and columns 128*(w/4)..)
+//     warp  8     TMA producer (4-stage ring, BK = 16) + TMEM alloc/dealloc
+//     warp  9     MMA issuer (one thread), tcgen05.commit -> mbarriers
+//     warps 10-17 transform  hi/lo split (+ gLN/PReLU operand prologue), fence.proxy.async
+//   TMEM: 2 x 256 columns (double-buffered accumulators: epilogue of tile i overlaps the MMAs of tile i+1).
+#include <cuda.h>
+
+#include "gemm_mma.cuh"
+
+namespace wb {
+
+constexpr int TC_BM = 128, TC_BN = 256, TC_BK = 16, TC_STAGES = 4;
+constexpr int TC_THREADS = 576;   // 8 epilogue + TMA + MMA + 8 transform warps
+constexpr int TC_W_TMA = 8, TC_W_MMA = 9, TC_W_XF = 10;
+constexpr int TC_BOX_BYTES = 32 * TC_BK * 4;             // one TMA box: 32 floats x 16 rows = 2048 B
+constexpr int TC_W_BYTES = (TC_BM / 32) * TC_BOX_BYTES;  // 8192
+constexpr int TC_X_BYTES = (TC_BN / 32) * TC_BOX_BYTES;  // 16384
+constexpr int TC_OFF_WHI = 0, TC_OFF_WLO = TC_W_BYTES, TC_OFF_XHI = 2 * TC_W_BYTES, TC_OFF_XLO = 2 * TC_W_BYTES + TC_X_BYTES;
+constexpr int TC_STAGE_BYTES = 2 * TC_W_BYTES + 2 * TC_X_BYTES;  // 49152
+constexpr int TC_TX_BYTES = 2 * TC_W_BYTES + TC_X_BYTES;         // bytes the TMA delivers per stage
+constexpr int TC_MAXK = 512;
+constexpr int TC_SMEM_AUX = 2 * TC_MAXK * 4 + 256;                // sc/sh + barriers
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + TC_SMEM_AUX + 1024;
+
+// ------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(dst),
+               "l"(map), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+
+// Shared-memory matrix descriptor: MN-major 32-bit (tf32) operand.  For MN-major tf32 the only legal smem layout
+// is SWIZZLE_128B_BASE32B (cutlass sm100_common.inl:92; cute Layout_MN_SW128_32B_Atom = Swizzle<2,5,2> over
+// 32 floats x 4 K-rows): 128-byte rows, 32-byte swizzle granules, K atoms of 4 rows (512 B).  The matching TMA mode
+// is CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+//   LBO = byte stride between MN atoms (next 32 floats of M/N) = one TMA box; SBO = stride between K atoms = 512 B.
+//   (cute::UMMA::SmemDescriptor: start[0,14) lbo[16,30) sbo[32,46) version[46,48)=1 layout_type[61,64)=1)
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t saddr) {
+  uint64_t d = (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(TC_BOX_BYTES >> 4) << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, both MN-major, N=256, M=128.
+constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(TC_BN >> 3) << 17) |
+                              ((uint32_t)(TC_BM >> 4) << 24);
+
+// ------------------------------------------------------------------------------------------ prep kernel
+// Whi_t[k][o] = tf32-truncated W[o][k] (or W[k][o] if w_trans), Wlo_t = W - Whi.  [Kd][M] row-major.
+__global__ void split_w_kernel(const float* __restrict__ W, int64_t ldw, int w_trans, int M, int Kd, float* __restrict__ hi,
+                               float* __restrict__ lo) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * Kd) return;
+  int k = idx / M, o = idx % M;
+  float w = w_trans ? W[(int64_t)k * ldw + o] : W[(int64_t)o * ldw + k];
+  float h = __uint_as_float(__float_as_uint(w) & 0xFFFFE000u);
+  hi[idx] = h;
+  lo[idx] = w - h;
+}
+
+struct TcParams {
+  GemmWxP g;
+  int n_ob, n_tt, n_tiles;
+  int skip_hi_store;   // PRO 0 only: leave the raw fp32 tile as the "hi" operand (valid iff the MMA truncates to tf32)
+};
+int g_tc_flags = 0;
+
+// ------------------------------------------------------------------------------------------ main kernel
+template <int PRO, int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    gemm_wx_tc_kernel(const __grid_constant__ CUtensorMap map_whi, const __grid_constant__ CUtensorMap map_wlo,
+                      const __grid_constant__ CUtensorMap map_x, const TcParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const GemmWxP& p = P.g;
+  // 1024-byte aligned base (swizzle atoms)
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw);
+  float* sc = reinterpret_cast<float*>(gbase + TC_STAGES * TC_STAGE_BYTES);
+  float* sh = sc + TC_MAXK;
+  const uint32_t bar0 = base + TC_STAGES * TC_STAGE_BYTES + 2 * TC_MAXK * 4;
+  // barrier addresses (8 B each)
+  auto bar_full = [&](int s) { return bar0 + 8u * s; };
+  auto bar_ready = [&](int s) { return bar0 + 8u * (TC_STAGES + s); };
+  auto bar_empty = [&](int s) { return bar0 + 8u * (2 * TC_STAGES + s); };
+  auto bar_accf = [&](int a) { return bar0 + 8u * (3 * TC_STAGES + a); };
+  auto bar_acce = [&](int a) { return bar0 + 8u * (3 * TC_STAGES + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + TC_STAGES * TC_STAGE_BYTES + 2 * TC_MAXK * 4 + 8 * (3 * TC_STAGES + 4));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int KB = (p.Kd + TC_BK - 1) / TC_BK;
+
+  if (tid == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_ready(s), 8);
+      mbar_init(bar_empty(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_accf(a), 1);
+      mbar_init(bar_acce(a), 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    fence_proxy_async();
+  }
+  if (warp == TC_W_TMA) {  // TMEM allocation: 512 columns (2 accumulator buffers)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == TC_W_TMA) {
+    // =========================================================================== TMA producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+        const int ob = tile % P.n_ob, rest = tile / P.n_ob;
+        const int tt = rest % P.n_tt, n = rest / P.n_tt;
+        const int o0 = ob * TC_BM, t0 = tt * TC_BN;
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % TC_STAGES;
+          const uint32_t ph = (it / TC_STAGES) & 1;
+          mbar_wait(bar_empty(s), ph ^ 1);
+          const uint32_t sb = base + s * TC_STAGE_BYTES;
+          mbar_expect_tx(bar_full(s), TC_TX_BYTES);
+          const int k0 = kb * TC_BK;
+#pragma unroll
+          for (int i = 0; i < TC_BM / 32; ++i) {
+            tma_load_2d(sb + TC_OFF_WHI + i * TC_BOX_BYTES, &map_whi, bar_full(s), o0 + 32 * i, k0);
+            tma_load_2d(sb + TC_OFF_WLO + i * TC_BOX_BYTES, &map_wlo, bar_full(s), o0 + 32 * i, k0);
+          }
+#pragma unroll
+          for (int j = 0; j < TC_BN / 32; ++j)
+            tma_load_3d(sb + TC_OFF_XHI + j * TC_BOX_BYTES, &map_x, bar_full(s), t0 + 32 * j, k0, n);
+        }
+      }
+    }
+  } else if (warp == TC_W_MMA) {
+    // =========================================================================== MMA issuer
+    if (lane == 0) {
+      uint32_t it = 0, ti = 0;
+      for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++ti) {
+        const int a = ti & 1;
+        const uint32_t aph = (ti >> 1) & 1;
+        mbar_wait(bar_acce(a), aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + a * TC_BN;
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % TC_STAGES;
+          const uint32_t ph = (it / TC_STAGES) & 1;
+          mbar_wait(bar_ready(s), ph);
+          tc_fence_after();
+          const uint32_t sb = base + s * TC_STAGE_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < TC_BK / 8; ++ks) {
+            const uint64_t a_hi = make_desc_mn_sw128(sb + TC_OFF_WHI + ks * 1024);
+            const uint64_t a_lo = make_desc_mn_sw128(sb + TC_OFF_WLO + ks * 1024);
+            const uint64_t b_hi = make_desc_mn_sw128(sb + TC_OFF_XHI + ks * 1024);
+            const uint64_t b_lo = make_desc_mn_sw128(sb + TC_OFF_XLO + ks * 1024);
+            tc_mma_tf32(d_tmem, a_lo, b_hi, TC_IDESC, (kb | ks) != 0 ? 1u : 0u);
+            tc_mma_tf32(d_tmem, a_hi, b_lo, TC_IDESC, 1u);
+            tc_mma_tf32(d_tmem, a_hi, b_hi, TC_IDESC, 1u);
+          }
+          tc_commit(bar_empty(s));   // stage reusable once these MMAs have read it
+        }
+        tc_commit(bar_accf(a));      // accumulator complete
+      }
+    }
+  } else if (warp >= TC_W_XF) {
+    // =========================================================================== transform warps
+    const int tt_id = tid - TC_W_XF * 32;  // 0..255
+    float alpha = 1.f;
+    if constexpr (PRO >= 1) alpha = p.xf.alpha ? __ldg(p.xf.alpha) : 1.f;
+    uint32_t it = 0;
+    int cur_n = -1;
+    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+      const int n = (tile / P.n_ob) / P.n_tt;
+      if constexpr (PRO == 2) {
+        if (n != cur_n) {  // per-row gLN constants: sc[k] = gamma*rstd, sh[k] = beta - gamma*mean*rstd
+          // all transform warps of this CTA see the same tile sequence: sync them around the table rewrite
+          asm volatile("bar.sync 1, 256;\n" ::: "memory");
+          float mu = 0.f, r = 1.f;
+          if (p.xf.row_stats) gln_mean_rstd(p.xf.row_stats + 2 * n, p.xf.count, p.xf.eps, mu, r);
+          for (int k = tt_id; k < p.Kd; k += 256) {
+            const float gm = p.xf.ch_scale ? __ldg(p.xf.ch_scale + k) : 1.f;
+            const float bt = p.xf.ch_shift ? __ldg(p.xf.ch_shift + k) : 0.f;
+            sc[k] = gm * r;
+            sh[k] = bt - gm * mu * r;
+          }
+          asm volatile("bar.sync 1, 256;\n" ::: "memory");
+          cur_n = n;
+        }
+      }
+      for (int kb = 0; kb < KB; ++kb, ++it) {
+        const int s = it % TC_STAGES;
+        const uint32_t ph = (it / TC_STAGES) & 1;
+        mbar_wait(bar_full(s), ph);
+        uint8_t* xs_hi = gbase + s * TC_STAGE_BYTES + TC_OFF_XHI;
+        uint8_t* xs_lo = gbase + s * TC_STAGE_BYTES + TC_OFF_XLO;
+#pragma unroll
+        for (int i = 0; i < TC_X_BYTES / 16 / 256; ++i) {
+          const int off = (tt_id + 256 * i) * 16;
+          float4 v = *reinterpret_cast<const float4*>(xs_hi + off);
+          if constexpr (PRO >= 1) {
+            float c = 1.f, d = 0.f;
+            if constexpr (PRO == 2) {
+              const int kk = kb * TC_BK + ((off % TC_BOX_BYTES) >> 7);  // row inside the box = channel
+              const bool kok = kk < p.Kd;
+              c = kok ? sc[kk] : 0.f;
+              d = kok ? sh[kk] : 0.f;
+            }
+            v.x = fmaf(c, prelu_f(v.x, alpha), d);
+            v.y = fmaf(c, prelu_f(v.y, alpha), d);
+            v.z = fmaf(c, prelu_f(v.z, alpha), d);
+            v.w = fmaf(c, prelu_f(v.w, alpha), d);
+          }
+          float4 h, l;
+          h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+          h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+          h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+          h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+          if (PRO != 0 || !P.skip_hi_store) *reinterpret_cast<float4*>(xs_hi + off) = h;
+          *reinterpret_cast<float4*>(xs_lo + off) = l;
+        }
+        fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_ready(s));
+      }
+    }
+  } else {
+    // =========================================================================== epilogue warps 0..7
+    const int q = warp & 3;        // TMEM lane quarter this warp may access
+    const int chalf = warp >> 2;   // which 128-column half of the accumulator
+    const EpiP& e = p.ep;
+    uint32_t ti = 0;
+    for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++ti) {
+      const int ob = tile % P.n_ob, rest = tile / P.n_ob;
+      const int tt = rest % P.n_tt, n = rest / P.n_tt;
+      const int o = ob * TC_BM + q * 32 + lane;  // this thread's output channel (M % 128 == 0 => always valid)
+      const int t0 = tt * TC_BN;
+      const int a = ti & 1;
+      const uint32_t aph = (ti >> 1) & 1;
+
+      // per-channel constants
+      float bias_o = 0.f;
+      if (e.bias) bias_o = __ldg(e.bias + o);
+      if (e.row_bias) bias_o += __ldg(e.row_bias + (int64_t)n * p.M + o);
+      float out_alpha = 1.f;
+      if constexpr (EPI == 0) out_alpha = e.out_alpha ? __ldg(e.out_alpha) : 1.f;
+      float mu2 = 0.f, r2 = 1.f, a2 = 1.f, gam2 = 0.f, mh = 0.f, mhy = 0.f, gam1 = 0.f, bet1 = 0.f, bdm = 0.f, w0 = 0.f, w1 = 0.f,
+            w2 = 0.f;
+      if constexpr (EPI == 10) {
+        gln_mean_rstd(e.stats2 + 2 * n, e.count2, e.eps2, mu2, r2);
+        a2 = __ldg(e.a2); gam2 = __ldg(e.g2 + o);
+        mh = (float)e.rowsc[8 * n + 0]; mhy = (float)e.rowsc[8 * n + 1];
+        gam1 = __ldg(e.g1 + o); bet1 = __ldg(e.be1 + o); bdm = __ldg(e.bd + o);
+        w0 = __ldg(e.wd + 3 * o); w1 = __ldg(e.wd + 3 * o + 1); w2 = __ldg(e.wd + 3 * o + 2);
+      }
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+
+      mbar_wait(bar_accf(a), aph);
+      tc_fence_after();
+      float* yrow = e.Y + n * e.bsy + (int64_t)o * e.ldy;
+#pragma unroll 1
+      for (int c0 = chalf * (TC_BN / 2); c0 < (chalf + 1) * (TC_BN / 2); c0 += 32) {
+        if (t0 + c0 >= p.T) break;   // warp-uniform
+        // issue this chunk's global operand loads before the TMEM load so their latency overlaps it
+        float4 gop[8];
+        if constexpr (EPI == 2 || EPI == 10) {
+          const float* gsrc = (EPI == 2) ? (e.R + n * e.bsr + (int64_t)o * e.ldr) : (e.d + n * e.bsd + (int64_t)o * e.ldd);
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const int t = t0 + c0 + 4 * g;
+            gop[g] = (t < p.T) ? *reinterpret_cast<const float4*>(gsrc + t) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        uint32_t r[32];
+        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TC_BN + c0), r);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const int t = t0 + c0 + 4 * g;
+          if (t < p.T) {
+            float v[4] = {__uint_as_float(r[4 * g]) + bias_o, __uint_as_float(r[4 * g + 1]) + bias_o,
+                          __uint_as_float(r[4 * g + 2]) + bias_o, __uint_as_float(r[4 * g + 3]) + bias_o};
+            if constexpr (EPI == 0) {
+              *reinterpret_cast<float4*>(yrow + t) = make_float4(v[0], v[1], v[2], v[3]);
+              if (e.out_stats) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float y = (t + i < p.T) ? prelu_f(v[i], out_alpha) : 0.f;
+                  s0 += y;
+                  s1 = fmaf(y, y, s1);
+                }
+              }
+            } else if constexpr (EPI == 2) {
+              const float4 rr = gop[g];
+              *reinterpret_cast<float4*>(yrow + t) = make_float4(v[0] + rr.x, v[1] + rr.y, v[2] + rr.z, v[3] + rr.w);
+            } else if constexpr (EPI == 10) {
+              const float4 d4 = gop[g];
+              const float draw[4] = {d4.x, d4.y, d4.z, d4.w};
+              float dd[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int tt_ = t + i;
+                const bool ok = tt_ < p.T;
+                // columns >= T are padding (possibly NaN): neutralise the operands, not just the result
+                const float dvi = ok ? draw[i] : 1.f;
+                const float h = ok ? v[i] * gam2 : 0.f;
+                const float y2 = prelu_f(dvi, a2);
+                const float yh = (y2 - mu2) * r2;
+                const float dy2 = r2 * (h - mh - yh * mhy);
+                const float ddv = ok ? dy2 * (dvi > 0.f ? 1.f : a2) : 0.f;
+                dd[i] = ddv;
+                const float kap = w1 + (tt_ >= e.dil ? w0 : 0.f) + (tt_ < p.T - e.dil ? w2 : 0.f);
+                s0 = fmaf(ddv * gam1, kap, s0);
+                s1 = fmaf(ddv, dvi - bdm, s1);
+                s2 = fmaf(ddv * bet1, kap, s2);
+                s3 += (dvi > 0.f || !ok) ? 0.f : dy2 * dvi;
+              }
+              *reinterpret_cast<float4*>(yrow + t) = make_float4(dd[0], dd[1], dd[2], dd[3]);
+            }
+          }
+        }
+      }
+      // release the accumulator buffer to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acce(a));
+      // per-row statistics: one (double) atomic per warp and quantity
+      if constexpr (EPI == 0) {
+        if (e.out_stats) {
+          s0 = warp_sum(s0);
+          s1 = warp_sum(s1);
+          if (lane == 0) {
+            atomicAdd(e.out_stats + 2 * n, (double)s0);
+            atomicAdd(e.out_stats + 2 * n + 1, (double)s1);
+          }
+        }
+      }
+      if constexpr (EPI == 10) {
+        s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
+        if (lane == 0) {
+          atomicAdd(e.rowacc + 8 * n + 2, (double)s0);
+          atomicAdd(e.rowacc + 8 * n + 3, (double)s1);
+          atomicAdd(e.rowacc + 8 * n + 4, (double)s2);
+          atomicAdd(e.rowacc + 8 * n + 5, (double)s3);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == TC_W_TMA) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+static int encode_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(-3, "cuTensorMapEncodeTiled entry point not available");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(ptr), (const cuuint64_t*)dims,
+                  (const cuuint64_t*)strides_bytes, (const cuuint32_t*)box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_err, sizeof(g_err), "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return -3;
+  }
+  return 0;
+}
+
+bool gemm_wx_tc_eligible(const GemmWxP& p, int pro, int epi) {
+  if (p.M % TC_BM || p.Kd % TC_BK || p.Kd > TC_MAXK) return false;
+  if ((p.ldx & 3) || !aligned16(p.X) || (p.bsx & 3)) return false;
+  if (!(pro == 0 || pro == 2)) return false;
+  if (!(epi == 0 || epi == 2 || epi == 10)) return false;
+  if (epi == 0 && p.ep.ch_stats) return false;
+  if ((p.ep.ldy & 3) || !aligned16(p.ep.Y) || (p.ep.bsy & 3)) return false;
+  if (epi == 2 && ((p.ep.ldr & 3) || !aligned16(p.ep.R) || (p.ep.bsr & 3))) return false;
+  if (epi == 10 && ((p.ep.ldd & 3) || !aligned16(p.ep.d) || (p.ep.bsd & 3))) return false;
+  return true;
+}
+
+size_t gemm_wx_tc_ws_bytes(int M, int Kd) { return (size_t)2 * M * Kd * sizeof(float); }
+
+template <int PRO, int EPI>
+static int launch_tc_t(const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& mx, const TcParams& P, cudaStream_t st) {
+  auto k = gemm_wx_tc_kernel<PRO, EPI>;
+  WB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+  static int n_sm = 0;
+  if (!n_sm) {
+    int dev = 0;
+    WB_CUDA(cudaGetDevice(&dev));
+    WB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  }
+  int grid = P.n_tiles < n_sm ? P.n_tiles : n_sm;
+  k<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mh, ml, mx, P);
+  WB_LAUNCH_CHECK("gemm_wx_tc");
+  return 0;
+}
+
+// W is [M][Kd] (ldw) or, a_trans, [Kd][M] (ldw). ws: >= gemm_wx_tc_ws_bytes(M, Kd), 16-byte aligned.
+int launch_gemm_wx_tc(const GemmWxP& p, bool a_trans, int pro, int epi, void* ws, cudaStream_t st) {
+  if (!gemm_wx_tc_eligible(p, pro, epi)) return fail(-2, "gemm_wx_tc: shape/config not eligible");
+  if (!ws || !aligned16(ws)) return fail(-1, "gemm_wx_tc: workspace missing or misaligned");
+  float* whi = reinterpret_cast<float*>(ws);
+  float* wlo = whi + (size_t)p.M * p.Kd;
+  {
+    int total = p.M * p.Kd;
+    split_w_kernel<<<cdiv(total, 256), 256, 0, st>>>(p.W, p.ldw, a_trans ? 1 : 0, p.M, p.Kd, whi, wlo);
+    WB_LAUNCH_CHECK("split_w");
+  }
+  CUtensorMap mh, ml, mx;
+  {
+    uint64_t dims[2] = {(uint64_t)p.M, (uint64_t)p.Kd};
+    uint64_t strides[1] = {(uint64_t)p.M * 4};
+    uint32_t box[2] = {32, TC_BK};
+    if (int rc = encode_map(&mh, whi, 2, dims, strides, box)) return rc;
+    if (int rc = encode_map(&ml, wlo, 2, dims, strides, box)) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)p.T, (uint64_t)p.Kd, (uint64_t)p.n};
+    uint64_t strides[2] = {(uint64_t)p.ldx * 4, (uint64_t)p.bsx * 4};
+    uint32_t box[3] = {32, TC_BK, 1};
+    if (int rc = encode_map(&mx, p.X, 3, dims, strides, box)) return rc;
+  }
+  TcParams P;
+  P.g = p;
+  P.n_ob = p.M / TC_BM;
+  P.n_tt = cdiv(p.T, TC_BN);
+  P.n_tiles = P.n_ob * P.n_tt * p.n;
+  P.skip_hi_store = (g_tc_flags & 1) ? 0 : 1;   // default: raw tile is the hi operand (HW truncates tf32 inputs; measured)
+  if (pro == 0 && epi == 0) return launch_tc_t<0, 0>(mh, ml, mx, P, st);
+  if (pro == 0 && epi == 2) return launch_tc_t<0, 2>(mh, ml, mx, P, st);
+  if (pro == 0 && epi == 10) return launch_tc_t<0, 10>(mh, ml, mx, P, st);
+  if (pro == 2 && epi == 2) return launch_tc_t<2, 2>(mh, ml, mx, P, st);
+  if (pro == 2 && epi == 0) return launch_tc_t<2, 0>(mh, ml, mx, P, st);
+  return fail(-2, "gemm_wx_tc: unsupported (pro, epi)");
+}
+
+}  // namespace wb
+
+extern "C" int wesep_b200_set_tc_flags(int flags) {
+  wb::g_tc_flags = flags;
+  return 0;
+}
+extern "C" int64_t wesep_b200_gemm_ws_bytes(int M, int Kd) { return (int64_t)wb::gemm_wx_tc_ws_bytes(M, Kd); }
+
+// ================================================================================================
+// Weight-gradient GEMM on tcgen05:  C[o][c] += sum_t A[n][o][t] * f(B[n][c][t])   (contraction over time)
+//   D[M = 128 rows of A][N = 256 rows of B] in TMEM; both operands K-major (time contiguous): rows of
+//   16 floats (64 B) with the 64-byte TMA/UMMA swizzle, 8-row atoms of 512 B.  Both operands are
+//   activations, so both are split hi/lo by the transform warps (f = identity or PReLU on B).
+//   One tile (and one K range) per CTA; partial results are added to C with fp32 atomics.
+// ================================================================================================
+namespace wb {
+
+constexpr int DW_BM = 128, DW_BN = 256, DW_BK = 16, DW_STAGES = 4, DW_THREADS = 448;
+constexpr int DW_A_BYTES = DW_BM * DW_BK * 4;   // 8192
+constexpr int DW_B_BYTES = DW_BN * DW_BK * 4;   // 16384
+constexpr int DW_OFF_AHI = 0, DW_OFF_ALO = DW_A_BYTES, DW_OFF_BHI = 2 * DW_A_BYTES, DW_OFF_BLO = 2 * DW_A_BYTES + DW_B_BYTES;
+constexpr int DW_STAGE_BYTES = 2 * DW_A_BYTES + 2 * DW_B_BYTES;  // 49152
+constexpr int DW_TX_BYTES = DW_A_BYTES + DW_B_BYTES;
+constexpr int DW_SMEM_BYTES = DW_STAGES * DW_STAGE_BYTES + 256 + 1024;
+
+// K-major operand, SWIZZLE_64B: rows of 64 B, 8-row atoms (512 B) -> SBO = 512 B; LBO unused (1).
+__device__ __forceinline__ uint64_t make_desc_k_sw64(uint32_t saddr) {
+  uint64_t d = (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
+// D=f32, A=B=tf32, both K-major, N=256, M=128
+constexpr uint32_t DW_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(DW_BN >> 3) << 17) | ((uint32_t)(DW_BM >> 4) << 24);
+
+struct DwTcParams {
+  GemmDwP g;
+  int n_ob, n_cb, ksplit, kb_per_split;
+  int skip_hi_store;
+};
+
+template <int PRO_B>
+__global__ void __launch_bounds__(DW_THREADS, 1)
+    gemm_dw_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const DwTcParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const GemmDwP& p = P.g;
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw);
+  const uint32_t bar0 = base + DW_STAGES * DW_STAGE_BYTES;
+  auto bar_full = [&](int s) { return bar0 + 8u * s; };
+  auto bar_ready = [&](int s) { return bar0 + 8u * (DW_STAGES + s); };
+  auto bar_empty = [&](int s) { return bar0 + 8u * (2 * DW_STAGES + s); };
+  const uint32_t bar_accf = bar0 + 8u * (3 * DW_STAGES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + DW_STAGES * DW_STAGE_BYTES + 8 * (3 * DW_STAGES + 1));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // tile decode: blockIdx.x = ((row * ksplit + ks) * n_cb + cb) * n_ob + ob
+  int b = blockIdx.x;
+  const int ob = b % P.n_ob; b /= P.n_ob;
+  const int cb = b % P.n_cb; b /= P.n_cb;
+  const int ksp = b % P.ksplit;
+  const int row = b / P.ksplit;
+  const int KBT = (p.T + DW_BK - 1) / DW_BK;
+  const int kb0 = ksp * P.kb_per_split;
+  const int kb1 = min(kb0 + P.kb_per_split, KBT);
+  const int KB = max(kb1 - kb0, 0);
+
+  if (tid == 0) {
+    for (int s = 0; s < DW_STAGES; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_ready(s), 8);
+      mbar_init(bar_empty(s), 1);
+    }
+    mbar_init(bar_accf, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    fence_proxy_async();
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (KB > 0) {
+    if (warp == 4) {
+      if (lane == 0) {
+        for (int it = 0; it < KB; ++it) {
+          const int s = it % DW_STAGES;
+          const uint32_t ph = (it / DW_STAGES) & 1;
+          mbar_wait(bar_empty(s), ph ^ 1);
+          const uint32_t sb = base + s * DW_STAGE_BYTES;
+          mbar_expect_tx(bar_full(s), DW_TX_BYTES);
+          const int t0 = (kb0 + it) * DW_BK;
+          tma_load_3d(sb + DW_OFF_AHI, &map_a, bar_full(s), t0, ob * DW_BM, row);
+          tma_load_3d(sb + DW_OFF_BHI, &map_b, bar_full(s), t0, cb * DW_BN, row);
+        }
+      }
+    } else if (warp == 5) {
+      if (lane == 0) {
+        for (int it = 0; it < KB; ++it) {
+          const int s = it % DW_STAGES;
+          const uint32_t ph = (it / DW_STAGES) & 1;
+          mbar_wait(bar_ready(s), ph);
+          tc_fence_after();
+          const uint32_t sb = base + s * DW_STAGE_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < DW_BK / 8; ++ks) {
+            const uint64_t a_hi = make_desc_k_sw64(sb + DW_OFF_AHI + ks * 32);
+            const uint64_t a_lo = make_desc_k_sw64(sb + DW_OFF_ALO + ks * 32);
+            const uint64_t b_hi = make_desc_k_sw64(sb + DW_OFF_BHI + ks * 32);
+            const uint64_t b_lo = make_desc_k_sw64(sb + DW_OFF_BLO + ks * 32);
+            tc_mma_tf32(tmem_base, a_lo, b_hi, DW_IDESC, (it | ks) != 0 ? 1u : 0u);
+            tc_mma_tf32(tmem_base, a_hi, b_lo, DW_IDESC, 1u);
+            tc_mma_tf32(tmem_base, a_hi, b_hi, DW_IDESC, 1u);
+          }
+          tc_commit(bar_empty(s));
+        }
+        tc_commit(bar_accf);
+      }
+    } else if (warp >= 6) {
+      const int tt_id = tid - 6 * 32;
+      float alpha = 1.f;
+      if constexpr (PRO_B == 1) alpha = p.xb.alpha ? __ldg(p.xb.alpha) : 1.f;
+      for (int it = 0; it < KB; ++it) {
+        const int s = it % DW_STAGES;
+        const uint32_t ph = (it / DW_STAGES) & 1;
+        mbar_wait(bar_full(s), ph);
+        uint8_t* st = gbase + s * DW_STAGE_BYTES;
+#pragma unroll
+        for (int i = 0; i < (DW_A_BYTES + DW_B_BYTES) / 16 / 256; ++i) {
+          const int idx = tt_id + 256 * i;              // float4 index over [A tile | B tile]
+          const bool is_b = idx >= DW_A_BYTES / 16;
+          const int off = is_b ? (idx * 16 - DW_A_BYTES) : idx * 16;
+          uint8_t* hi_p = st + (is_b ? DW_OFF_BHI : DW_OFF_AHI) + off;
+          uint8_t* lo_p = st + (is_b ? DW_OFF_BLO : DW_OFF_ALO) + off;
+          float4 v = *reinterpret_cast<const float4*>(hi_p);
+          if constexpr (PRO_B == 1) {
+            if (is_b) { v.x = prelu_f(v.x, alpha); v.y = prelu_f(v.y, alpha); v.z = prelu_f(v.z, alpha); v.w = prelu_f(v.w, alpha); }
+          }
+          float4 h, l;
+          h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+          h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+          h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+          h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+          if (!P.skip_hi_store || (PRO_B == 1 && is_b)) *reinterpret_cast<float4*>(hi_p) = h;
+          *reinterpret_cast<float4*>(lo_p) = l;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_ready(s));
+      }
+    } else {
+      // epilogue warps 0..3: C[o][c] += D
+      const int q = warp;
+      const int o = ob * DW_BM + q * 32 + lane;
+      float* C = p.C + (p.per_row ? (int64_t)row * p.M * p.ldc : 0) + (int64_t)o * p.ldc + cb * DW_BN;
+      mbar_wait(bar_accf, 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < DW_BN; c0 += 32) {
+        uint32_t r[32];
+        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) atomicAdd(C + c0 + i, __uint_as_float(r[i]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(256u) : "memory");
+  }
+}
+
+static int encode_map_sw(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                         const uint32_t* box, CUtensorMapSwizzle sw) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(-3, "cuTensorMapEncodeTiled entry point not available");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(ptr), (const cuuint64_t*)dims,
+                  (const cuuint64_t*)strides_bytes, (const cuuint32_t*)box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_err, sizeof(g_err), "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return -3;
+  }
+  return 0;
+}
+
+bool gemm_dw_tc_eligible(const GemmDwP& p, int pro_b) {
+  if (p.M % DW_BM || p.N % DW_BN) return false;
+  if (!(pro_b == 0 || pro_b == 1)) return false;
+  if ((p.lda & 3) || (p.ldb & 3) || (p.bsa & 3) || (p.bsb & 3) || !aligned16(p.A) || !aligned16(p.B)) return false;
+  return true;
+}
+
+int launch_gemm_dw_tc(const GemmDwP& p, int pro_b, cudaStream_t st) {
+  if (!gemm_dw_tc_eligible(p, pro_b)) return fail(-2, "gemm_dw_tc: not eligible");
+  CUtensorMap ma, mb;
+  {
+    uint64_t dims[3] = {(uint64_t)p.T, (uint64_t)p.M, (uint64_t)p.n};
+    uint64_t strides[2] = {(uint64_t)p.lda * 4, (uint64_t)p.bsa * 4};
+    uint32_t box[3] = {DW_BK, DW_BM, 1};
+    if (int rc = encode_map_sw(&ma, p.A, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)p.T, (uint64_t)p.N, (uint64_t)p.n};
+    uint64_t strides[2] = {(uint64_t)p.ldb * 4, (uint64_t)p.bsb * 4};
+    uint32_t box[3] = {DW_BK, DW_BN, 1};
+    if (int rc = encode_map_sw(&mb, p.B, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
+  }
+  DwTcParams P;
+  P.g = p;
+  P.n_ob = p.M / DW_BM;
+  P.n_cb = p.N / DW_BN;
+  const int tiles = P.n_ob * P.n_cb * p.n;
+  const int KBT = cdiv(p.T, DW_BK);
+  int ksplit = tiles >= 100 ? 1 : (148 + tiles - 1) / tiles;
+  if (ksplit > KBT / 8) ksplit = KBT / 8 > 0 ? KBT / 8 : 1;     // keep >= 8 k-blocks per CTA
+  P.kb_per_split = cdiv(KBT, ksplit);
+  P.ksplit = cdiv(KBT, P.kb_per_split);
+  P.skip_hi_store = (g_tc_flags & 1) ? 0 : 1;
+  const int grid = tiles * P.ksplit;
+  if (pro_b == 0) {
+    auto k = gemm_dw_tc_kernel<0>;
+    WB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM_BYTES));
+    k<<<grid, DW_THREADS, DW_SMEM_BYTES, st>>>(ma, mb, P);
+  } else {
+    auto k = gemm_dw_tc_kernel<1>;
+    WB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM_BYTES));
+    k<<<grid, DW_THREADS, DW_SMEM_BYTES, st>>>(ma, mb, P);
+  }
+  WB_LAUNCH_CHECK("gemm_dw_tc");
+  return 0;
+}
+
+}  // namespace wb

@@ -335,6 +335,7 @@ extern "C" int wesep_b200_tcn_block_fwd(const WesepTcnFwdArgs* ap, void* stream)
     p.ep.Y = a.u; p.ep.ldy = a.ld; p.ep.bsy = (int64_t)a.H * a.ld;
     p.ep.bias = a.b1; p.ep.row_bias = a.aux ? a.row_bias : nullptr;
     p.ep.out_stats = a.stats1; p.ep.out_alpha = a.a1;
+    p.ws = a.ws; p.ws_bytes = a.ws_bytes;
     if (int rc = launch_gemm_wx(p, false, 0, 0, st)) return rc;
   }
   {  // K3: depthwise dilated conv on gLN1(prelu(u)); gLN2 statistics
@@ -353,6 +354,7 @@ extern "C" int wesep_b200_tcn_block_fwd(const WesepTcnFwdArgs* ap, void* stream)
     p.ep.Y = a.out; p.ep.ldy = a.ld; p.ep.bsy = (int64_t)a.B * a.ld;
     p.ep.bias = a.b3;
     p.ep.R = a.x; p.ep.ldr = a.ld; p.ep.bsr = (int64_t)a.B * a.ld;
+    p.ws = a.ws; p.ws_bytes = a.ws_bytes;
     if (int rc = launch_gemm_wx(p, false, 2, 2, st)) return rc;
   }
   return 0;
@@ -398,6 +400,7 @@ extern "C" int wesep_b200_tcn_block_bwd(const WesepTcnBwdArgs* bp, void* stream)
     e.a2 = a.a2; e.g2 = a.g2; e.stats2 = a.stats2; e.count2 = count; e.eps2 = GLN_EPS;
     e.rowsc = b.rowsc; e.rowacc = b.rowsc;
     e.g1 = a.g1; e.be1 = a.be1; e.bd = a.bd; e.wd = a.wd; e.dil = a.dil;
+    p.ws = a.ws; p.ws_bytes = a.ws_bytes;
     if (int rc = launch_gemm_wx(p, true, 0, 10, st)) return rc;
   }
   {  // B3: depthwise conv + gLN1 + PReLU_1 backward
@@ -415,6 +418,7 @@ extern "C" int wesep_b200_tcn_block_bwd(const WesepTcnBwdArgs* bp, void* stream)
     p.W = a.W1; p.ldw = a.ldw1; p.X = b.du; p.ldx = a.ld; p.bsx = (int64_t)a.H * a.ld;
     p.ep.Y = b.dx; p.ep.ldy = a.ld; p.ep.bsy = (int64_t)a.B * a.ld;
     p.ep.R = b.gout; p.ep.ldr = a.ld; p.ep.bsr = (int64_t)a.B * a.ld;
+    p.ws = a.ws; p.ws_bytes = a.ws_bytes;
     if (int rc = launch_gemm_wx(p, true, 0, 2, st)) return rc;
   }
   {  // dW1[:, :B] += sum_n sum_t du x^T

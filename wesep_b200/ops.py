@@ -31,6 +31,19 @@ def _args(name, **kw):
     return s
 
 
+_WS = {}
+
+
+def gemm_ws(device, nbytes=8 << 20):
+    """Per-device scratch for the tcgen05 GEMMs' split-weight copies (all launches are stream-ordered)."""
+    key = (device.type, device.index)
+    t = _WS.get(key)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _WS[key] = t
+    return t
+
+
 def _check_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -104,6 +117,8 @@ def conv1x1_raw(x, W2d, w_trans, M, *, bias=None, row_bias=None, pro=0, alpha=No
               R=R, ldr=0 if R is None else R.stride(1), Y2=Y2, ldy2=0 if Y2 is None else Y2.stride(1),
               out_stats=out_stats, out_alpha=out_alpha, ch_stats=ch_stats, bsx=x.stride(0), bsy=Y.stride(0),
               bsr=0 if R is None else R.stride(0), bsy2=0 if Y2 is None else Y2.stride(0))
+    ws = gemm_ws(x.device)
+    a.ws, a.ws_bytes = ws.data_ptr(), ws.numel()
     for t_ in (x, Y, R, Y2):
         if t_ is not None and not is_act_slice(t_):
             raise RuntimeError("conv1x1: operand is not in act layout")
@@ -170,6 +185,8 @@ class TCNBlockFn(torch.autograd.Function):
         fa = _args("WesepTcnFwdArgs", n=n, B=B, H=H, T=T, dil=int(dil), E=E, ld=x.stride(1), x=x, aux=auxc, W1=W1c,
                    ldw1=W1c.stride(0), W3=W3c, ldw3=W3c.stride(0), u=u, d=d, out=out, stats1=stats[0], stats2=stats[1],
                    row_bias=row_bias, **P)
+        ws = gemm_ws(dev)
+        fa.ws, fa.ws_bytes = ws.data_ptr(), ws.numel()
         if u.stride(1) != x.stride(1):
             raise RuntimeError("TCN block: inconsistent row strides")
         _lib.call("wesep_b200_tcn_block_fwd", fa, _stream())
@@ -207,6 +224,8 @@ class TCNBlockFn(torch.autograd.Function):
         fa = _args("WesepTcnFwdArgs", n=n, B=B, H=H, T=T, dil=ctx.dil, E=E, ld=x.stride(1), x=x, aux=auxc, W1=W1c,
                    ldw1=W1c.stride(0), b1=b1, a1=a1, g1=g1, be1=be1, wd=wd, bd=bd, a2=a2, g2=g2, be2=be2, W3=W3c,
                    ldw3=W3c.stride(0), b3=b3, u=u, d=d, out=None, stats1=stats[0], stats2=stats[1], row_bias=None)
+        ws = gemm_ws(dev)
+        fa.ws, fa.ws_bytes = ws.data_ptr(), ws.numel()
         ba = _args("WesepTcnBwdArgs", gout=gout, dx=dx, dW1=dW1, db1=db1, da1=da1, dg1=dg1, dbe1=dbe1, dwd=dwd, dbd=dbd,
                    da2=da2, dg2=dg2, dbe2=dbe2, dW3=dW3, db3=db3, daux=daux, dd=dd, du=du, Gn=Gn, sg=sg, sdu=sdu,
                    rowsc=rowsc)
