@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(G_THREADS, 2) gemm_wx_kernel(const GemmWxP p) 
           float mu2, r2;
           gln_mean_rstd(e.stats2 + 2 * n, e.count2, e.eps2, mu2, r2);
           const float a2 = __ldg(e.a2), gam2 = __ldg(e.g2 + m);
-          const float mh = (float)e.rowsc[8 * n + 0], mhy = (float)e.rowsc[8 * n + 1];
+          const float mh = (float)(e.rowsc[8 * n + 0] / e.count2), mhy = (float)(e.rowsc[8 * n + 1] / e.count2);
           const float gam1 = __ldg(e.g1 + m), bet1 = __ldg(e.be1 + m), bdm = __ldg(e.bd + m);
           const float w0 = __ldg(e.wd + 3 * m), w1 = __ldg(e.wd + 3 * m + 1), w2 = __ldg(e.wd + 3 * m + 2);
           const float* drow = e.d + n * e.bsd + (int64_t)m * e.ldd;

@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       if constexpr (EPI == 10) {
         gln_mean_rstd(e.stats2 + 2 * n, e.count2, e.eps2, mu2, r2);
         a2 = __ldg(e.a2); gam2 = __ldg(e.g2 + o);
-        mh = (float)e.rowsc[8 * n + 0]; mhy = (float)e.rowsc[8 * n + 1];
+        mh = (float)(e.rowsc[8 * n + 0] / e.count2); mhy = (float)(e.rowsc[8 * n + 1] / e.count2);
         gam1 = __ldg(e.g1 + o); bet1 = __ldg(e.be1 + o); bdm = __ldg(e.bd + o);
         w0 = __ldg(e.wd + 3 * o); w1 = __ldg(e.wd + 3 * o + 1); w2 = __ldg(e.wd + 3 * o + 2);
       }

@@ -23,7 +23,7 @@ struct StFwdP {
   const double* stats1; double* stats2; double count;
 };
 
-__global__ void __launch_bounds__(ST_THREADS) tcn_dw_fwd_kernel(const StFwdP p) {
+__global__ void __launch_bounds__(ST_THREADS) tcn_dw_fwd_generic_kernel(const StFwdP p) {
   extern __shared__ float z[];  // [ST_CH][ST_TT + 2*dil]
   __shared__ float red[2 * 32];
   const int tid = threadIdx.x, sub = tid & 63, chl = tid >> 6;
@@ -82,7 +82,7 @@ struct StBwdP {
   float* sdu;                    // += [n][H] sum_t du
 };
 
-__global__ void __launch_bounds__(ST_THREADS) tcn_dw_bwd_kernel(const StBwdP p) {
+__global__ void __launch_bounds__(ST_THREADS) tcn_dw_bwd_generic_kernel(const StBwdP p) {
   extern __shared__ float sm[];  // dds[CH][W], z1s[CH][W], us[CH][TT]
   __shared__ float red[32];
   __shared__ float chred[ST_CH][2][8];
@@ -175,6 +175,245 @@ __global__ void __launch_bounds__(ST_THREADS) tcn_dw_bwd_kernel(const StBwdP p) 
   }
 }
 
+
+// ------------------------------------------------------------------------------------ vectorised stencils
+// Same math as the *_generic kernels above, 4 consecutive time steps per thread: 128-bit global loads / stores,
+// 128-bit shared-memory tap loads.  DM = 0: dilation is a multiple of 4 (taps are 16-byte aligned);
+// DM = 1,2,3: dilation == DM (taps assembled from the previous / centre / next vectors).
+template <int DM>
+__device__ __forceinline__ void taps4(const float* c_ptr, int dil, float (&L)[4], float (&C)[4], float (&R)[4]) {
+  const float4 c = *reinterpret_cast<const float4*>(c_ptr);
+  C[0] = c.x; C[1] = c.y; C[2] = c.z; C[3] = c.w;
+  if constexpr (DM == 0) {
+    const float4 l = *reinterpret_cast<const float4*>(c_ptr - dil);
+    const float4 r = *reinterpret_cast<const float4*>(c_ptr + dil);
+    L[0] = l.x; L[1] = l.y; L[2] = l.z; L[3] = l.w;
+    R[0] = r.x; R[1] = r.y; R[2] = r.z; R[3] = r.w;
+  } else {
+    const float4 p = *reinterpret_cast<const float4*>(c_ptr - 4);
+    const float4 n = *reinterpret_cast<const float4*>(c_ptr + 4);
+    const float a[12] = {p.x, p.y, p.z, p.w, c.x, c.y, c.z, c.w, n.x, n.y, n.z, n.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      L[i] = a[4 + i - DM];
+      R[i] = a[4 + i + DM];
+    }
+  }
+}
+
+template <int DM>
+__global__ void __launch_bounds__(ST_THREADS) tcn_dw_fwd_kernel(const StFwdP p) {
+  extern __shared__ __align__(16) float z[];  // [ST_CH][RW], RW = ST_TT + 2*halo
+  __shared__ float red[2 * 32];
+  const int tid = threadIdx.x, sub = tid & 63, chl = tid >> 6;
+  const int t0 = blockIdx.x * ST_TT, c = blockIdx.y * ST_CH + chl, n = blockIdx.z;
+  const int dil = p.dil, halo = DM == 0 ? dil : 4, RW = ST_TT + 2 * halo;
+  float s = 0.f, q = 0.f;
+  float* zr = z + chl * RW;
+  if (c < p.H) {
+    float mu, r;
+    gln_mean_rstd(p.stats1 + 2 * n, p.count, GLN_EPS, mu, r);
+    const float a1 = __ldg(p.a1), gm = __ldg(p.g1 + c), bt = __ldg(p.be1 + c);
+    const float sc = gm * r, sh = bt - gm * mu * r;
+    const float* urow = p.u + ((int64_t)n * p.H + c) * p.ld;
+    for (int j = 4 * sub; j < RW; j += 256) {
+      const int t = t0 - halo + j;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t >= 0 && t < p.T) {
+        const float4 u4 = __ldg(reinterpret_cast<const float4*>(urow + t));
+        v.x = fmaf(sc, prelu_f(u4.x, a1), sh);
+        v.y = t + 1 < p.T ? fmaf(sc, prelu_f(u4.y, a1), sh) : 0.f;
+        v.z = t + 2 < p.T ? fmaf(sc, prelu_f(u4.z, a1), sh) : 0.f;
+        v.w = t + 3 < p.T ? fmaf(sc, prelu_f(u4.w, a1), sh) : 0.f;
+      }
+      *reinterpret_cast<float4*>(zr + j) = v;
+    }
+  }
+  __syncthreads();
+  if (c < p.H) {
+    const float w0 = __ldg(p.wd + 3 * c), w1 = __ldg(p.wd + 3 * c + 1), w2 = __ldg(p.wd + 3 * c + 2);
+    const float bd = __ldg(p.bd + c), a2 = __ldg(p.a2);
+    float* drow = p.d + ((int64_t)n * p.H + c) * p.ld;
+#pragma unroll 2
+    for (int i = 4 * sub; i < ST_TT; i += 256) {
+      const int t = t0 + i;
+      if (t < p.T) {
+        float L[4], C[4], R[4], o[4];
+        taps4<DM>(zr + halo + i, dil, L, C, R);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          o[k] = fmaf(w0, L[k], fmaf(w1, C[k], fmaf(w2, R[k], bd)));
+          const float y = (t + k < p.T) ? prelu_f(o[k], a2) : 0.f;
+          s += y;
+          q = fmaf(y, y, q);
+        }
+        *reinterpret_cast<float4*>(drow + t) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+  float v[2] = {s, q};
+  block_sum<2>(v, red);
+  if (tid == 0) {
+    atomicAdd(p.stats2 + 2 * n, (double)v[0]);
+    atomicAdd(p.stats2 + 2 * n + 1, (double)v[1]);
+  }
+}
+
+template <int DM>
+__global__ void __launch_bounds__(ST_THREADS) tcn_dw_bwd_kernel(const StBwdP p) {
+  extern __shared__ __align__(16) float sm[];  // dds[CH][RW], z1s[CH][RW], us[CH][TTB]
+  __shared__ float red[32];
+  __shared__ float chred[ST_CH][2][8];
+  const int tid = threadIdx.x, sub = tid & 63, chl = tid >> 6, lane = tid & 31;
+  const int t0 = blockIdx.x * ST_TTB, c = blockIdx.y * ST_CH + chl, n = blockIdx.z;
+  const int dil = p.dil, halo = DM == 0 ? dil : 4, RW = ST_TTB + 2 * halo;
+  float* dds = sm + chl * RW;
+  float* z1s = sm + ST_CH * RW + chl * RW;
+  float* us = sm + 2 * ST_CH * RW + chl * ST_TTB;
+  float mu = 0.f, r = 1.f, a1 = 1.f, gm = 0.f;
+  if (c < p.H) {
+    gln_mean_rstd(p.stats1 + 2 * n, p.count, GLN_EPS, mu, r);
+    a1 = __ldg(p.a1);
+    gm = __ldg(p.g1 + c);
+    const float bt = __ldg(p.be1 + c);
+    const float sc = gm * r, sh = bt - gm * mu * r;
+    const float* urow = p.u + ((int64_t)n * p.H + c) * p.ld;
+    const float* drow = p.dd + ((int64_t)n * p.H + c) * p.ld;
+    for (int j = 4 * sub; j < RW; j += 256) {
+      const int t = t0 - halo + j;
+      float4 dv = make_float4(0.f, 0.f, 0.f, 0.f), zv = dv, uv = dv;
+      if (t >= 0 && t < p.T) {
+        const float4 d4 = __ldg(reinterpret_cast<const float4*>(drow + t));
+        uv = __ldg(reinterpret_cast<const float4*>(urow + t));
+        const bool k1 = t + 1 < p.T, k2 = t + 2 < p.T, k3 = t + 3 < p.T;
+        dv.x = d4.x; dv.y = k1 ? d4.y : 0.f; dv.z = k2 ? d4.z : 0.f; dv.w = k3 ? d4.w : 0.f;
+        zv.x = fmaf(sc, prelu_f(uv.x, a1), sh);
+        zv.y = k1 ? fmaf(sc, prelu_f(uv.y, a1), sh) : 0.f;
+        zv.z = k2 ? fmaf(sc, prelu_f(uv.z, a1), sh) : 0.f;
+        zv.w = k3 ? fmaf(sc, prelu_f(uv.w, a1), sh) : 0.f;
+        if (!k1) uv.y = 1.f;   // padding: harmless finite values
+        if (!k2) uv.z = 1.f;
+        if (!k3) uv.w = 1.f;
+      }
+      *reinterpret_cast<float4*>(dds + j) = dv;
+      *reinterpret_cast<float4*>(z1s + j) = zv;
+      const int jc = j - halo;
+      if (jc >= 0 && jc < ST_TTB) *reinterpret_cast<float4*>(us + jc) = uv;
+    }
+  }
+  __syncthreads();
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  float dal = 0.f;
+  if (c < p.H) {
+    const double Mc = p.count;
+    const float m1 = (float)(p.rowacc[8 * n + 2] / Mc);
+    const float m2 = (float)((p.rowacc[8 * n + 3] - p.rowacc[8 * n + 4]) / Mc);
+    const float w0 = __ldg(p.wd + 3 * c), w1 = __ldg(p.wd + 3 * c + 1), w2 = __ldg(p.wd + 3 * c + 2);
+    float* durow = p.du + ((int64_t)n * p.H + c) * p.ld;
+    for (int i = 4 * sub; i < ST_TTB; i += 256) {
+      const int t = t0 + i;
+      if (t < p.T) {
+        float dL[4], dC[4], dR[4], zL[4], zC[4], zR[4], o[4];
+        taps4<DM>(dds + halo + i, dil, dL, dC, dR);
+        taps4<DM>(z1s + halo + i, dil, zL, zC, zR);
+        const float4 u4 = *reinterpret_cast<const float4*>(us + i);
+        const float uu[4] = {u4.x, u4.y, u4.z, u4.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const bool ok = t + k < p.T;
+          const float ddv = dC[k];                                    // 0 beyond T (masked at fill)
+          const float dz = fmaf(w0, dR[k], fmaf(w1, ddv, w2 * dL[k]));  // dz1[t] = sum_j w[j] dd[t - (j-1) dil]
+          const float uv = uu[k];
+          const float yh = (prelu_f(uv, a1) - mu) * r;
+          const float dy = r * (gm * dz - m1 - yh * m2);
+          const float duv = ok ? dy * (uv > 0.f ? 1.f : a1) : 0.f;
+          o[k] = duv;
+          if (ok) {
+            acc[0] += dz;
+            acc[1] = fmaf(dz, yh, acc[1]);
+            acc[2] = fmaf(ddv, zL[k], acc[2]);
+            acc[3] = fmaf(ddv, zC[k], acc[3]);
+            acc[4] = fmaf(ddv, zR[k], acc[4]);
+            acc[5] += ddv;
+            acc[6] += duv;
+            dal += uv > 0.f ? 0.f : dy * uv;
+          }
+        }
+        *reinterpret_cast<float4*>(durow + t) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 7; ++i) acc[i] = warp_sum(acc[i]);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 7; ++i) chred[chl][(tid >> 5) & 1][i] = acc[i];
+  }
+  float v[1] = {dal};
+  block_sum<1>(v, red);
+  if (tid == 0 && v[0] != 0.f) atomicAdd(p.da1, v[0]);
+  if (sub == 0 && c < p.H) {
+    float r7[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) r7[i] = chred[chl][0][i] + chred[chl][1][i];
+    atomicAdd(p.dbe1 + c, r7[0]);
+    atomicAdd(p.dg1 + c, r7[1]);
+    atomicAdd(p.dwd + 3 * c + 0, r7[2]);
+    atomicAdd(p.dwd + 3 * c + 1, r7[3]);
+    atomicAdd(p.dwd + 3 * c + 2, r7[4]);
+    atomicAdd(p.dbd + c, r7[5]);
+    atomicAdd(p.sdu + (int64_t)n * p.H + c, r7[6]);
+  }
+}
+
+static int launch_dw_fwd(const StFwdP& p, cudaStream_t st) {
+  dim3 grid(cdiv(p.T, ST_TT), cdiv(p.H, ST_CH), p.n);
+  const int dm = (p.dil % 4 == 0) ? 0 : (p.dil <= 3 ? p.dil : -1);
+  if (dm < 0) {
+    size_t smem = (size_t)ST_CH * (ST_TT + 2 * p.dil) * sizeof(float);
+    WB_CUDA(cudaFuncSetAttribute(tcn_dw_fwd_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tcn_dw_fwd_generic_kernel<<<grid, ST_THREADS, smem, st>>>(p);
+  } else {
+    const int halo = dm == 0 ? p.dil : 4;
+    size_t smem = (size_t)ST_CH * (ST_TT + 2 * halo) * sizeof(float);
+    auto launch = [&](auto k) -> int {
+      WB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k<<<grid, ST_THREADS, smem, st>>>(p);
+      return 0;
+    };
+    int rc = dm == 0 ? launch(tcn_dw_fwd_kernel<0>) : dm == 1 ? launch(tcn_dw_fwd_kernel<1>)
+                     : dm == 2 ? launch(tcn_dw_fwd_kernel<2>) : launch(tcn_dw_fwd_kernel<3>);
+    if (rc) return rc;
+  }
+  WB_LAUNCH_CHECK("tcn_dw_fwd");
+  return 0;
+}
+
+static int launch_dw_bwd(const StBwdP& p, cudaStream_t st) {
+  dim3 grid(cdiv(p.T, ST_TTB), cdiv(p.H, ST_CH), p.n);
+  const int dm = (p.dil % 4 == 0) ? 0 : (p.dil <= 3 ? p.dil : -1);
+  if (dm < 0) {
+    size_t smem = (size_t)ST_CH * (2 * (ST_TTB + 2 * p.dil) + ST_TTB) * sizeof(float);
+    WB_CUDA(cudaFuncSetAttribute(tcn_dw_bwd_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tcn_dw_bwd_generic_kernel<<<grid, ST_THREADS, smem, st>>>(p);
+  } else {
+    const int halo = dm == 0 ? p.dil : 4;
+    size_t smem = (size_t)ST_CH * (2 * (ST_TTB + 2 * halo) + ST_TTB) * sizeof(float);
+    auto launch = [&](auto k) -> int {
+      WB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k<<<grid, ST_THREADS, smem, st>>>(p);
+      return 0;
+    };
+    int rc = dm == 0 ? launch(tcn_dw_bwd_kernel<0>) : dm == 1 ? launch(tcn_dw_bwd_kernel<1>)
+                     : dm == 2 ? launch(tcn_dw_bwd_kernel<2>) : launch(tcn_dw_bwd_kernel<3>);
+    if (rc) return rc;
+  }
+  WB_LAUNCH_CHECK("tcn_dw_bwd");
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------ small kernels
 // out[n][c] = sum_t x[n][c][t]; one warp per row.
 __global__ void rowsum_kernel(const float* x, int64_t ld, int rows, int T, float* out) {
@@ -201,57 +440,73 @@ struct F2P {
   float* dW3; float* dg2; float* dbe2; float* db3;
 };
 __global__ void __launch_bounds__(256) tcn_f2a_kernel(const F2P p) {
+  // grid (cdiv(H,64), n): thread = (channel c, 1 of 4 o-groups); raw sums -> rowsc[8n+0], [8n+1] (double atomics)
   __shared__ float red[2 * 32];
-  const int n = blockIdx.x, tid = threadIdx.x;
+  const int n = blockIdx.y, tid = threadIdx.x;
+  const int c = blockIdx.x * 64 + (tid & 63), og = tid >> 6;
   float mu, r;
   gln_mean_rstd(p.stats2 + 2 * n, p.count, GLN_EPS, mu, r);
   const float* G = p.Gn + (int64_t)n * p.B * p.H;
   const float* sg = p.sg + (int64_t)n * p.B;
   float s1 = 0.f, s2 = 0.f;
-  for (int c = tid; c < p.H; c += 256) {
-    const float gm = __ldg(p.g2 + c);
+  if (c < p.H) {
     float a = 0.f, b = 0.f;
-    for (int o = 0; o < p.B; ++o) {
+#pragma unroll 4
+    for (int o = og; o < p.B; o += 4) {
       const float w = __ldg(p.W3 + (int64_t)o * p.ldw3 + c);
-      const float sgo = sg[o];
+      const float sgo = __ldg(sg + o);
       a = fmaf(w, sgo, a);
-      b = fmaf(w, r * (G[(int64_t)o * p.H + c] - mu * sgo), b);
+      b = fmaf(w, r * (__ldg(G + (int64_t)o * p.H + c) - mu * sgo), b);
     }
-    s1 = fmaf(gm, a, s1);
-    s2 = fmaf(gm, b, s2);
+    const float gm = __ldg(p.g2 + c);
+    s1 = gm * a;
+    s2 = gm * b;
   }
   float v[2] = {s1, s2};
   block_sum<2>(v, red);
   if (tid == 0) {
-    p.rowsc[8 * n + 0] = (double)v[0] / p.count;
-    p.rowsc[8 * n + 1] = (double)v[1] / p.count;
-    p.rowsc[8 * n + 6] = (double)mu;
-    p.rowsc[8 * n + 7] = (double)r;
+    atomicAdd(p.rowsc + 8 * n + 0, (double)v[0]);   // sum_{c,t} h        (consumers divide by count)
+    atomicAdd(p.rowsc + 8 * n + 1, (double)v[1]);   // sum_{c,t} h*yhat2
+    if (blockIdx.x == 0) {
+      p.rowsc[8 * n + 6] = (double)mu;
+      p.rowsc[8 * n + 7] = (double)r;
+    }
   }
 }
-// step 2 (per weight element): dW3, dgamma2, dbeta2, db3. grid (H/128, B/8), block 128: thread <-> c.
+// step 2 (per weight element): dW3, dgamma2, dbeta2, db3. grid (cdiv(H,128), B), block 128: thread <-> (o, c);
+// the n loads per thread are independent (unrolled) so the kernel is bandwidth- not latency-bound.
 __global__ void __launch_bounds__(128) tcn_f2b_kernel(const F2P p) {
   const int c = blockIdx.x * 128 + threadIdx.x;
-  const int o0 = blockIdx.y * 8;
+  const int o = blockIdx.y;
   if (c >= p.H) return;
-  const float gm = __ldg(p.g2 + c), bt = __ldg(p.be2 + c);
-  float dg = 0.f, db = 0.f;
-  for (int o = o0; o < min(o0 + 8, p.B); ++o) {
-    float a1 = 0.f, a2 = 0.f;
-    for (int n = 0; n < p.n; ++n) {
-      const float mu = (float)p.rowsc[8 * n + 6], r = (float)p.rowsc[8 * n + 7];
-      const float sgo = __ldg(p.sg + (int64_t)n * p.B + o);
-      a1 += r * (__ldg(p.Gn + ((int64_t)n * p.B + o) * p.H + c) - mu * sgo);
+  float a1 = 0.f, a2 = 0.f;
+  const float* gp = p.Gn + (int64_t)o * p.H + c;
+  const int64_t gs = (int64_t)p.B * p.H;
+  int n = 0;
+  for (; n + 8 <= p.n; n += 8) {
+    float gv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) gv[j] = __ldg(gp + (n + j) * gs);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float mu = (float)p.rowsc[8 * (n + j) + 6], r = (float)p.rowsc[8 * (n + j) + 7];   // written by tcn_f2a_kernel
+      const float sgo = __ldg(p.sg + (int64_t)(n + j) * p.B + o);
+      a1 = fmaf(r, gv[j] - mu * sgo, a1);
       a2 += sgo;
     }
-    const float w = __ldg(p.W3 + (int64_t)o * p.ldw3 + c);
-    atomicAdd(p.dW3 + (int64_t)o * p.ldw3 + c, gm * a1 + bt * a2);   // sole writer of this element in this call
-    dg = fmaf(w, a1, dg);
-    db = fmaf(w, a2, db);
-    if (c == 0) atomicAdd(p.db3 + o, a2);
   }
-  atomicAdd(p.dg2 + c, dg);
-  atomicAdd(p.dbe2 + c, db);
+  for (; n < p.n; ++n) {
+    const float mu = (float)p.rowsc[8 * n + 6], r = (float)p.rowsc[8 * n + 7];
+    const float sgo = __ldg(p.sg + (int64_t)n * p.B + o);
+    a1 = fmaf(r, __ldg(gp + n * gs) - mu * sgo, a1);
+    a2 += sgo;
+  }
+  const float gm = __ldg(p.g2 + c), bt = __ldg(p.be2 + c);
+  const float w = __ldg(p.W3 + (int64_t)o * p.ldw3 + c);
+  atomicAdd(p.dW3 + (int64_t)o * p.ldw3 + c, gm * a1 + bt * a2);
+  atomicAdd(p.dg2 + c, w * a1);
+  atomicAdd(p.dbe2 + c, w * a2);
+  if (c == 0) atomicAdd(p.db3 + o, a2);
 }
 
 // speaker fold of the fuse block: row_bias[n][h] = sum_e W1[h][B+e] aux[n][e]; one warp per (n,h)
@@ -340,11 +595,7 @@ extern "C" int wesep_b200_tcn_block_fwd(const WesepTcnFwdArgs* ap, void* stream)
   }
   {  // K3: depthwise dilated conv on gLN1(prelu(u)); gLN2 statistics
     StFwdP p{a.n, a.H, a.T, a.dil, a.ld, a.u, a.d, a.a1, a.g1, a.be1, a.wd, a.bd, a.a2, a.stats1, a.stats2, count};
-    dim3 grid(cdiv(a.T, ST_TT), cdiv(a.H, ST_CH), a.n);
-    size_t smem = (size_t)ST_CH * (ST_TT + 2 * a.dil) * sizeof(float);
-    WB_CUDA(cudaFuncSetAttribute(tcn_dw_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tcn_dw_fwd_kernel<<<grid, ST_THREADS, smem, st>>>(p);
-    WB_LAUNCH_CHECK("tcn_dw_fwd");
+    if (int rc = launch_dw_fwd(p, st)) return rc;
   }
   {  // K4: out = x + W3 gLN2(prelu(d)) + b3
     GemmWxP p{};
@@ -385,9 +636,9 @@ extern "C" int wesep_b200_tcn_block_bwd(const WesepTcnBwdArgs* bp, void* stream)
   }
   {
     F2P p{a.n, a.B, a.H, count, b.Gn, b.sg, a.W3, a.ldw3, a.g2, a.be2, a.stats2, b.rowsc, b.dW3, b.dg2, b.dbe2, b.db3};
-    tcn_f2a_kernel<<<a.n, 256, 0, st>>>(p);
+    tcn_f2a_kernel<<<dim3(cdiv(a.H, 64), a.n), 256, 0, st>>>(p);
     WB_LAUNCH_CHECK("tcn_f2a");
-    tcn_f2b_kernel<<<dim3(cdiv(a.H, 128), cdiv(a.B, 8)), 128, 0, st>>>(p);
+    tcn_f2b_kernel<<<dim3(cdiv(a.H, 128), a.B), 128, 0, st>>>(p);
     WB_LAUNCH_CHECK("tcn_f2b");
   }
   {  // B2: dd = dL/d(d) from h = g2 * (W3^T g), gLN2 + PReLU_2 backward fused in the epilogue
@@ -406,11 +657,7 @@ extern "C" int wesep_b200_tcn_block_bwd(const WesepTcnBwdArgs* bp, void* stream)
   {  // B3: depthwise conv + gLN1 + PReLU_1 backward
     StBwdP p{a.n, a.H, a.T, a.dil, a.ld, a.u, b.dd, b.du, a.a1, a.g1, a.be1, a.wd, a.stats1, count, b.rowsc,
              b.dg1, b.dbe1, b.dwd, b.dbd, b.da1, b.sdu};
-    dim3 grid(cdiv(a.T, ST_TTB), cdiv(a.H, ST_CH), a.n);
-    size_t smem = (size_t)ST_CH * (2 * (ST_TTB + 2 * a.dil) + ST_TTB) * sizeof(float);
-    WB_CUDA(cudaFuncSetAttribute(tcn_dw_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tcn_dw_bwd_kernel<<<grid, ST_THREADS, smem, st>>>(p);
-    WB_LAUNCH_CHECK("tcn_dw_bwd");
+    if (int rc = launch_dw_bwd(p, st)) return rc;
   }
   {  // B4: dx = g + W1[:, :B]^T du
     GemmWxP p{};
