@@ -109,7 +109,8 @@ int wesep_b200_clip_adam(const WesepClipAdamArgs* a, void* stream);
  * wesep/modules/tasnet/{convs,encoder,decoder,speaker}.py.  Exposed for tests and for the host
  * modules that are not fused TCN blocks.
  *   pro:  0 identity | 1 prelu(alpha) | 2 scale_c*prelu(x; alpha)+shift_c with per-(row,channel)
- *         scale/shift built from (ch_scale, ch_shift, row_stats): gLN-apply or BN-apply.
+ *         scale/shift built from (ch_scale, ch_shift, row_stats): PReLU then gLN-apply (TCN blocks)
+ *         | 3 prelu(scale_c*x+shift_c; alpha): BatchNorm-apply then PReLU (speaker ResBlock).
  *   epi:  0 Y=acc+bias | 1 Y=relu(acc+bias) | 2 Y=acc+bias+R (residual) |
  *         3 Y=aux*relu(acc+bias), Y2=relu(acc+bias) (decoder mask, decoder.py:96-102)
  * ---------------------------------------------------------------------------------------------- */
@@ -265,6 +266,72 @@ typedef struct {
   const float* x; float* out;   /* out [n][C] overwritten */
 } WesepRowSumArgs;
 int wesep_b200_rowsum(const WesepRowSumArgs* a, void* stream);
+
+
+/* ------------------------------------------------------------------------------------------------
+ * Speaker-encoder ResBlock pieces (ResBlock wesep/modules/tasnet/speaker.py:7-45): BatchNorm1d with batch
+ * statistics (the pointwise convs accumulate per-channel (sum, sumsq) in their GEMM epilogue: WesepGemmArgs.ch_stats),
+ * BN-apply + residual + PReLU + MaxPool1d(3), and the two-pass backward.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int C; double count;              /* count = n*T elements per channel */
+  const double* ch_stats;           /* [C][2] (sum, sumsq) — training only */
+  const float* weight; const float* bias;
+  float* running_mean; float* running_var; float momentum; float eps; int training;
+  float* scale; float* shift;       /* out [C]: y = scale*x + shift */
+  float* mean; float* rstd;         /* out [C] (saved for backward) */
+} WesepBnFinalizeArgs;
+int wesep_b200_bn_finalize(const WesepBnFinalizeArgs* a, void* stream);
+
+typedef struct {
+  int n, C, T, pool;                /* pool = 1 (none) or 3 (MaxPool1d(3)) */
+  int64_t ldx, ldr, ldy;
+  const float* x; const float* res; /* res may be NULL */
+  const float* scale; const float* shift; const float* alpha;
+  float* y;                         /* [n][C][ldy], T/pool frames */
+} WesepBnActPoolFwdArgs;
+int wesep_b200_bn_act_pool_fwd(const WesepBnActPoolFwdArgs* a, void* stream);
+
+typedef struct {
+  int n, C, T, pool;
+  int64_t ldx, ldr, ldgy, ldgv;
+  const float* x; const float* res;
+  const float* scale; const float* shift; const float* alpha; const float* mean; const float* rstd;
+  const float* gy;                  /* [n][C][ldgy] gradient of the pooled output */
+  float* gv;                        /* out [n][C][ldgv]: gradient w.r.t. v = scale*x+shift(+res) */
+  double* ch_sums;                  /* += [C][2]: sum gv, sum gv*xhat (zeroed by the caller) */
+  float* dalpha;                    /* += [1] */
+} WesepBnActPoolBwdArgs;
+int wesep_b200_bn_act_pool_bwd(const WesepBnActPoolBwdArgs* a, void* stream);
+
+typedef struct {
+  int n, C, T, training; int64_t ldgv, ldx, lddx; double count;
+  const float* gv; const float* x; float* dx;
+  const float* scale; const float* mean; const float* rstd;
+  const double* ch_sums;
+} WesepBnBwdArgs;
+int wesep_b200_bn_bwd(const WesepBnBwdArgs* a, void* stream);
+
+/* pred_linear (nn.Linear, wesep/models/convtasnet.py:115,194) and nn.CrossEntropyLoss (wesep/utils/losses.py:11). */
+typedef struct {
+  int n, J, K;
+  const float* x;                   /* [n][K] */
+  const float* W; const float* b;   /* [J][K], [J] or NULL */
+  float* y;                         /* fwd out [n][J] */
+  const float* gy;                  /* bwd in  [n][J] */
+  float* dW; float* db; float* dx;  /* bwd out (overwritten) */
+} WesepLinearArgs;
+int wesep_b200_linear_fwd(const WesepLinearArgs* a, void* stream);
+int wesep_b200_linear_bwd(const WesepLinearArgs* a, void* stream);
+
+typedef struct {
+  int n, J;
+  const float* logits;              /* [n][J] */
+  const int64_t* labels;            /* [n] */
+  float* loss;                      /* out [1] mean over rows (zeroed by the call) */
+  float* dlogits;                   /* out [n][J] d loss / d logits */
+} WesepCeArgs;
+int wesep_b200_cross_entropy(const WesepCeArgs* a, void* stream);
 
 #ifdef __cplusplus
 }

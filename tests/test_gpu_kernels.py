@@ -324,3 +324,63 @@ def test_multi_decoder(n, K):
         check(f"est{i + 1}", a, b, 3e-6)
     for nm, a, b in zip(["de", "dw"] + names, grads, ref):
         check(nm, a, b, 1e-4)
+
+
+# --------------------------------------------------------------------------- speaker ResBlock / linear / CE
+@pytest.mark.parametrize("ci,co,n,T,train", [(64, 64, 2, 300, True), (64, 128, 3, 301, True), (256, 512, 2, 2133, True),
+                                             (64, 64, 2, 299, False)])
+def test_resblock(ci, co, n, T, train):
+    from wesep_b200.modules.tasnet.speaker import ResBlock
+    ops = _ops()
+    blk = ResBlock(ci, co)
+    synth.fill_state_dict_(blk.state_dict(), seed=ci + co + T)
+    with torch.no_grad():   # non-trivial running statistics so that eval mode is a real test
+        for k, v in blk.state_dict().items():
+            if k.endswith("running_mean"):
+                v.copy_(0.1 * torch.randn(v.shape, generator=torch.Generator().manual_seed(1)))
+            if k.endswith("running_var"):
+                v.copy_(1.0 + 0.2 * torch.rand(v.shape, generator=torch.Generator().manual_seed(2)))
+    sd0 = {k: v.detach().clone() for k, v in blk.state_dict().items()}
+    blk = blk.to(DEV).train(train)
+    x = ops.new_act(n, ci, T, DEV)
+    x.copy_(rnd(n, ci, T, seed=5))
+    x.requires_grad_(True)
+    y = blk(x)
+    gy = rnd(*y.shape, seed=6)
+    params = list(blk.parameters())
+    grads = torch.autograd.grad(y, [x] + params, gy)
+    sd64 = {k: (v.double().to(DEV).requires_grad_(v.is_floating_point() and "running" not in k)) for k, v in sd0.items()}
+    x64 = x.detach().double().requires_grad_(True)
+    bufs = {}
+    y64 = ospex.resblock(sd64, "", x64, train, bufs)
+    names = [k for k, _ in blk.named_parameters()]
+    ref = torch.autograd.grad(y64, [x64] + [sd64[k] for k in names], gy.double())
+    assert y.shape == y64.shape
+    check("y", y, y64, 1e-5)
+    for nm, a, b in zip(["dx"] + names, grads, ref):
+        # PReLU / max-pool branch flips at |v| ~ 1e-7 bound this comparison, not the arithmetic (scalar slopes most)
+        check(nm, a, b, 3e-3 if "prelu" in nm else 5e-4)
+    if train:
+        for k, v in bufs.items():
+            check(k, blk.state_dict()[k], v, 1e-5)
+        assert int(blk.batch_norm1.num_batches_tracked) == 1
+
+
+def test_linear_and_cross_entropy():
+    ops = _ops()
+    x = rnd(7, 256, seed=1).requires_grad_(True)
+    W = rnd(251, 256, seed=2, scale=1 / 16).requires_grad_(True)
+    b = rnd(251, seed=3).requires_grad_(True)
+    lab = torch.randint(0, 251, (7,), generator=torch.Generator().manual_seed(4)).to(DEV)
+    z = ops.LinearFn.apply(x, W, b)
+    loss = ops.cross_entropy(z, lab)
+    gx, gW, gb = torch.autograd.grad(0.5 * loss, (x, W, b))
+    x64, W64, b64 = (t.detach().double().requires_grad_(True) for t in (x, W, b))
+    z64 = torch.nn.functional.linear(x64, W64, b64)
+    l64 = torch.nn.functional.cross_entropy(z64, lab)
+    rx, rW, rb = torch.autograd.grad(0.5 * l64, (x64, W64, b64))
+    check("logits", z, z64, 1e-6)
+    assert abs(float(loss) - float(l64)) <= 1e-5
+    check("dx", gx, rx, 1e-5)
+    check("dW", gW, rW, 1e-5)
+    check("db", gb, rb, 1e-5)

@@ -11,7 +11,7 @@ int launch_gemm_wx(const GemmWxP& p, bool a_trans, int pro, int epi, cudaStream_
   if ((p.ldx & 3) || (p.ldw & 3) || !aligned16(p.X) || !aligned16(p.W)) return fail(-1, "gemm_wx: ldx/ldw/base alignment");
   if ((p.Kd & 3) || (a_trans && (p.M & 3))) return fail(-1, "gemm_wx: Kd (and M when transposed) must be multiples of 4");
   if (p.ep.ldy & 1) return fail(-1, "gemm_wx: ldy must be even");
-  if (pro == 2 && p.Kd > G_MAXK) return fail(-2, "gemm_wx: Kd too large for per-channel prologue");
+  if (pro >= 2 && p.Kd > G_MAXK) return fail(-2, "gemm_wx: Kd too large for per-channel prologue");
 #define WB_CASE(AT, PRO, EPI) \
   if (a_trans == AT && pro == PRO && epi == EPI) return launch_gemm_wx_t<AT, PRO, EPI>(p, st);
   WB_CASE(false, 0, 0)
@@ -21,6 +21,7 @@ int launch_gemm_wx(const GemmWxP& p, bool a_trans, int pro, int epi, cudaStream_
   WB_CASE(false, 1, 0)
   WB_CASE(false, 2, 0)
   WB_CASE(false, 2, 2)
+  WB_CASE(false, 3, 0)
   WB_CASE(true, 0, 0)
   WB_CASE(true, 0, 1)
   WB_CASE(true, 0, 2)
@@ -52,7 +53,7 @@ __global__ void __launch_bounds__(G_THREADS, 2) gemm_dw_kernel(const GemmDwP p) 
 
   float alpha = 1.f;
   if constexpr (PRO >= 1) alpha = p.xb.alpha ? __ldg(p.xb.alpha) : 1.f;
-  if constexpr (PRO == 2) {
+  if constexpr (PRO >= 2) {
     float mu = 0.f, r = 1.f;
     if (p.xb.row_stats) gln_mean_rstd(p.xb.row_stats + 2 * row, p.xb.count, p.xb.eps, mu, r);
     if (tid < G_BN) {
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(G_THREADS, 2) gemm_dw_kernel(const GemmDwP p) 
 #pragma unroll
   for (int ni = 0; ni < 4; ++ni) {
     csc[ni] = 1.f; csh[ni] = 0.f;
-    if constexpr (PRO == 2) { csc[ni] = sc[wn * 32 + ni * 8 + g]; csh[ni] = sh[wn * 32 + ni * 8 + g]; }
+    if constexpr (PRO >= 2) { csc[ni] = sc[wn * 32 + ni * 8 + g]; csh[ni] = sh[wn * 32 + ni * 8 + g]; }
   }
 
   float acc[4][4][4];
@@ -122,6 +123,7 @@ __global__ void __launch_bounds__(G_THREADS, 2) gemm_dw_kernel(const GemmDwP p) 
         float x1 = b_s[col * G_A_LD + kk + tig + 4];
         if constexpr (PRO == 1) { x0 = prelu_f(x0, alpha); x1 = prelu_f(x1, alpha); }
         if constexpr (PRO == 2) { x0 = fmaf(csc[ni], prelu_f(x0, alpha), csh[ni]); x1 = fmaf(csc[ni], prelu_f(x1, alpha), csh[ni]); }
+        if constexpr (PRO == 3) { x0 = prelu_f(fmaf(csc[ni], x0, csh[ni]), alpha); x1 = prelu_f(fmaf(csc[ni], x1, csh[ni]), alpha); }
         x0 = k0ok ? x0 : 0.f;
         x1 = k1ok ? x1 : 0.f;
         if constexpr (X3) { split_tf32(x0, bh[ni][0], bl[ni][0]); split_tf32(x1, bh[ni][1], bl[ni][1]); }
@@ -205,6 +207,7 @@ int launch_gemm_dw(const GemmDwP& pin, int pro_b, cudaStream_t st) {
   if (pro_b == 0) return launch_gemm_dw_t<0>(p, st);
   if (pro_b == 1) return launch_gemm_dw_t<1>(p, st);
   if (pro_b == 2) return launch_gemm_dw_t<2>(p, st);
+  if (pro_b == 3) return launch_gemm_dw_t<3>(p, st);
   return fail(-2, "gemm_dw: unsupported prologue");
 }
 

@@ -157,14 +157,14 @@ __device__ __forceinline__ void load_b_tile(float* Bs, const float* Xn, int64_t 
   }
 }
 
-// PRO: 0 identity, 1 prelu, 2 per-channel affine of prelu (gLN / BN apply)
+// PRO: 0 identity, 1 prelu, 2 sc*prelu(x)+sh (PReLU then gLN apply), 3 prelu(sc*x+sh) (BatchNorm apply then PReLU)
 template <bool A_TRANS, int PRO, int EPI, bool X3>
 __global__ void __launch_bounds__(G_THREADS, 2) gemm_wx_kernel(const GemmWxP p) {
   extern __shared__ __align__(16) float smem[];
   float* As = smem;
   float* Bs = smem + G_STAGES * G_A_TILE;
   float* sc = Bs + G_STAGES * G_B_TILE;  // [Kd] (PRO 2)
-  float* sh = sc + (PRO == 2 ? p.Kd : 0);
+  float* sh = sc + (PRO >= 2 ? p.Kd : 0);
   __shared__ float red[4 * 32];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(G_THREADS, 2) gemm_wx_kernel(const GemmWxP p) 
 
   float alpha = 1.f;
   if constexpr (PRO >= 1) alpha = p.xf.alpha ? __ldg(p.xf.alpha) : 1.f;
-  if constexpr (PRO == 2) {
+  if constexpr (PRO >= 2) {
     float mu = 0.f, r = 1.f;
     if (p.xf.row_stats) gln_mean_rstd(p.xf.row_stats + 2 * n, p.xf.count, p.xf.eps, mu, r);
     for (int k = tid; k < p.Kd; k += G_THREADS) {
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(G_THREADS, 2) gemm_wx_kernel(const GemmWxP p) 
       uint32_t bh[4][2], bl[4][2];
       const int kg0 = kt * G_BK + kk + tig, kg1 = kg0 + 4;
       float c0 = 1.f, d0 = 0.f, c1 = 1.f, d1 = 0.f;
-      if constexpr (PRO == 2) {
+      if constexpr (PRO >= 2) {
         // rows beyond Kd hold zero-filled X; force their transformed value to 0 as well
         c0 = kg0 < p.Kd ? sc[kg0] : 0.f; d0 = kg0 < p.Kd ? sh[kg0] : 0.f;
         c1 = kg1 < p.Kd ? sc[kg1] : 0.f; d1 = kg1 < p.Kd ? sh[kg1] : 0.f;
@@ -236,6 +236,7 @@ __global__ void __launch_bounds__(G_THREADS, 2) gemm_wx_kernel(const GemmWxP p) 
         float x1 = b_s[(kk + tig + 4) * G_B_LD + col];
         if constexpr (PRO == 1) { x0 = prelu_f(x0, alpha); x1 = prelu_f(x1, alpha); }
         if constexpr (PRO == 2) { x0 = fmaf(c0, prelu_f(x0, alpha), d0); x1 = fmaf(c1, prelu_f(x1, alpha), d1); }
+        if constexpr (PRO == 3) { x0 = prelu_f(fmaf(c0, x0, d0), alpha); x1 = prelu_f(fmaf(c1, x1, d1), alpha); }
         if constexpr (X3) {
           split_tf32(x0, bh[ni][0], bl[ni][0]);
           split_tf32(x1, bh[ni][1], bl[ni][1]);
@@ -380,7 +381,7 @@ __global__ void __launch_bounds__(G_THREADS, 2) gemm_wx_kernel(const GemmWxP p) 
 }
 
 inline size_t gemm_wx_smem(int pro, int Kd) {
-  return (size_t)(G_STAGES * (G_A_TILE + G_B_TILE) + (pro == 2 ? 2 * Kd : 0)) * sizeof(float);
+  return (size_t)(G_STAGES * (G_A_TILE + G_B_TILE) + (pro >= 2 ? 2 * Kd : 0)) * sizeof(float);
 }
 
 template <bool A_TRANS, int PRO, int EPI>

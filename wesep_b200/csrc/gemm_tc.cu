@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     int cur_n = -1;
     for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
       const int n = (tile / P.n_ob) / P.n_tt;
-      if constexpr (PRO == 2) {
+      if constexpr (PRO >= 2) {
         if (n != cur_n) {  // per-row gLN constants: sc[k] = gamma*rstd, sh[k] = beta - gamma*mean*rstd
           // all transform warps of this CTA see the same tile sequence: sync them around the table rewrite
           asm volatile("bar.sync 1, 256;\n" ::: "memory");
@@ -276,16 +276,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           float4 v = *reinterpret_cast<const float4*>(xs_hi + off);
           if constexpr (PRO >= 1) {
             float c = 1.f, d = 0.f;
-            if constexpr (PRO == 2) {
+            if constexpr (PRO >= 2) {
               const int kk = kb * TC_BK + ((off % TC_BOX_BYTES) >> 7);  // row inside the box = channel
               const bool kok = kk < p.Kd;
               c = kok ? sc[kk] : 0.f;
               d = kok ? sh[kk] : 0.f;
             }
-            v.x = fmaf(c, prelu_f(v.x, alpha), d);
-            v.y = fmaf(c, prelu_f(v.y, alpha), d);
-            v.z = fmaf(c, prelu_f(v.z, alpha), d);
-            v.w = fmaf(c, prelu_f(v.w, alpha), d);
+            if constexpr (PRO == 3) {   // BatchNorm apply, then PReLU
+              v.x = prelu_f(fmaf(c, v.x, d), alpha);
+              v.y = prelu_f(fmaf(c, v.y, d), alpha);
+              v.z = prelu_f(fmaf(c, v.z, d), alpha);
+              v.w = prelu_f(fmaf(c, v.w, d), alpha);
+            } else {                    // PReLU, then gLN apply
+              v.x = fmaf(c, prelu_f(v.x, alpha), d);
+              v.y = fmaf(c, prelu_f(v.y, alpha), d);
+              v.z = fmaf(c, prelu_f(v.z, alpha), d);
+              v.w = fmaf(c, prelu_f(v.w, alpha), d);
+            }
           }
           float4 h, l;
           h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
@@ -365,6 +372,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                   s1 = fmaf(y, y, s1);
                 }
               }
+              if (e.ch_stats) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float y = (t + i < p.T) ? v[i] : 0.f;
+                  s2 += y;
+                  s3 = fmaf(y, y, s3);
+                }
+              }
             } else if constexpr (EPI == 2) {
               const float4 rr = gop[g];
               *reinterpret_cast<float4*>(yrow + t) = make_float4(v[0] + rr.x, v[1] + rr.y, v[2] + rr.z, v[3] + rr.w);
@@ -408,6 +423,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             atomicAdd(e.out_stats + 2 * n, (double)s0);
             atomicAdd(e.out_stats + 2 * n + 1, (double)s1);
           }
+        }
+        if (e.ch_stats) {   // BatchNorm batch statistics: this thread owns channel o
+          atomicAdd(e.ch_stats + 2 * o, (double)s2);
+          atomicAdd(e.ch_stats + 2 * o + 1, (double)s3);
         }
       }
       if constexpr (EPI == 10) {
@@ -463,9 +482,8 @@ static int encode_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t*
 bool gemm_wx_tc_eligible(const GemmWxP& p, int pro, int epi) {
   if (p.M % TC_BM || p.Kd % TC_BK || p.Kd > TC_MAXK) return false;
   if ((p.ldx & 3) || !aligned16(p.X) || (p.bsx & 3)) return false;
-  if (!(pro == 0 || pro == 2)) return false;
+  if (!(pro == 0 || pro == 2 || pro == 3)) return false;
   if (!(epi == 0 || epi == 2 || epi == 10)) return false;
-  if (epi == 0 && p.ep.ch_stats) return false;
   if ((p.ep.ldy & 3) || !aligned16(p.ep.Y) || (p.ep.bsy & 3)) return false;
   if (epi == 2 && ((p.ep.ldr & 3) || !aligned16(p.ep.R) || (p.ep.bsr & 3))) return false;
   if (epi == 10 && ((p.ep.ldd & 3) || !aligned16(p.ep.d) || (p.ep.bsd & 3))) return false;
@@ -526,6 +544,7 @@ int launch_gemm_wx_tc(const GemmWxP& p, bool a_trans, int pro, int epi, void* ws
   if (pro == 0 && epi == 10) return launch_tc_t<0, 10>(mh, ml, mx, P, st);
   if (pro == 2 && epi == 2) return launch_tc_t<2, 2>(mh, ml, mx, P, st);
   if (pro == 2 && epi == 0) return launch_tc_t<2, 0>(mh, ml, mx, P, st);
+  if (pro == 3 && epi == 0) return launch_tc_t<3, 0>(mh, ml, mx, P, st);
   return fail(-2, "gemm_wx_tc: unsupported (pro, epi)");
 }
 

@@ -3,6 +3,7 @@ keys as the reference wesep/models/convtasnet.py:14-219; the forward runs on lib
 import torch
 import torch.nn as nn
 
+from wesep_b200 import ops
 from wesep_b200.modules.common.speaker import SpeakerTransform
 from wesep_b200.modules.tasnet import FuseSeparation, MultiDecoder, MultiEncoder, ResNet4SpExplus
 
@@ -81,7 +82,7 @@ class ConvTasNet(nn.Module):
             aux = self.encoder.filterbank(embeddings)       # cat[aux_w1, aux_w2, aux_w3]  (:185)
             embeddings = self.spk_model(aux)                # (:190)
             if self.multi_task:
-                predict_speaker_lable = self.pred_linear(embeddings)
+                predict_speaker_lable = ops.LinearFn.apply(embeddings, self.pred_linear.weight, self.pred_linear.bias)
         spk_embeds = self.spk_transform(embeddings.unsqueeze(-1))
         e = self.separation(e, spk_embeds)
         s = self.decoder.forward_cat(e, w) if isinstance(self.activation, nn.ReLU) else None

@@ -1,8 +1,7 @@
-"""ResNet4SpExplus / ResBlock — reference wesep/modules/tasnet/speaker.py:7-64.
-
-Pointwise convs and the cLN run on the library's kernels; BatchNorm1d (batch statistics),
-PReLU and MaxPool1d(3) of the three ResBlocks are still ATen ops in this round (small tensors:
-lengths 6399 -> 2133 -> 711 -> 237; ~3 % of the step's bytes) — see DESIGN.md "open items"."""
+"""ResNet4SpExplus / ResBlock — reference wesep/modules/tasnet/speaker.py:7-64, executed on the library's
+kernels: pointwise convs as tensor-core GEMMs (BatchNorm batch statistics accumulated in their epilogues),
+BN-apply + PReLU as the next GEMM's operand prologue, BN-apply + residual + PReLU + MaxPool1d(3) fused."""
+import torch
 import torch.nn as nn
 
 from wesep_b200 import ops
@@ -35,17 +34,16 @@ class ResBlock(nn.Module):
             self.downsample = False
 
     def forward(self, x):
-        residual = x
-        x = self.conv1(x)
-        x = self.batch_norm1(x)
-        x = self.prelu1(x)
-        x = self.conv2(x)
-        x = self.batch_norm2(x)
-        if self.downsample:
-            residual = self.conv_downsample(residual)
-        x = x + residual
-        x = self.prelu2(x)
-        return self.mp(x)
+        b1, b2 = self.batch_norm1, self.batch_norm2
+        if self.training:
+            with torch.no_grad():
+                b1.num_batches_tracked += 1
+                b2.num_batches_tracked += 1
+        return ops.ResBlockFn.apply(x, self.conv1.weight, self.conv2.weight,
+                                    self.conv_downsample.weight if self.downsample else None,
+                                    b1.weight, b1.bias, b1.running_mean, b1.running_var,
+                                    b2.weight, b2.bias, b2.running_mean, b2.running_var,
+                                    self.prelu1.weight, self.prelu2.weight, self.training, b1.momentum, b1.eps)
 
 
 class ResNet4SpExplus(nn.Module):
@@ -63,4 +61,4 @@ class ResNet4SpExplus(nn.Module):
 
     def forward(self, x):
         aux = self.aux_enc3(x)
-        return aux.mean(dim=-1)
+        return ops.MeanTimeFn.apply(aux)

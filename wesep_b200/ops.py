@@ -516,3 +516,174 @@ class SisdrFn(torch.autograd.Function):
 def sisdr_losses(ests, tgt):
     """Returns (losses [k], per-row SI-SDR [k, n] in dB)."""
     return SisdrFn.apply(tgt, *ests)
+
+
+# --------------------------------------------------------------------------- speaker ResBlock / linear / CE
+def _bn_finalize(ch_stats, count, weight, bias, running_mean, running_var, momentum, eps, training):
+    C = weight.numel()
+    dev = weight.device
+    out = torch.empty((4, C), dtype=torch.float32, device=dev)   # scale, shift, mean, rstd
+    _lib.call("wesep_b200_bn_finalize", _args("WesepBnFinalizeArgs", C=C, count=float(count), ch_stats=ch_stats,
+                                              weight=_vec(weight), bias=_vec(bias), running_mean=running_mean,
+                                              running_var=running_var, momentum=float(momentum), eps=float(eps),
+                                              training=int(training), scale=out[0], shift=out[1], mean=out[2], rstd=out[3]),
+              _stream())
+    return out
+
+
+class ResBlockFn(torch.autograd.Function):
+    """ResBlock.forward (wesep/modules/tasnet/speaker.py:31-45): conv1 - BN - PReLU - conv2 - BN - (+ residual) -
+    PReLU - MaxPool1d(3).  The two pointwise convs are tensor-core GEMMs whose epilogues accumulate the BatchNorm
+    batch statistics; BN1-apply + PReLU is conv2's operand prologue; BN2-apply + residual + PReLU + max-pool is one
+    kernel.  Backward: two passes per BatchNorm (sums, then apply)."""
+
+    @staticmethod
+    def forward(ctx, x, W1, W2, Wd, g1, b1, rm1, rv1, g2, b2, rm2, rv2, a1, a2, training, momentum, eps):
+        x = as_act(x)
+        n, Ci, T = x.shape
+        W1c, W2c = _w2d(W1), _w2d(W2)
+        Wdc = None if Wd is None else _w2d(Wd)
+        Co = W1c.shape[0]
+        dev = x.device
+        count = n * T
+        a1v, a2v = _vec(a1), _vec(a2)
+        st = torch.zeros((2, Co, 2), dtype=torch.float64, device=dev)
+        c1 = conv1x1_raw(x, W1c, False, Co, ch_stats=st[0] if training else None)
+        bn1 = _bn_finalize(st[0], count, g1, b1, rm1, rv1, momentum, eps, training)
+        c2 = conv1x1_raw(c1, W2c, False, Co, pro=3, alpha=a1v, ch_scale=bn1[0], ch_shift=bn1[1],
+                         ch_stats=st[1] if training else None)
+        bn2 = _bn_finalize(st[1], count, g2, b2, rm2, rv2, momentum, eps, training)
+        res = x if Wdc is None else conv1x1_raw(x, Wdc, False, Co)
+        Tp = T // 3
+        y = new_act(n, Co, Tp, dev)
+        _lib.call("wesep_b200_bn_act_pool_fwd", _args("WesepBnActPoolFwdArgs", n=n, C=Co, T=T, pool=3, ldx=c2.stride(1),
+                                                      ldr=res.stride(1), ldy=y.stride(1), x=c2, res=res, scale=bn2[0],
+                                                      shift=bn2[1], alpha=a2v, y=y), _stream())
+        ctx.training = bool(training)
+        ctx.shapes = (W1.shape, W2.shape, None if Wd is None else Wd.shape)
+        ctx.save_for_backward(x, c1, c2, res if Wdc is not None else None, W1c, W2c, Wdc, bn1, bn2, a1v, a2v)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, c1, c2, res, W1c, W2c, Wdc, bn1, bn2, a1v, a2v = ctx.saved_tensors
+        n, Ci, T = x.shape
+        Co = W1c.shape[0]
+        dev = x.device
+        count = n * T
+        if res is None:
+            res = x
+        gy = as_act(gy)
+        sums = torch.zeros((2, Co, 2), dtype=torch.float64, device=dev)
+        dal = torch.zeros(2, dtype=torch.float32, device=dev)
+        # ---- second half: maxpool + PReLU_2 + residual + BN2
+        gv2 = new_act(n, Co, T, dev)
+        _lib.call("wesep_b200_bn_act_pool_bwd", _args("WesepBnActPoolBwdArgs", n=n, C=Co, T=T, pool=3, ldx=c2.stride(1),
+                                                      ldr=res.stride(1), ldgy=gy.stride(1), ldgv=gv2.stride(1), x=c2,
+                                                      res=res, scale=bn2[0], shift=bn2[1], alpha=a2v, mean=bn2[2],
+                                                      rstd=bn2[3], gy=gy, gv=gv2, ch_sums=sums[1], dalpha=dal[1:]),
+                  _stream())
+        dc2 = new_act(n, Co, T, dev)
+        _lib.call("wesep_b200_bn_bwd", _args("WesepBnBwdArgs", n=n, C=Co, T=T, training=int(ctx.training),
+                                             ldgv=gv2.stride(1), ldx=c2.stride(1), lddx=dc2.stride(1), count=float(count),
+                                             gv=gv2, x=c2, dx=dc2, scale=bn2[0], mean=bn2[2], rstd=bn2[3],
+                                             ch_sums=sums[1]), _stream())
+        dW2 = torch.zeros_like(W2c)
+        conv1x1_dw_raw(dc2, c1, dW2, pro_b=3, alpha_b=a1v, ch_scale_b=bn1[0], ch_shift_b=bn1[1])
+        gp1 = conv1x1_raw(dc2, W2c, True, Co)
+        # ---- first half: PReLU_1 + BN1
+        gv1 = new_act(n, Co, T, dev)
+        _lib.call("wesep_b200_bn_act_pool_bwd", _args("WesepBnActPoolBwdArgs", n=n, C=Co, T=T, pool=1, ldx=c1.stride(1),
+                                                      ldr=0, ldgy=gp1.stride(1), ldgv=gv1.stride(1), x=c1, res=None,
+                                                      scale=bn1[0], shift=bn1[1], alpha=a1v, mean=bn1[2], rstd=bn1[3],
+                                                      gy=gp1, gv=gv1, ch_sums=sums[0], dalpha=dal[0:]), _stream())
+        dc1 = new_act(n, Co, T, dev)
+        _lib.call("wesep_b200_bn_bwd", _args("WesepBnBwdArgs", n=n, C=Co, T=T, training=int(ctx.training),
+                                             ldgv=gv1.stride(1), ldx=c1.stride(1), lddx=dc1.stride(1), count=float(count),
+                                             gv=gv1, x=c1, dx=dc1, scale=bn1[0], mean=bn1[2], rstd=bn1[3],
+                                             ch_sums=sums[0]), _stream())
+        dW1 = torch.zeros_like(W1c)
+        conv1x1_dw_raw(dc1, x, dW1)
+        dWd = None
+        if Wdc is None:
+            dx = conv1x1_raw(dc1, W1c, True, Ci, epi=2, R=gv2)          # + identity residual
+        else:
+            dx = conv1x1_raw(dc1, W1c, True, Ci)
+            conv1x1_raw(gv2, Wdc, True, Ci, epi=2, R=dx, Y=dx)          # + downsample-conv residual (in place)
+            dWd = torch.zeros_like(Wdc)
+            conv1x1_dw_raw(gv2, x, dWd)
+        sf = sums.float()
+        W1s, W2s, Wds = ctx.shapes
+        return (dx, dW1.view(W1s), dW2.view(W2s), None if dWd is None else dWd.view(Wds),
+                sf[0, :, 1].contiguous(), sf[0, :, 0].contiguous(), None, None,
+                sf[1, :, 1].contiguous(), sf[1, :, 0].contiguous(), None, None, dal[0:1], dal[1:2], None, None, None)
+
+
+class MeanTimeFn(torch.autograd.Function):
+    """x.mean(dim=-1) over the valid frames of an act tensor (ResNet4SpExplus.forward, speaker.py:63)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = as_act(x)
+        ctx.T = x.shape[2]
+        return rowsum_raw(x) / x.shape[2]
+
+    @staticmethod
+    def backward(ctx, g):
+        return (g / ctx.T).unsqueeze(-1).expand(-1, -1, ctx.T)
+
+
+class LinearFn(torch.autograd.Function):
+    """nn.Linear on [n, K] rows (pred_linear, wesep/models/convtasnet.py:194)."""
+
+    @staticmethod
+    def forward(ctx, x, W, b):
+        _check_cuda(x, W)
+        x = x.contiguous().float()
+        W = W.contiguous()
+        n, K = x.shape
+        J = W.shape[0]
+        y = torch.empty((n, J), dtype=torch.float32, device=x.device)
+        _lib.call("wesep_b200_linear_fwd", _args("WesepLinearArgs", n=n, J=J, K=K, x=x, W=W, b=b, y=y), _stream())
+        ctx.has_b = b is not None
+        ctx.save_for_backward(x, W)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, W = ctx.saved_tensors
+        n, K = x.shape
+        J = W.shape[0]
+        gy = gy.contiguous().float()
+        dW = torch.empty_like(W)
+        db = torch.empty(J, dtype=torch.float32, device=x.device) if ctx.has_b else None
+        dx = torch.empty_like(x)
+        _lib.call("wesep_b200_linear_bwd", _args("WesepLinearArgs", n=n, J=J, K=K, x=x, W=W, gy=gy, dW=dW, db=db, dx=dx),
+                  _stream())
+        return dx, dW, db
+
+
+class CrossEntropyFn(torch.autograd.Function):
+    """nn.CrossEntropyLoss() (mean over rows) on [n, J] logits with int64 labels (wesep/utils/losses.py:11)."""
+
+    @staticmethod
+    def forward(ctx, logits, labels):
+        _check_cuda(logits, labels)
+        logits = logits.contiguous().float()
+        labels = labels.contiguous().long()
+        n, J = logits.shape
+        loss = torch.empty(1, dtype=torch.float32, device=logits.device)
+        dlogits = torch.empty_like(logits)
+        _lib.call("wesep_b200_cross_entropy", _args("WesepCeArgs", n=n, J=J, logits=logits, labels=labels, loss=loss,
+                                                    dlogits=dlogits), _stream())
+        ctx.save_for_backward(dlogits)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (dlogits,) = ctx.saved_tensors
+        return g * dlogits, None
+
+
+def cross_entropy(logits, labels):
+    return CrossEntropyFn.apply(logits, labels)

@@ -2,7 +2,6 @@
 (wesep/utils/executor.py:70-134): forward, weighted SI-SDR (+CE) loss, backward, gradient
 all-reduce, per-tensor clip + Adam.  Host syncs per step: only the caller's optional loss read."""
 import torch
-import torch.nn.functional as F
 
 from wesep_b200 import ops
 
@@ -21,7 +20,7 @@ def compute_loss(outputs, targets, spk_label, loss_posi=((0, 1, 2), (3,)), loss_
     loss = (losses * w).sum()
     if multi_task and len(loss_posi) > 1:
         for j, p in enumerate(loss_posi[1]):
-            loss = loss + loss_weight[1][j] * F.cross_entropy(outputs[p], spk_label)
+            loss = loss + loss_weight[1][j] * ops.cross_entropy(outputs[p], spk_label)
     return loss, rows
 
 
