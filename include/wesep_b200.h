@@ -333,6 +333,30 @@ typedef struct {
 } WesepCeArgs;
 int wesep_b200_cross_entropy(const WesepCeArgs* a, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Alternative speaker fusion in front of each TCN repeat (FuseSeparation, spk_fuse_type in {concat, additive,
+ * multiply, FiLM}: wesep/modules/tasnet/separation.py:116-135,172-181; SpeakerFuseLayer common/speaker.py:81-125;
+ * FiLM common/norm.py:118-139) followed by the stand-alone nn.PReLU and gLN of the reference:
+ *     z = gLN( PReLU( ra[n][c] * x + rb[n][c] ; alpha ) ; gamma, beta )
+ * fwd fills `stats` (double [n][2], saved); bwd needs them plus a [n][2] scratch `rowsums`.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int n, C, T; int64_t ldx, ldy, ldg, lddx;
+  const float* x;                   /* [n][C][ldx] */
+  const float* ra; const float* rb; /* [n][C] per-row channel scale / shift, NULL = 1 / 0 */
+  const float* alpha; const float* gamma; const float* beta;
+  double* stats;                    /* [n][2] */
+  float* y;                         /* fwd out [n][C][ldy] */
+  const float* gz;                  /* bwd in  [n][C][ldg] */
+  double* rowsums;                  /* bwd scratch [n][2] */
+  float* dx;                        /* bwd out [n][C][lddx] */
+  float* dra; float* drb;           /* bwd out [n][C] (overwritten; may be NULL) */
+  float* dalpha; float* dgamma; float* dbeta;  /* bwd += [1], [C], [C] */
+} WesepFuseArgs;
+int wesep_b200_fuse_prelu_gln_fwd(const WesepFuseArgs* a, void* stream);
+int wesep_b200_fuse_prelu_gln_bwd(const WesepFuseArgs* a, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -384,3 +384,39 @@ def test_linear_and_cross_entropy():
     check("dx", gx, rx, 1e-5)
     check("dW", gW, rW, 1e-5)
     check("db", gb, rb, 1e-5)
+
+
+@pytest.mark.parametrize("mode", ["film", "multiply", "additive", "identity"])
+@pytest.mark.parametrize("n,C,T", [(2, 64, 319), (3, 256, 6399)])
+def test_fuse_prelu_gln(mode, n, C, T):
+    ops = _ops()
+    x = ops.new_act(n, C, T, DEV)
+    x.copy_(rnd(n, C, T, seed=1))
+    x.requires_grad_(True)
+    ra = (1 + 0.3 * rnd(n, C, seed=2)).requires_grad_(True) if mode in ("film", "multiply") else None
+    rb = (0.3 * rnd(n, C, seed=3)).requires_grad_(True) if mode in ("film", "additive") else None
+    al = torch.tensor([0.2], device=DEV, requires_grad=True)
+    gm = (1 + 0.1 * rnd(C, 1, seed=4)).requires_grad_(True)
+    bt = (0.1 * rnd(C, 1, seed=5)).requires_grad_(True)
+    z = ops.FusePreluGlnFn.apply(x, ra, rb, al, gm, bt)
+    gz = rnd(n, C, T, seed=6)
+    ins = [t for t in (x, ra, rb, al, gm, bt) if t is not None]
+    grads = torch.autograd.grad(z, ins, gz)
+    ins64 = [t.detach().double().requires_grad_(True) for t in ins]
+    it = iter(ins64)
+    x64 = next(it)
+    ra64 = next(it) if ra is not None else None
+    rb64 = next(it) if rb is not None else None
+    al64, gm64, bt64 = next(it), next(it), next(it)
+    v = x64
+    if ra64 is not None:
+        v = v * ra64[:, :, None]
+    if rb64 is not None:
+        v = v + rb64[:, :, None]
+    pre = v.detach()
+    y = torch.where(pre > 0, v, al64 * v)
+    z64 = ospex.gln(y, gm64, bt64)
+    ref = torch.autograd.grad(z64, ins64, gz.double())
+    check("z", z, z64, 2e-6)
+    for i, (a, b) in enumerate(zip(grads, ref)):
+        check(f"grad{i}", a, b, 2e-4)

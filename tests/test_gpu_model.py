@@ -82,6 +82,12 @@ def test_golden_small(name):
     run_fixture(name)
 
 
+@pytest.mark.parametrize("ft", ["FiLM", "multiply", "additive", "concat"])
+def test_golden_alternative_fusion(ft):
+    """spk_fuse_type variants of FuseSeparation (separation.py:116-135) vs goldens of the real reference."""
+    run_fixture("spex_small_" + ft)
+
+
 def test_golden_full_cfg1_eval():
     """BASELINE config 1: Spex+ forward + SI-SNR, one 2-speaker 4 s mixture, vs the real reference."""
     run_fixture("spex_full_cfg1_eval")

@@ -29,7 +29,7 @@ constexpr int TC_X_BYTES = (TC_BN / 32) * TC_BOX_BYTES;  // 16384
 constexpr int TC_OFF_WHI = 0, TC_OFF_WLO = TC_W_BYTES, TC_OFF_XHI = 2 * TC_W_BYTES, TC_OFF_XLO = 2 * TC_W_BYTES + TC_X_BYTES;
 constexpr int TC_STAGE_BYTES = 2 * TC_W_BYTES + 2 * TC_X_BYTES;  // 49152
 constexpr int TC_TX_BYTES = 2 * TC_W_BYTES + TC_X_BYTES;         // bytes the TMA delivers per stage
-constexpr int TC_MAXK = 512;
+constexpr int TC_MAXK = 1024;
 constexpr int TC_SMEM_AUX = 2 * TC_MAXK * 4 + 256;                // sc/sh + barriers
 constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + TC_SMEM_AUX + 1024;
 
@@ -316,7 +316,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     for (int tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, ++ti) {
       const int ob = tile % P.n_ob, rest = tile / P.n_ob;
       const int tt = rest % P.n_tt, n = rest / P.n_tt;
-      const int o = ob * TC_BM + q * 32 + lane;  // this thread's output channel (M % 128 == 0 => always valid)
+      const int o_raw = ob * TC_BM + q * 32 + lane;
+      const bool o_ok = o_raw < p.M;                 // partial last channel block
+      const int o = o_ok ? o_raw : p.M - 1;          // clamp for the constant loads; stores are masked
       const int t0 = tt * TC_BN;
       const int a = ti & 1;
       const uint32_t aph = (ti >> 1) & 1;
@@ -336,7 +338,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         gam1 = __ldg(e.g1 + o); bet1 = __ldg(e.be1 + o); bdm = __ldg(e.bd + o);
         w0 = __ldg(e.wd + 3 * o); w1 = __ldg(e.wd + 3 * o + 1); w2 = __ldg(e.wd + 3 * o + 2);
       }
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, sL = 0.f, sR = 0.f;
+      float cA = 0.f, cB = 0.f, cC = 0.f;
+      if constexpr (EPI == 10) {
+        cA = r2 * gam2;
+        cB = -r2 * r2 * mhy;
+        cC = -r2 * mh + r2 * r2 * mhy * mu2;
+      }
 
       mbar_wait(bar_accf(a), aph);
       tc_fence_after();
@@ -344,14 +352,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #pragma unroll 1
       for (int c0 = chalf * (TC_BN / 2); c0 < (chalf + 1) * (TC_BN / 2); c0 += 32) {
         if (t0 + c0 >= p.T) break;   // warp-uniform
+        const bool edge_chunk = (EPI == 10) && ((t0 + c0 < e.dil) || (t0 + c0 + 32 > p.T - e.dil));
         // issue this chunk's global operand loads before the TMEM load so their latency overlaps it
         float4 gop[8];
-        if constexpr (EPI == 2 || EPI == 10) {
-          const float* gsrc = (EPI == 2) ? (e.R + n * e.bsr + (int64_t)o * e.ldr) : (e.d + n * e.bsd + (int64_t)o * e.ldd);
+        if constexpr (EPI == 2 || EPI == 3 || EPI == 10) {
+          const float* gsrc = (EPI == 10) ? (e.d + n * e.bsd + (int64_t)o * e.ldd) : (e.R + n * e.bsr + (int64_t)o * e.ldr);
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
             const int t = t0 + c0 + 4 * g;
-            gop[g] = (t < p.T) ? *reinterpret_cast<const float4*>(gsrc + t) : make_float4(0.f, 0.f, 0.f, 0.f);
+            gop[g] = (t < p.T && o_ok) ? *reinterpret_cast<const float4*>(gsrc + t) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
         uint32_t r[32];
@@ -359,7 +368,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
           const int t = t0 + c0 + 4 * g;
-          if (t < p.T) {
+          if (t < p.T && o_ok) {
             float v[4] = {__uint_as_float(r[4 * g]) + bias_o, __uint_as_float(r[4 * g + 1]) + bias_o,
                           __uint_as_float(r[4 * g + 2]) + bias_o, __uint_as_float(r[4 * g + 3]) + bias_o};
             if constexpr (EPI == 0) {
@@ -380,30 +389,51 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                   s3 = fmaf(y, y, s3);
                 }
               }
+            } else if constexpr (EPI == 1) {
+              *reinterpret_cast<float4*>(yrow + t) = make_float4(fmaxf(v[0], 0.f), fmaxf(v[1], 0.f), fmaxf(v[2], 0.f), fmaxf(v[3], 0.f));
+            } else if constexpr (EPI == 3) {   // decoder masks: Y2 = relu(v), Y = aux * relu(v)
+              const float4 rr = gop[g];
+              const float m0 = fmaxf(v[0], 0.f), m1 = fmaxf(v[1], 0.f), m2 = fmaxf(v[2], 0.f), m3 = fmaxf(v[3], 0.f);
+              *reinterpret_cast<float4*>(e.Y2 + n * e.bsy2 + (int64_t)o * e.ldy2 + t) = make_float4(m0, m1, m2, m3);
+              *reinterpret_cast<float4*>(yrow + t) = make_float4(rr.x * m0, rr.y * m1, rr.z * m2, rr.w * m3);
             } else if constexpr (EPI == 2) {
               const float4 rr = gop[g];
               *reinterpret_cast<float4*>(yrow + t) = make_float4(v[0] + rr.x, v[1] + rr.y, v[2] + rr.z, v[3] + rr.w);
             } else if constexpr (EPI == 10) {
+              // dy2 = r2*(g2*v - mh - yhat2*mhy) = cA*v + cB*y2 + cC ;  dd = dy2 * prelu'(d)
               const float4 d4 = gop[g];
               const float draw[4] = {d4.x, d4.y, d4.z, d4.w};
               float dd[4];
+              if (!edge_chunk) {   // interior columns: no masks, no edge bookkeeping (warp-uniform)
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int tt_ = t + i;
-                const bool ok = tt_ < p.T;
-                // columns >= T are padding (possibly NaN): neutralise the operands, not just the result
-                const float dvi = ok ? draw[i] : 1.f;
-                const float h = ok ? v[i] * gam2 : 0.f;
-                const float y2 = prelu_f(dvi, a2);
-                const float yh = (y2 - mu2) * r2;
-                const float dy2 = r2 * (h - mh - yh * mhy);
-                const float ddv = ok ? dy2 * (dvi > 0.f ? 1.f : a2) : 0.f;
-                dd[i] = ddv;
-                const float kap = w1 + (tt_ >= e.dil ? w0 : 0.f) + (tt_ < p.T - e.dil ? w2 : 0.f);
-                s0 = fmaf(ddv * gam1, kap, s0);
-                s1 = fmaf(ddv, dvi - bdm, s1);
-                s2 = fmaf(ddv * bet1, kap, s2);
-                s3 += (dvi > 0.f || !ok) ? 0.f : dy2 * dvi;
+                for (int i = 0; i < 4; ++i) {
+                  const float dvi = draw[i];
+                  const bool pos = dvi > 0.f;
+                  const float y2 = pos ? dvi : a2 * dvi;
+                  const float dy2 = fmaf(cA, v[i], fmaf(cB, y2, cC));
+                  const float ddv = pos ? dy2 : a2 * dy2;
+                  dd[i] = ddv;
+                  s0 += ddv;                        // S
+                  s1 = fmaf(ddv, dvi, s1);          // sum dd*d
+                  s3 += pos ? 0.f : dy2 * dvi;      // dalpha2
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const int tt_ = t + i;
+                  const bool ok = tt_ < p.T;
+                  const float dvi = ok ? draw[i] : 1.f;       // padding columns may hold NaN: neutralise the operands
+                  const bool pos = dvi > 0.f;
+                  const float y2 = pos ? dvi : a2 * dvi;
+                  const float dy2 = ok ? fmaf(cA, v[i], fmaf(cB, y2, cC)) : 0.f;
+                  const float ddv = pos ? dy2 : a2 * dy2;
+                  dd[i] = ddv;
+                  s0 += ddv;
+                  s1 = fmaf(ddv, dvi, s1);
+                  s3 += pos ? 0.f : dy2 * dvi;
+                  sL += tt_ < e.dil ? ddv : 0.f;              // columns whose left tap falls off the sequence
+                  sR += tt_ >= p.T - e.dil ? ddv : 0.f;       // ... right tap
+                }
               }
               *reinterpret_cast<float4*>(yrow + t) = make_float4(dd[0], dd[1], dd[2], dd[3]);
             }
@@ -424,12 +454,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             atomicAdd(e.out_stats + 2 * n + 1, (double)s1);
           }
         }
-        if (e.ch_stats) {   // BatchNorm batch statistics: this thread owns channel o
+        if (e.ch_stats && o_ok) {   // BatchNorm batch statistics: this thread owns channel o
           atomicAdd(e.ch_stats + 2 * o, (double)s2);
           atomicAdd(e.ch_stats + 2 * o + 1, (double)s3);
         }
       }
       if constexpr (EPI == 10) {
+        // P1 = sum dd*g1*kappa, P2 = sum dd*(d - bd), P3 = sum dd*be1*kappa with kappa = w0+w1+w2 minus the taps
+        // that fall outside [0,T) (interior columns all share kappa = w0+w1+w2)
+        const float S = s0, SD = s1;
+        const float kS = (w0 + w1 + w2) * S - w0 * sL - w2 * sR;
+        s0 = gam1 * kS;
+        s1 = SD - bdm * S;
+        s2 = bet1 * kS;
         s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
         if (lane == 0) {
           atomicAdd(e.rowacc + 8 * n + 2, (double)s0);
@@ -480,10 +517,11 @@ static int encode_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t*
 }
 
 bool gemm_wx_tc_eligible(const GemmWxP& p, int pro, int epi) {
-  if (p.M % TC_BM || p.Kd % TC_BK || p.Kd > TC_MAXK) return false;
+  if ((p.M & 3) || (p.Kd & 3) || p.Kd > TC_MAXK) return false;   // partial tiles: TMA zero-fill + epilogue row mask
   if ((p.ldx & 3) || !aligned16(p.X) || (p.bsx & 3)) return false;
   if (!(pro == 0 || pro == 2 || pro == 3)) return false;
-  if (!(epi == 0 || epi == 2 || epi == 10)) return false;
+  if (!(epi == 0 || epi == 1 || epi == 2 || epi == 3 || epi == 10)) return false;
+  if (epi == 3 && ((p.ep.ldy2 & 3) || !aligned16(p.ep.Y2) || (p.ep.bsy2 & 3) || (p.ep.ldr & 3) || !aligned16(p.ep.R) || (p.ep.bsr & 3))) return false;
   if ((p.ep.ldy & 3) || !aligned16(p.ep.Y) || (p.ep.bsy & 3)) return false;
   if (epi == 2 && ((p.ep.ldr & 3) || !aligned16(p.ep.R) || (p.ep.bsr & 3))) return false;
   if (epi == 10 && ((p.ep.ldd & 3) || !aligned16(p.ep.d) || (p.ep.bsd & 3))) return false;
@@ -535,7 +573,7 @@ int launch_gemm_wx_tc(const GemmWxP& p, bool a_trans, int pro, int epi, void* ws
   }
   TcParams P;
   P.g = p;
-  P.n_ob = p.M / TC_BM;
+  P.n_ob = cdiv(p.M, TC_BM);
   P.n_tt = cdiv(p.T, TC_BN);
   P.n_tiles = P.n_ob * P.n_tt * p.n;
   P.skip_hi_store = (g_tc_flags & 1) ? 0 : 1;   // default: raw tile is the hi operand (HW truncates tf32 inputs; measured)
@@ -545,6 +583,8 @@ int launch_gemm_wx_tc(const GemmWxP& p, bool a_trans, int pro, int epi, void* ws
   if (pro == 2 && epi == 2) return launch_tc_t<2, 2>(mh, ml, mx, P, st);
   if (pro == 2 && epi == 0) return launch_tc_t<2, 0>(mh, ml, mx, P, st);
   if (pro == 3 && epi == 0) return launch_tc_t<3, 0>(mh, ml, mx, P, st);
+  if (pro == 0 && epi == 1) return launch_tc_t<0, 1>(mh, ml, mx, P, st);
+  if (pro == 0 && epi == 3) return launch_tc_t<0, 3>(mh, ml, mx, P, st);
   return fail(-2, "gemm_wx_tc: unsupported (pro, epi)");
 }
 
@@ -709,15 +749,19 @@ __global__ void __launch_bounds__(DW_THREADS, 1)
       // epilogue warps 0..3: C[o][c] += D
       const int q = warp;
       const int o = ob * DW_BM + q * 32 + lane;
-      float* C = p.C + (p.per_row ? (int64_t)row * p.M * p.ldc : 0) + (int64_t)o * p.ldc + cb * DW_BN;
+      const bool o_ok = o < p.M;                      // rows beyond M were zero-filled by the TMA
+      float* C = p.C + (p.per_row ? (int64_t)row * p.M * p.ldc : 0) + (int64_t)(o_ok ? o : 0) * p.ldc + cb * DW_BN;
+      const int ncols = min(DW_BN, p.N - cb * DW_BN);
       mbar_wait(bar_accf, 0);
       tc_fence_after();
 #pragma unroll 1
       for (int c0 = 0; c0 < DW_BN; c0 += 32) {
+        if (c0 >= ncols) break;                       // warp-uniform
         uint32_t r[32];
         tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) atomicAdd(C + c0 + i, __uint_as_float(r[i]));
+        for (int i = 0; i < 32; ++i)
+          if (o_ok && c0 + i < ncols) atomicAdd(C + c0 + i, __uint_as_float(r[i]));
       }
     }
   }
@@ -745,7 +789,6 @@ static int encode_map_sw(CUtensorMap* m, const void* ptr, int rank, const uint64
 }
 
 bool gemm_dw_tc_eligible(const GemmDwP& p, int pro_b) {
-  if (p.M % DW_BM || p.N % DW_BN) return false;
   if (!(pro_b == 0 || pro_b == 1)) return false;
   if ((p.lda & 3) || (p.ldb & 3) || (p.bsa & 3) || (p.bsb & 3) || !aligned16(p.A) || !aligned16(p.B)) return false;
   return true;
@@ -768,8 +811,8 @@ int launch_gemm_dw_tc(const GemmDwP& p, int pro_b, cudaStream_t st) {
   }
   DwTcParams P;
   P.g = p;
-  P.n_ob = p.M / DW_BM;
-  P.n_cb = p.N / DW_BN;
+  P.n_ob = cdiv(p.M, DW_BM);
+  P.n_cb = cdiv(p.N, DW_BN);
   const int tiles = P.n_ob * P.n_cb * p.n;
   const int KBT = cdiv(p.T, DW_BK);
   int ksplit = tiles >= 100 ? 1 : (148 + tiles - 1) / tiles;

@@ -45,14 +45,19 @@ __global__ void __launch_bounds__(256) cln_fwd_kernel(WesepClnFwdArgs a) {
   }
 }
 
-// grid (cdiv(T,128), n): each block covers 4 sub-tiles of 32 frames so the per-channel
-// (dgamma, dbeta) partials are reduced over 128 frames before touching global atomics.
+// grid (cdiv(T,1024), n): each block sweeps 32 sub-tiles of 32 frames and keeps its per-channel (dgamma, dbeta)
+// partials in shared memory, so global atomics are 2*C per CTA (not per sub-tile).
+constexpr int CLN_BWD_FRAMES = 512;
 __global__ void __launch_bounds__(256) cln_bwd_kernel(WesepClnBwdArgs a) {
+  extern __shared__ float cacc[];  // [2][C]
   __shared__ float red[2][8][33];
   const int tx = threadIdx.x, ty = threadIdx.y, n = blockIdx.y;
   const int nch = (a.C + 7) / 8;  // channels per ty
-  for (int sub = 0; sub < 4; ++sub) {
-    const int t = blockIdx.x * 128 + sub * 32 + tx;
+  for (int i = ty * 32 + tx; i < 2 * a.C; i += 256) cacc[i] = 0.f;
+  __syncthreads();
+  for (int sub = 0; sub < CLN_BWD_FRAMES / 32; ++sub) {
+    const int t = blockIdx.x * CLN_BWD_FRAMES + sub * 32 + tx;
+    if (blockIdx.x * CLN_BWD_FRAMES + sub * 32 >= a.T) break;   // block-uniform
     const bool ok = t < a.T;
     const float* x = a.x + (int64_t)n * a.C * a.ldx + t;
     const float* gy = a.gy + (int64_t)n * a.C * a.ldg + t;
@@ -86,13 +91,18 @@ __global__ void __launch_bounds__(256) cln_bwd_kernel(WesepClnBwdArgs a) {
         dg = gyv * xh;
         db = gyv;
       }
-      dg = warp_sum(dg);   // warp == fixed ty: reduces over the 32 frames
+      dg = warp_sum(dg);   // warp == fixed ty: reduces over the 32 frames; channel c is owned by this warp only
       db = warp_sum(db);
-      if (tx == 0 && c < a.C && (dg != 0.f || db != 0.f)) {
-        atomicAdd(a.dgamma + c, dg);
-        atomicAdd(a.dbeta + c, db);
+      if (tx == 0 && c < a.C) {
+        cacc[c] += dg;
+        cacc[a.C + c] += db;
       }
     }
+  }
+  __syncthreads();
+  for (int c = ty * 32 + tx; c < a.C; c += 256) {
+    atomicAdd(a.dgamma + c, cacc[c]);
+    atomicAdd(a.dbeta + c, cacc[a.C + c]);
   }
 }
 
@@ -166,7 +176,7 @@ extern "C" int wesep_b200_cln_fwd(const WesepClnFwdArgs* a, void* stream) {
 }
 extern "C" int wesep_b200_cln_bwd(const WesepClnBwdArgs* a, void* stream) {
   if (a->n <= 0 || a->C <= 0 || a->T <= 0) return fail(-1, "cln: empty shape");
-  cln_bwd_kernel<<<dim3(cdiv(a->T, 128), a->n), dim3(32, 8), 0, (cudaStream_t)stream>>>(*a);
+  cln_bwd_kernel<<<dim3(cdiv(a->T, CLN_BWD_FRAMES), a->n), dim3(32, 8), 2 * a->C * sizeof(float), (cudaStream_t)stream>>>(*a);
   WB_LAUNCH_CHECK("cln_bwd");
   return 0;
 }

@@ -312,6 +312,8 @@ __global__ void __launch_bounds__(ST_THREADS) tcn_dw_bwd_kernel(const StBwdP p) 
     const float m2 = (float)((p.rowacc[8 * n + 3] - p.rowacc[8 * n + 4]) / Mc);
     const float w0 = __ldg(p.wd + 3 * c), w1 = __ldg(p.wd + 3 * c + 1), w2 = __ldg(p.wd + 3 * c + 2);
     float* durow = p.du + ((int64_t)n * p.H + c) * p.ld;
+    // dy = r*(g1*dz - m1 - yhat1*m2) = cA*dz + cB*y1 + cC with y1 = prelu(u)
+    const float cA = r * gm, cB = -r * r * m2, cC = -r * m1 + r * r * m2 * mu;
     for (int i = 4 * sub; i < ST_TTB; i += 256) {
       const int t = t0 + i;
       if (t < p.T) {
@@ -320,30 +322,33 @@ __global__ void __launch_bounds__(ST_THREADS) tcn_dw_bwd_kernel(const StBwdP p) 
         taps4<DM>(z1s + halo + i, dil, zL, zC, zR);
         const float4 u4 = *reinterpret_cast<const float4*>(us + i);
         const float uu[4] = {u4.x, u4.y, u4.z, u4.w};
+        const bool full = t + 3 < p.T;   // only the last vector of a row can be partial
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const bool ok = t + k < p.T;
-          const float ddv = dC[k];                                    // 0 beyond T (masked at fill)
+          const bool ok = full || (t + k < p.T);
+          const float ddv = dC[k];                                      // 0 beyond T (masked at fill)
           const float dz = fmaf(w0, dR[k], fmaf(w1, ddv, w2 * dL[k]));  // dz1[t] = sum_j w[j] dd[t - (j-1) dil]
           const float uv = uu[k];
-          const float yh = (prelu_f(uv, a1) - mu) * r;
-          const float dy = r * (gm * dz - m1 - yh * m2);
-          const float duv = ok ? dy * (uv > 0.f ? 1.f : a1) : 0.f;
+          const bool pos = uv > 0.f;
+          const float y1 = pos ? uv : a1 * uv;
+          const float dy = fmaf(cA, dz, fmaf(cB, y1, cC));
+          float duv = pos ? dy : a1 * dy;
+          float dzy = dz * y1, dyu = pos ? 0.f : dy * uv, dzm = dz;
+          if (!ok) { duv = 0.f; dzy = 0.f; dyu = 0.f; dzm = 0.f; }
           o[k] = duv;
-          if (ok) {
-            acc[0] += dz;
-            acc[1] = fmaf(dz, yh, acc[1]);
-            acc[2] = fmaf(ddv, zL[k], acc[2]);
-            acc[3] = fmaf(ddv, zC[k], acc[3]);
-            acc[4] = fmaf(ddv, zR[k], acc[4]);
-            acc[5] += ddv;
-            acc[6] += duv;
-            dal += uv > 0.f ? 0.f : dy * uv;
-          }
+          acc[0] += dzm;                       // sum dz            -> dbeta1
+          acc[1] += dzy;                       // sum dz*y1         -> dgamma1 = r*(sum dz*y1 - mu*sum dz)
+          acc[2] = fmaf(ddv, zL[k], acc[2]);
+          acc[3] = fmaf(ddv, zC[k], acc[3]);
+          acc[4] = fmaf(ddv, zR[k], acc[4]);
+          acc[5] += ddv;
+          acc[6] += duv;
+          dal += dyu;
         }
         *reinterpret_cast<float4*>(durow + t) = make_float4(o[0], o[1], o[2], o[3]);
       }
     }
+    acc[1] = r * (acc[1] - mu * acc[0]);
   }
 #pragma unroll
   for (int i = 0; i < 7; ++i) acc[i] = warp_sum(acc[i]);

@@ -38,6 +38,36 @@ class ChannelWiseLayerNorm(nn.LayerNorm):
         return ops.cln(x, self.weight, self.bias, self.eps)
 
 
+class FiLM(nn.Module):
+    """Feature-wise Linear Modulation — reference wesep/modules/common/norm.py:84-139 (gamma/beta Linears,
+    zero-initialised).  Parameter holder: the modulation (1+gamma)*x + beta is applied by the fused fusion kernel."""
+
+    def __init__(self, feat_size, embed_size, num_film_layers=1, layer_norm=False):
+        super().__init__()
+        if num_film_layers != 1 or layer_norm:
+            raise NotImplementedError("FiLM: only num_film_layers=1, layer_norm=False (the reference's use) is accelerated")
+        self.feat_size = feat_size
+        self.embed_size = embed_size
+        self.num_film_layers = num_film_layers
+        self.layer_norm = None
+        self.gamma_fcs = nn.ModuleList([nn.Linear(embed_size, feat_size)])
+        self.beta_fcs = nn.ModuleList([nn.Linear(embed_size, feat_size)])
+        self.init_weights()
+
+    def init_weights(self):
+        for i in range(self.num_film_layers):
+            nn.init.zeros_(self.gamma_fcs[i].weight)
+            nn.init.zeros_(self.gamma_fcs[i].bias)
+            nn.init.zeros_(self.beta_fcs[i].weight)
+            nn.init.zeros_(self.beta_fcs[i].bias)
+
+    def row_affine(self, embed):
+        """embed [n, E] -> (1 + gamma [n, feat], beta [n, feat])"""
+        g = ops.LinearFn.apply(embed, self.gamma_fcs[0].weight, self.gamma_fcs[0].bias)
+        b = ops.LinearFn.apply(embed, self.beta_fcs[0].weight, self.beta_fcs[0].bias)
+        return 1 + g, b
+
+
 def select_norm(norm, dim):
     """reference wesep/modules/common/norm.py:69-81"""
     if norm not in ["cLN", "gLN", "BN"]:

@@ -687,3 +687,70 @@ class CrossEntropyFn(torch.autograd.Function):
 
 def cross_entropy(logits, labels):
     return CrossEntropyFn.apply(logits, labels)
+
+
+# --------------------------------------------------------------------------- alternative speaker fusion
+class Conv1x1RowBiasFn(torch.autograd.Function):
+    """y[n] = W x[n] + row_bias[n] (+ bias): the concat-type speaker fusion with the embedding half of the Linear
+    folded into a per-row bias (SpeakerFuseLayer 'concat', wesep/modules/common/speaker.py:88-94)."""
+
+    @staticmethod
+    def forward(ctx, x, W2d, row_bias):
+        x = as_act(x)
+        W2d = W2d.contiguous()
+        rb = row_bias.contiguous().float()
+        y = conv1x1_raw(x, W2d, False, W2d.shape[0], row_bias=rb)
+        ctx.save_for_backward(x, W2d)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, W2d = ctx.saved_tensors
+        g = as_act(gy)
+        dW = torch.zeros_like(W2d)
+        conv1x1_dw_raw(g, x, dW)
+        drb = rowsum_raw(g)
+        dx = conv1x1_raw(g, W2d, True, x.shape[1])
+        return dx, dW, drb
+
+
+class FusePreluGlnFn(torch.autograd.Function):
+    """z = gLN(PReLU(ra[n,c] * x + rb[n,c])): speaker fusion (multiply / additive / FiLM; identity affine for
+    concat) + the nn.PReLU and gLN that follow it in FuseSeparation (wesep/modules/tasnet/separation.py:116-126)."""
+
+    @staticmethod
+    def forward(ctx, x, ra, rb, alpha, gamma, beta):
+        x = as_act(x)
+        n, C, T = x.shape
+        dev = x.device
+        ra_c = None if ra is None else ra.reshape(n, C).contiguous().float()
+        rb_c = None if rb is None else rb.reshape(n, C).contiguous().float()
+        al, gm, bt = _vec(alpha), _vec(gamma), _vec(beta)
+        stats = torch.empty((n, 2), dtype=torch.float64, device=dev)
+        y = new_act(n, C, T, dev)
+        _lib.call("wesep_b200_fuse_prelu_gln_fwd", _args("WesepFuseArgs", n=n, C=C, T=T, ldx=x.stride(1), ldy=y.stride(1),
+                                                         x=x, ra=ra_c, rb=rb_c, alpha=al, gamma=gm, beta=bt, stats=stats,
+                                                         y=y), _stream())
+        ctx.flags = (ra is not None, rb is not None, None if ra is None else ra.shape, None if rb is None else rb.shape)
+        ctx.save_for_backward(x, ra_c, rb_c, al, gm, bt, stats)
+        return y
+
+    @staticmethod
+    def backward(ctx, gz):
+        x, ra_c, rb_c, al, gm, bt, stats = ctx.saved_tensors
+        n, C, T = x.shape
+        dev = x.device
+        has_a, has_b, sha, shb = ctx.flags
+        gz = as_act(gz)
+        dx = new_act(n, C, T, dev)
+        rowsums = torch.empty((n, 2), dtype=torch.float64, device=dev)
+        dra = torch.empty((n, C), dtype=torch.float32, device=dev) if has_a else None
+        drb = torch.empty((n, C), dtype=torch.float32, device=dev) if has_b else None
+        acc = torch.zeros(1 + 2 * C, dtype=torch.float32, device=dev)
+        _lib.call("wesep_b200_fuse_prelu_gln_bwd", _args("WesepFuseArgs", n=n, C=C, T=T, ldx=x.stride(1), ldg=gz.stride(1),
+                                                         lddx=dx.stride(1), x=x, ra=ra_c, rb=rb_c, alpha=al, gamma=gm,
+                                                         beta=bt, stats=stats, gz=gz, rowsums=rowsums, dx=dx, dra=dra,
+                                                         drb=drb, dalpha=acc[0:], dgamma=acc[1:], dbeta=acc[1 + C:]),
+                  _stream())
+        return (dx, None if dra is None else dra.view(sha), None if drb is None else drb.view(shb), acc[0:1],
+                acc[1:1 + C].view(C, 1), acc[1 + C:].view(C, 1))
