@@ -42,7 +42,8 @@ int wesep_b200_set_gemm_mode(int mode);
  * (M % 128 == 0, Kd % 16 == 0, Kd <= 512, a workspace is supplied); other shapes stay on backend 0. Process-wide. */
 int wesep_b200_set_gemm_backend(int backend);
 /* tcgen05 debug flags. bit 0: also store the explicitly truncated "hi" operand tile (default off: the tensor core
- * ignores the 13 low mantissa bits of tf32 inputs — measured identical results — so the raw tile serves as hi). */
+ * ignores the 13 low mantissa bits of tf32 inputs — measured identical results — so the raw tile serves as hi).
+ * bit 1: disable the 2-CTA (cta_group::2) GEMM variant.  bits 2-3: transform-warp groups (0 = default 2, 1 = one group, 2 = two, 3 = four; clamped so it divides the ring depth). */
 int wesep_b200_set_tc_flags(int flags);
 /* Workspace bytes the tcgen05 GEMM needs for an [M x Kd] weight (split hi/lo copies). */
 int64_t wesep_b200_gemm_ws_bytes(int M, int Kd);

@@ -68,6 +68,12 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
@@ -116,14 +122,18 @@ constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | 
                               ((uint32_t)(TC_BM >> 4) << 24);
 
 // ------------------------------------------------------------------------------------------ prep kernel
-// Whi_t[k][o] = tf32-truncated W[o][k] (or W[k][o] if w_trans), Wlo_t = W - Whi.  [Kd][M] row-major.
+// hi[oa][k][oi] = tf32-truncated W[o = 32*oa + oi][k] (or W[k][o] if w_trans), lo = W - hi; rows o >= M are zero.
+// Tiling by 32-channel atoms makes the CTA's 128 x 16 weight tile ONE 3-D TMA box (32, 16, 4).
 __global__ void split_w_kernel(const float* __restrict__ W, int64_t ldw, int w_trans, int M, int Kd, float* __restrict__ hi,
                                float* __restrict__ lo) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= M * Kd) return;
-  int k = idx / M, o = idx % M;
-  float w = w_trans ? W[(int64_t)k * ldw + o] : W[(int64_t)o * ldw + k];
-  float h = __uint_as_float(__float_as_uint(w) & 0xFFFFE000u);
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int M32 = (M + 31) & ~31;
+  if (idx >= M32 * Kd) return;
+  const int oi = idx & 31, k = (idx >> 5) % Kd, oa = (idx >> 5) / Kd;
+  const int o = oa * 32 + oi;
+  float w = 0.f;
+  if (o < M) w = w_trans ? W[(int64_t)k * ldw + o] : W[(int64_t)o * ldw + k];
+  const float h = __uint_as_float(__float_as_uint(w) & 0xFFFFE000u);
   hi[idx] = h;
   lo[idx] = w - h;
 }
@@ -132,6 +142,7 @@ struct TcParams {
   GemmWxP g;
   int n_ob, n_tt, n_tiles;
   int skip_hi_store;   // PRO 0 only: leave the raw fp32 tile as the "hi" operand (valid iff the MMA truncates to tf32)
+  int xf_groups;       // transform warps split into this many groups (1, 2, 4); group g handles stages with it % groups == g
 };
 int g_tc_flags = 0;
 
@@ -163,7 +174,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   if (tid == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(bar_full(s), 1);
-      mbar_init(bar_ready(s), 8);
+      mbar_init(bar_ready(s), 8 / P.xf_groups);
       mbar_init(bar_empty(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -197,14 +208,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           const uint32_t sb = base + s * TC_STAGE_BYTES;
           mbar_expect_tx(bar_full(s), TC_TX_BYTES);
           const int k0 = kb * TC_BK;
-#pragma unroll
-          for (int i = 0; i < TC_BM / 32; ++i) {
-            tma_load_2d(sb + TC_OFF_WHI + i * TC_BOX_BYTES, &map_whi, bar_full(s), o0 + 32 * i, k0);
-            tma_load_2d(sb + TC_OFF_WLO + i * TC_BOX_BYTES, &map_wlo, bar_full(s), o0 + 32 * i, k0);
-          }
-#pragma unroll
-          for (int j = 0; j < TC_BN / 32; ++j)
-            tma_load_3d(sb + TC_OFF_XHI + j * TC_BOX_BYTES, &map_x, bar_full(s), t0 + 32 * j, k0, n);
+          // 3 TMA operations per stage (per-box overhead, not bytes, bounds the small-box variant)
+          tma_load_3d(sb + TC_OFF_WHI, &map_whi, bar_full(s), 0, k0, o0 >> 5);
+          tma_load_3d(sb + TC_OFF_WLO, &map_wlo, bar_full(s), 0, k0, o0 >> 5);
+          tma_load_4d(sb + TC_OFF_XHI, &map_x, bar_full(s), 0, k0, t0 >> 5, n);
         }
       }
     }
@@ -242,6 +249,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   } else if (warp >= TC_W_XF) {
     // =========================================================================== transform warps
     const int tt_id = tid - TC_W_XF * 32;  // 0..255
+    const int xf_groups = P.xf_groups, xf_nthr = 256 / xf_groups;
+    const int xf_gid = tt_id / xf_nthr, xf_tid = tt_id % xf_nthr;   // group of this warp, thread index inside the group
     float alpha = 1.f;
     if constexpr (PRO >= 1) alpha = p.xf.alpha ? __ldg(p.xf.alpha) : 1.f;
     uint32_t it = 0;
@@ -265,14 +274,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         }
       }
       for (int kb = 0; kb < KB; ++kb, ++it) {
+        if ((int)(it % (uint32_t)xf_groups) != xf_gid) continue;   // another transform group owns this stage
         const int s = it % TC_STAGES;
         const uint32_t ph = (it / TC_STAGES) & 1;
         mbar_wait(bar_full(s), ph);
         uint8_t* xs_hi = gbase + s * TC_STAGE_BYTES + TC_OFF_XHI;
         uint8_t* xs_lo = gbase + s * TC_STAGE_BYTES + TC_OFF_XLO;
-#pragma unroll
-        for (int i = 0; i < TC_X_BYTES / 16 / 256; ++i) {
-          const int off = (tt_id + 256 * i) * 16;
+        for (int i = 0; i < TC_X_BYTES / 16 / xf_nthr; ++i) {
+          const int off = (xf_tid + xf_nthr * i) * 16;
           float4 v = *reinterpret_cast<const float4*>(xs_hi + off);
           if constexpr (PRO >= 1) {
             float c = 1.f, d = 0.f;
@@ -518,7 +527,7 @@ static int encode_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t*
 
 bool gemm_wx_tc_eligible(const GemmWxP& p, int pro, int epi) {
   if ((p.M & 3) || (p.Kd & 3) || p.Kd > TC_MAXK) return false;   // partial tiles: TMA zero-fill + epilogue row mask
-  if ((p.ldx & 3) || !aligned16(p.X) || (p.bsx & 3)) return false;
+  if ((p.ldx & 31) || (reinterpret_cast<uintptr_t>(p.X) & 127) || (p.bsx & 3)) return false;   // 4-D map over 128-byte atoms
   if (!(pro == 0 || pro == 2 || pro == 3)) return false;
   if (!(epi == 0 || epi == 1 || epi == 2 || epi == 3 || epi == 10)) return false;
   if (epi == 3 && ((p.ep.ldy2 & 3) || !aligned16(p.ep.Y2) || (p.ep.bsy2 & 3) || (p.ep.ldr & 3) || !aligned16(p.ep.R) || (p.ep.bsr & 3))) return false;
@@ -528,7 +537,7 @@ bool gemm_wx_tc_eligible(const GemmWxP& p, int pro, int epi) {
   return true;
 }
 
-size_t gemm_wx_tc_ws_bytes(int M, int Kd) { return (size_t)2 * M * Kd * sizeof(float); }
+size_t gemm_wx_tc_ws_bytes(int M, int Kd) { return (size_t)2 * ((M + 31) & ~31) * Kd * sizeof(float); }
 
 template <int PRO, int EPI>
 static int launch_tc_t(const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& mx, const TcParams& P, cudaStream_t st) {
@@ -546,30 +555,38 @@ static int launch_tc_t(const CUtensorMap& mh, const CUtensorMap& ml, const CUten
   return 0;
 }
 
+bool gemm_wx_tc2_eligible(const GemmWxP& p, int pro, int epi);
+int launch_gemm_wx_tc2(const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& mx, TcParams P, int pro, int epi,
+                       cudaStream_t st);
+
 // W is [M][Kd] (ldw) or, a_trans, [Kd][M] (ldw). ws: >= gemm_wx_tc_ws_bytes(M, Kd), 16-byte aligned.
 int launch_gemm_wx_tc(const GemmWxP& p, bool a_trans, int pro, int epi, void* ws, cudaStream_t st) {
   if (!gemm_wx_tc_eligible(p, pro, epi)) return fail(-2, "gemm_wx_tc: shape/config not eligible");
   if (!ws || !aligned16(ws)) return fail(-1, "gemm_wx_tc: workspace missing or misaligned");
+  const int M32 = (p.M + 31) & ~31;
   float* whi = reinterpret_cast<float*>(ws);
-  float* wlo = whi + (size_t)p.M * p.Kd;
+  float* wlo = whi + (size_t)M32 * p.Kd;
   {
-    int total = p.M * p.Kd;
+    int total = M32 * p.Kd;
     split_w_kernel<<<cdiv(total, 256), 256, 0, st>>>(p.W, p.ldw, a_trans ? 1 : 0, p.M, p.Kd, whi, wlo);
     WB_LAUNCH_CHECK("split_w");
   }
-  CUtensorMap mh, ml, mx;
-  {
-    uint64_t dims[2] = {(uint64_t)p.M, (uint64_t)p.Kd};
-    uint64_t strides[1] = {(uint64_t)p.M * 4};
-    uint32_t box[2] = {32, TC_BK};
-    if (int rc = encode_map(&mh, whi, 2, dims, strides, box)) return rc;
-    if (int rc = encode_map(&ml, wlo, 2, dims, strides, box)) return rc;
+  CUtensorMap mh, ml, mx, mx2;
+  {  // weights, pre-tiled [o/32][k][32]: dims (32, Kd, M/32), box (32, 16, 4) = the CTA's whole 128 x 16 tile
+    uint64_t dims[3] = {32, (uint64_t)p.Kd, (uint64_t)(M32 / 32)};
+    uint64_t strides[2] = {128, (uint64_t)p.Kd * 128};
+    uint32_t box[3] = {32, TC_BK, TC_BM / 32};
+    if (int rc = encode_map(&mh, whi, 3, dims, strides, box)) return rc;
+    if (int rc = encode_map(&ml, wlo, 3, dims, strides, box)) return rc;
   }
-  {
-    uint64_t dims[3] = {(uint64_t)p.T, (uint64_t)p.Kd, (uint64_t)p.n};
-    uint64_t strides[2] = {(uint64_t)p.ldx * 4, (uint64_t)p.bsx * 4};
-    uint32_t box[3] = {32, TC_BK, 1};
-    if (int rc = encode_map(&mx, p.X, 3, dims, strides, box)) return rc;
+  {  // activations [n][k][ld] viewed as (32 t, Kd, ld/32 atoms, n): atoms are 128-byte row segments (ld % 32 == 0),
+     // so one box (32, 16, 8, 1) lands the 16 x 256 tile as 8 swizzle-atom columns; atoms beyond T are zero-filled
+    uint64_t dims[4] = {32, (uint64_t)p.Kd, (uint64_t)cdiv(p.T, 32), (uint64_t)p.n};
+    uint64_t strides[3] = {(uint64_t)p.ldx * 4, 128, (uint64_t)p.bsx * 4};
+    uint32_t box[4] = {32, TC_BK, TC_BN / 32, 1};
+    if (int rc = encode_map(&mx, p.X, 4, dims, strides, box)) return rc;
+    uint32_t box2[4] = {32, TC_BK, TC_BN / 64, 1};
+    if (int rc = encode_map(&mx2, p.X, 4, dims, strides, box2)) return rc;
   }
   TcParams P;
   P.g = p;
@@ -577,6 +594,17 @@ int launch_gemm_wx_tc(const GemmWxP& p, bool a_trans, int pro, int epi, void* ws
   P.n_tt = cdiv(p.T, TC_BN);
   P.n_tiles = P.n_ob * P.n_tt * p.n;
   P.skip_hi_store = (g_tc_flags & 1) ? 0 : 1;   // default: raw tile is the hi operand (HW truncates tf32 inputs; measured)
+  // transform-warp groups: bits 2-3 of the flags (0 = default 2 groups, 1 -> 1, 2 -> 2, 3 -> 4).  The group count MUST
+  // divide the stage count (a slot must always belong to the same group, or a group could run two mbarrier phases
+  // ahead and pass a parity wait spuriously): 1-CTA ring = 4 stages, 2-CTA ring = 6 stages.
+  {
+    const int sel = (g_tc_flags >> 2) & 3;
+    P.xf_groups = sel == 1 ? 1 : sel == 3 ? 4 : 2;
+  }
+  if (gemm_wx_tc2_eligible(p, pro, epi)) {      // 2-CTA (cta_group::2) kernel for 256-channel multiples
+    int rc = launch_gemm_wx_tc2(mh, ml, mx2, P, pro, epi, st);
+    if (rc != -100) return rc;
+  }
   if (pro == 0 && epi == 0) return launch_tc_t<0, 0>(mh, ml, mx, P, st);
   if (pro == 0 && epi == 2) return launch_tc_t<0, 2>(mh, ml, mx, P, st);
   if (pro == 0 && epi == 10) return launch_tc_t<0, 10>(mh, ml, mx, P, st);
@@ -832,6 +860,426 @@ int launch_gemm_dw_tc(const GemmDwP& p, int pro_b, cudaStream_t st) {
   }
   WB_LAUNCH_CHECK("gemm_dw_tc");
   return 0;
+}
+
+}  // namespace wb
+
+// ================================================================================================
+// 2-CTA variant of gemm_wx_tc (tcgen05 cta_group::2): a cluster of two CTAs (one TPC) computes a
+// 256-channel x 256-frame tile.  Each CTA stages ITS 128 weight rows and ITS 128-frame half of the
+// activation tile, so per-SM shared-memory traffic (MMA operand reads + TMA fills + hi/lo transform) drops from
+// ~177 B/clk to ~116 B/clk — below the 128 B/clk/SM limit that bounds the 1-CTA kernel — and the smaller
+// stages (32 KB) allow a 6-deep TMA ring.  The leader CTA's MMA thread issues tcgen05.mma.cta_group::2
+// (M = 256) reading both CTAs' smem; tcgen05.commit multicasts to both CTAs' barriers; the peer's transform /
+// epilogue warps signal the leader's barriers with remote mbarrier arrives.
+// ================================================================================================
+namespace wb {
+
+constexpr int T2_STAGES = 6;
+constexpr int T2_XH_BYTES = (TC_BN / 2 / 32) * TC_BOX_BYTES;  // this CTA's half of the X tile: 4 boxes = 8192
+constexpr int T2_OFF_WHI = 0, T2_OFF_WLO = TC_W_BYTES, T2_OFF_XHI = 2 * TC_W_BYTES, T2_OFF_XLO = 2 * TC_W_BYTES + T2_XH_BYTES;
+constexpr int T2_STAGE_BYTES = 2 * TC_W_BYTES + 2 * T2_XH_BYTES;  // 32768
+constexpr int T2_TX_BYTES = 2 * TC_W_BYTES + T2_XH_BYTES;          // per CTA per stage
+constexpr int T2_SMEM_BYTES = T2_STAGES * T2_STAGE_BYTES + TC_SMEM_AUX + 1024;
+// D=f32, A=B=tf32, both MN-major, N=256, M=256 (cta_group::2)
+constexpr uint32_t T2_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(TC_BN >> 3) << 17) |
+                              ((uint32_t)(256 >> 4) << 24);
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+// arrive on the barrier at the same smem offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n"
+      "}\n" ::"r"(bar),
+      "r"(rank)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc2(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_2cta(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+template <int PRO, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+    gemm_wx_tc2_kernel(const __grid_constant__ CUtensorMap map_whi, const __grid_constant__ CUtensorMap map_wlo,
+                       const __grid_constant__ CUtensorMap map_x2, const TcParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const GemmWxP& p = P.g;
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw);
+  float* sc = reinterpret_cast<float*>(gbase + T2_STAGES * T2_STAGE_BYTES);
+  float* sh = sc + TC_MAXK;
+  const uint32_t bar0 = base + T2_STAGES * T2_STAGE_BYTES + 2 * TC_MAXK * 4;
+  auto bar_full = [&](int s) { return bar0 + 8u * s; };
+  auto bar_ready = [&](int s) { return bar0 + 8u * (T2_STAGES + s); };
+  auto bar_empty = [&](int s) { return bar0 + 8u * (2 * T2_STAGES + s); };
+  auto bar_accf = [&](int a) { return bar0 + 8u * (3 * T2_STAGES + a); };
+  auto bar_acce = [&](int a) { return bar0 + 8u * (3 * T2_STAGES + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + T2_STAGES * T2_STAGE_BYTES + 2 * TC_MAXK * 4 + 8 * (3 * T2_STAGES + 4));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();       // 0 = leader
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int KB = (p.Kd + TC_BK - 1) / TC_BK;
+
+  if (tid == 0) {
+    for (int s = 0; s < T2_STAGES; ++s) {
+      mbar_init(bar_full(s), 1);     // local TMA transaction barrier
+      mbar_init(bar_ready(s), 16 / P.xf_groups);   // (leader's copy is used) transform warps of the owning group x 2 CTAs
+      mbar_init(bar_empty(s), 1);    // multicast tcgen05.commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_accf(a), 1);     // multicast tcgen05.commit
+      mbar_init(bar_acce(a), 16);    // (leader's copy is used) 8 epilogue warps x 2 CTAs
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    fence_proxy_async();
+  }
+  if (warp == TC_W_TMA) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // both CTAs' barriers are initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile decode shared by all roles: tile -> (channel pair, frame tile, row)
+  auto decode = [&](int tile, int& o0, int& t0, int& n) {
+    const int ob2 = tile % P.n_ob, rest = tile / P.n_ob;
+    t0 = (rest % P.n_tt) * TC_BN;
+    n = rest / P.n_tt;
+    o0 = ob2 * 256 + (int)rank * TC_BM;
+  };
+
+  if (warp == TC_W_TMA) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = cluster_id; tile < P.n_tiles; tile += n_clusters) {
+        int o0, t0, n;
+        decode(tile, o0, t0, n);
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % T2_STAGES;
+          const uint32_t ph = (it / T2_STAGES) & 1;
+          mbar_wait(bar_empty(s), ph ^ 1);
+          const uint32_t sb = base + s * T2_STAGE_BYTES;
+          mbar_expect_tx(bar_full(s), T2_TX_BYTES);
+          const int k0 = kb * TC_BK;
+          tma_load_3d(sb + T2_OFF_WHI, &map_whi, bar_full(s), 0, k0, o0 >> 5);
+          tma_load_3d(sb + T2_OFF_WLO, &map_wlo, bar_full(s), 0, k0, o0 >> 5);
+          tma_load_4d(sb + T2_OFF_XHI, &map_x2, bar_full(s), 0, k0, (t0 >> 5) + 4 * (int)rank, n);
+        }
+      }
+    }
+  } else if (warp == TC_W_MMA) {
+    if (lane == 0 && rank == 0) {   // leader CTA issues for the pair
+      uint32_t it = 0, ti = 0;
+      for (int tile = cluster_id; tile < P.n_tiles; tile += n_clusters, ++ti) {
+        const int a = ti & 1;
+        const uint32_t aph = (ti >> 1) & 1;
+        mbar_wait(bar_acce(a), aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + a * TC_BN;
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % T2_STAGES;
+          const uint32_t ph = (it / T2_STAGES) & 1;
+          mbar_wait(bar_ready(s), ph);
+          tc_fence_after();
+          const uint32_t sb = base + s * T2_STAGE_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < TC_BK / 8; ++ks) {
+            const uint64_t a_hi = make_desc_mn_sw128(sb + T2_OFF_WHI + ks * 1024);
+            const uint64_t a_lo = make_desc_mn_sw128(sb + T2_OFF_WLO + ks * 1024);
+            const uint64_t b_hi = make_desc_mn_sw128(sb + T2_OFF_XHI + ks * 1024);
+            const uint64_t b_lo = make_desc_mn_sw128(sb + T2_OFF_XLO + ks * 1024);
+            tc_mma_tf32_2cta(d_tmem, a_lo, b_hi, T2_IDESC, (kb | ks) != 0 ? 1u : 0u);
+            tc_mma_tf32_2cta(d_tmem, a_hi, b_lo, T2_IDESC, 1u);
+            tc_mma_tf32_2cta(d_tmem, a_hi, b_hi, T2_IDESC, 1u);
+          }
+          tc_commit_mc2(bar_empty(s));   // frees stage s in BOTH CTAs
+        }
+        tc_commit_mc2(bar_accf(a));      // accumulators complete in BOTH CTAs
+      }
+    }
+  } else if (warp >= TC_W_XF) {
+    const int tt_id = tid - TC_W_XF * 32;
+    const int xf_groups = P.xf_groups, xf_nthr = 256 / xf_groups;
+    const int xf_gid = tt_id / xf_nthr, xf_tid = tt_id % xf_nthr;
+    float alpha = 1.f;
+    if constexpr (PRO >= 1) alpha = p.xf.alpha ? __ldg(p.xf.alpha) : 1.f;
+    uint32_t it = 0;
+    int cur_n = -1;
+    for (int tile = cluster_id; tile < P.n_tiles; tile += n_clusters) {
+      int o0, t0, n;
+      decode(tile, o0, t0, n);
+      if constexpr (PRO >= 2) {
+        if (n != cur_n) {
+          asm volatile("bar.sync 1, 256;\n" ::: "memory");
+          float mu = 0.f, r = 1.f;
+          if (p.xf.row_stats) gln_mean_rstd(p.xf.row_stats + 2 * n, p.xf.count, p.xf.eps, mu, r);
+          for (int k = tt_id; k < p.Kd; k += 256) {
+            const float gm = p.xf.ch_scale ? __ldg(p.xf.ch_scale + k) : 1.f;
+            const float bt = p.xf.ch_shift ? __ldg(p.xf.ch_shift + k) : 0.f;
+            sc[k] = gm * r;
+            sh[k] = bt - gm * mu * r;
+          }
+          asm volatile("bar.sync 1, 256;\n" ::: "memory");
+          cur_n = n;
+        }
+      }
+      for (int kb = 0; kb < KB; ++kb, ++it) {
+        if ((int)(it % (uint32_t)xf_groups) != xf_gid) continue;
+        const int s = it % T2_STAGES;
+        const uint32_t ph = (it / T2_STAGES) & 1;
+        mbar_wait(bar_full(s), ph);
+        uint8_t* xs_hi = gbase + s * T2_STAGE_BYTES + T2_OFF_XHI;
+        uint8_t* xs_lo = gbase + s * T2_STAGE_BYTES + T2_OFF_XLO;
+        for (int i = 0; i < T2_XH_BYTES / 16 / xf_nthr; ++i) {
+          const int off = (xf_tid + xf_nthr * i) * 16;
+          float4 v = *reinterpret_cast<const float4*>(xs_hi + off);
+          if constexpr (PRO >= 1) {
+            float c = 1.f, d = 0.f;
+            if constexpr (PRO >= 2) {
+              const int kk = kb * TC_BK + ((off % TC_BOX_BYTES) >> 7);
+              const bool kok = kk < p.Kd;
+              c = kok ? sc[kk] : 0.f;
+              d = kok ? sh[kk] : 0.f;
+            }
+            if constexpr (PRO == 3) {
+              v.x = prelu_f(fmaf(c, v.x, d), alpha); v.y = prelu_f(fmaf(c, v.y, d), alpha);
+              v.z = prelu_f(fmaf(c, v.z, d), alpha); v.w = prelu_f(fmaf(c, v.w, d), alpha);
+            } else {
+              v.x = fmaf(c, prelu_f(v.x, alpha), d); v.y = fmaf(c, prelu_f(v.y, alpha), d);
+              v.z = fmaf(c, prelu_f(v.z, alpha), d); v.w = fmaf(c, prelu_f(v.w, alpha), d);
+            }
+          }
+          float4 h, l;
+          h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+          h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+          h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+          h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+          if (PRO != 0 || !P.skip_hi_store) *reinterpret_cast<float4*>(xs_hi + off) = h;
+          *reinterpret_cast<float4*>(xs_lo + off) = l;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {   // signal the LEADER's ready barrier (it gates the pair's MMAs)
+          if (rank == 0) mbar_arrive(bar_ready(s));
+          else mbar_arrive_cluster(bar_ready(s), 0);
+        }
+      }
+    }
+  } else {
+    // epilogue warps 0..7 (identical to the 1-CTA kernel, on this CTA's 128 channels)
+    const int q = warp & 3;
+    const int chalf = warp >> 2;
+    const EpiP& e = p.ep;
+    uint32_t ti = 0;
+    for (int tile = cluster_id; tile < P.n_tiles; tile += n_clusters, ++ti) {
+      int o0, t0, n;
+      decode(tile, o0, t0, n);
+      const int o = o0 + q * 32 + lane;   // M % 256 == 0: always valid
+      const int a = ti & 1;
+      const uint32_t aph = (ti >> 1) & 1;
+      float bias_o = 0.f;
+      if (e.bias) bias_o = __ldg(e.bias + o);
+      if (e.row_bias) bias_o += __ldg(e.row_bias + (int64_t)n * p.M + o);
+      float out_alpha = 1.f;
+      if constexpr (EPI == 0) out_alpha = e.out_alpha ? __ldg(e.out_alpha) : 1.f;
+      float mu2 = 0.f, r2 = 1.f, a2 = 1.f, gam2 = 0.f, mh = 0.f, mhy = 0.f, gam1 = 0.f, bet1 = 0.f, bdm = 0.f, w0 = 0.f, w1 = 0.f,
+            w2 = 0.f;
+      if constexpr (EPI == 10) {
+        gln_mean_rstd(e.stats2 + 2 * n, e.count2, e.eps2, mu2, r2);
+        a2 = __ldg(e.a2); gam2 = __ldg(e.g2 + o);
+        mh = (float)(e.rowsc[8 * n + 0] / e.count2); mhy = (float)(e.rowsc[8 * n + 1] / e.count2);
+        gam1 = __ldg(e.g1 + o); bet1 = __ldg(e.be1 + o); bdm = __ldg(e.bd + o);
+        w0 = __ldg(e.wd + 3 * o); w1 = __ldg(e.wd + 3 * o + 1); w2 = __ldg(e.wd + 3 * o + 2);
+      }
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, sL = 0.f, sR = 0.f;
+      float cA = 0.f, cB = 0.f, cC = 0.f;
+      if constexpr (EPI == 10) {
+        cA = r2 * gam2;
+        cB = -r2 * r2 * mhy;
+        cC = -r2 * mh + r2 * r2 * mhy * mu2;
+      }
+      mbar_wait(bar_accf(a), aph);
+      tc_fence_after();
+      float* yrow = e.Y + n * e.bsy + (int64_t)o * e.ldy;
+#pragma unroll 1
+      for (int c0 = chalf * (TC_BN / 2); c0 < (chalf + 1) * (TC_BN / 2); c0 += 32) {
+        if (t0 + c0 >= p.T) break;
+        const bool edge_chunk = (EPI == 10) && ((t0 + c0 < e.dil) || (t0 + c0 + 32 > p.T - e.dil));
+        float4 gop[8];
+        if constexpr (EPI == 2 || EPI == 10) {
+          const float* gsrc = (EPI == 10) ? (e.d + n * e.bsd + (int64_t)o * e.ldd) : (e.R + n * e.bsr + (int64_t)o * e.ldr);
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const int t = t0 + c0 + 4 * g;
+            gop[g] = (t < p.T) ? *reinterpret_cast<const float4*>(gsrc + t) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        uint32_t r[32];
+        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TC_BN + c0), r);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const int t = t0 + c0 + 4 * g;
+          if (t < p.T) {
+            float v[4] = {__uint_as_float(r[4 * g]) + bias_o, __uint_as_float(r[4 * g + 1]) + bias_o,
+                          __uint_as_float(r[4 * g + 2]) + bias_o, __uint_as_float(r[4 * g + 3]) + bias_o};
+            if constexpr (EPI == 0) {
+              *reinterpret_cast<float4*>(yrow + t) = make_float4(v[0], v[1], v[2], v[3]);
+              if (e.out_stats) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float y = (t + i < p.T) ? prelu_f(v[i], out_alpha) : 0.f;
+                  s0 += y;
+                  s1 = fmaf(y, y, s1);
+                }
+              }
+            } else if constexpr (EPI == 2) {
+              const float4 rr = gop[g];
+              *reinterpret_cast<float4*>(yrow + t) = make_float4(v[0] + rr.x, v[1] + rr.y, v[2] + rr.z, v[3] + rr.w);
+            } else if constexpr (EPI == 10) {
+              const float4 d4 = gop[g];
+              const float draw[4] = {d4.x, d4.y, d4.z, d4.w};
+              float dd[4];
+              if (!edge_chunk) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float dvi = draw[i];
+                  const bool pos = dvi > 0.f;
+                  const float y2 = pos ? dvi : a2 * dvi;
+                  const float dy2 = fmaf(cA, v[i], fmaf(cB, y2, cC));
+                  const float ddv = pos ? dy2 : a2 * dy2;
+                  dd[i] = ddv;
+                  s0 += ddv;
+                  s1 = fmaf(ddv, dvi, s1);
+                  s3 += pos ? 0.f : dy2 * dvi;
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const int tt_ = t + i;
+                  const bool ok = tt_ < p.T;
+                  const float dvi = ok ? draw[i] : 1.f;
+                  const bool pos = dvi > 0.f;
+                  const float y2 = pos ? dvi : a2 * dvi;
+                  const float dy2 = ok ? fmaf(cA, v[i], fmaf(cB, y2, cC)) : 0.f;
+                  const float ddv = pos ? dy2 : a2 * dy2;
+                  dd[i] = ddv;
+                  s0 += ddv;
+                  s1 = fmaf(ddv, dvi, s1);
+                  s3 += pos ? 0.f : dy2 * dvi;
+                  sL += tt_ < e.dil ? ddv : 0.f;
+                  sR += tt_ >= p.T - e.dil ? ddv : 0.f;
+                }
+              }
+              *reinterpret_cast<float4*>(yrow + t) = make_float4(dd[0], dd[1], dd[2], dd[3]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {   // release the accumulator buffer: the LEADER's barrier gates the pair's next MMAs
+        if (rank == 0) mbar_arrive(bar_acce(a));
+        else mbar_arrive_cluster(bar_acce(a), 0);
+      }
+      if constexpr (EPI == 0) {
+        if (e.out_stats) {
+          s0 = warp_sum(s0);
+          s1 = warp_sum(s1);
+          if (lane == 0) {
+            atomicAdd(e.out_stats + 2 * n, (double)s0);
+            atomicAdd(e.out_stats + 2 * n + 1, (double)s1);
+          }
+        }
+      }
+      if constexpr (EPI == 10) {
+        const float S = s0, SD = s1;
+        const float kS = (w0 + w1 + w2) * S - w0 * sL - w2 * sR;
+        s0 = gam1 * kS;
+        s1 = SD - bdm * S;
+        s2 = bet1 * kS;
+        s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
+        if (lane == 0) {
+          atomicAdd(e.rowacc + 8 * n + 2, (double)s0);
+          atomicAdd(e.rowacc + 8 * n + 3, (double)s1);
+          atomicAdd(e.rowacc + 8 * n + 4, (double)s2);
+          atomicAdd(e.rowacc + 8 * n + 5, (double)s3);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // the peer may still be reading this CTA's smem / signalling its barriers until here
+  if (warp == TC_W_TMA) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+bool gemm_wx_tc2_eligible(const GemmWxP& p, int pro, int epi) {
+  if (g_tc_flags & 2) return false;              // debug switch: force the 1-CTA kernel
+  if (p.M % 256) return false;
+  if (!(epi == 0 || epi == 2 || epi == 10)) return false;
+  if (epi == 0 && p.ep.ch_stats) return false;
+  return gemm_wx_tc_eligible(p, pro, epi);
+}
+
+template <int PRO, int EPI>
+static int launch_tc2_t(const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& mx, const TcParams& P, cudaStream_t st) {
+  auto k = gemm_wx_tc2_kernel<PRO, EPI>;
+  WB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
+  static int n_sm = 0;
+  if (!n_sm) {
+    int dev = 0;
+    WB_CUDA(cudaGetDevice(&dev));
+    WB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  }
+  int clusters = P.n_tiles < n_sm / 2 ? P.n_tiles : n_sm / 2;
+  k<<<2 * clusters, TC_THREADS, T2_SMEM_BYTES, st>>>(mh, ml, mx, P);
+  WB_LAUNCH_CHECK("gemm_wx_tc2");
+  return 0;
+}
+
+int launch_gemm_wx_tc2(const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& mx, TcParams P, int pro, int epi,
+                       cudaStream_t st) {
+  if (T2_STAGES % P.xf_groups) P.xf_groups = 2;   // must divide the ring depth (see launch_gemm_wx_tc)
+  P.n_ob = P.g.M / 256;                       // channel PAIRS
+  P.n_tiles = P.n_ob * P.n_tt * P.g.n;
+  if (pro == 0 && epi == 0) return launch_tc2_t<0, 0>(mh, ml, mx, P, st);
+  if (pro == 0 && epi == 2) return launch_tc2_t<0, 2>(mh, ml, mx, P, st);
+  if (pro == 0 && epi == 10) return launch_tc2_t<0, 10>(mh, ml, mx, P, st);
+  if (pro == 2 && epi == 2) return launch_tc2_t<2, 2>(mh, ml, mx, P, st);
+  if (pro == 3 && epi == 0) return launch_tc2_t<3, 0>(mh, ml, mx, P, st);
+  return -100;                                // not instantiated: caller falls back to the 1-CTA kernel
 }
 
 }  // namespace wb

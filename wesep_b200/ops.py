@@ -4,7 +4,7 @@ PyTorch here is plumbing only: device memory (caching allocator), streams and th
 tape.  All arithmetic on the hot path runs in libwesep_b200.so; there is no fallback.
 
 Activation layout ("act"): fp32 ``[n, C, T]`` views of ``[n, C, ld]`` storage with the time
-axis contiguous and ``ld = ceil4(T)`` so every row starts 16-byte aligned (6399 frames -> 6400).
+axis contiguous and ``ld = ceil32(T)`` so every row is a whole number of 128-byte TMA atoms (6399 frames -> 6400).
 """
 import torch
 
@@ -51,7 +51,8 @@ def _check_cuda(*ts):
 
 
 def ceil4(T):
-    return (T + 3) // 4 * 4
+    """row stride of an act tensor: a multiple of 32 floats (128 B) so rows are whole TMA swizzle atoms."""
+    return (T + 31) // 32 * 32
 
 
 def new_act(n, C, T, device, zero=False):
