@@ -689,7 +689,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1)
   if (tid == 0) {
     for (int s = 0; s < DW_STAGES; ++s) {
       mbar_init(bar_full(s), 1);
-      mbar_init(bar_ready(s), 8);
+      mbar_init(bar_ready(s), 4);   // 2 transform groups of 4 warps; group g owns stages with it % 2 == g
       mbar_init(bar_empty(s), 1);
     }
     mbar_init(bar_accf, 1);
@@ -745,14 +745,15 @@ __global__ void __launch_bounds__(DW_THREADS, 1)
       const int tt_id = tid - 6 * 32;
       float alpha = 1.f;
       if constexpr (PRO_B == 1) alpha = p.xb.alpha ? __ldg(p.xb.alpha) : 1.f;
-      for (int it = 0; it < KB; ++it) {
+      const int xf_gid = tt_id >> 7, xf_tid = tt_id & 127;   // DW_STAGES % 2 == 0: a slot always belongs to the same group
+      for (int it = xf_gid; it < KB; it += 2) {
         const int s = it % DW_STAGES;
         const uint32_t ph = (it / DW_STAGES) & 1;
         mbar_wait(bar_full(s), ph);
         uint8_t* st = gbase + s * DW_STAGE_BYTES;
 #pragma unroll
-        for (int i = 0; i < (DW_A_BYTES + DW_B_BYTES) / 16 / 256; ++i) {
-          const int idx = tt_id + 256 * i;              // float4 index over [A tile | B tile]
+        for (int i = 0; i < (DW_A_BYTES + DW_B_BYTES) / 16 / 128; ++i) {
+          const int idx = xf_tid + 128 * i;             // float4 index over [A tile | B tile]
           const bool is_b = idx >= DW_A_BYTES / 16;
           const int off = is_b ? (idx * 16 - DW_A_BYTES) : idx * 16;
           uint8_t* hi_p = st + (is_b ? DW_OFF_BHI : DW_OFF_AHI) + off;
