@@ -36,3 +36,9 @@ for flags, name in [(2 | 4, "1cta g1"), (2, "1cta g2"), (2 | 12, "1cta g4"), (4,
     err = float((yy - ref).abs().max())
     print(f"{name}: K2 {k2:.1f} us  K4 {k4:.1f} us  maxdiff vs first {err:.2e}", flush=True)
 _lib.lib().wesep_b200_set_tc_flags(0)
+
+# epilogue-pattern experiment: same GEMM as K2 (M=512, K=256) with (a) plain store, (b) residual load+store (EPI 2)
+r512 = ops.new_act(n, 512, K, DEV); r512.normal_()
+ka = timed(lambda: ops.conv1x1_raw(x256, W1, False, 512, Y=y512))
+kb = timed(lambda: ops.conv1x1_raw(x256, W1, False, 512, Y=y512, epi=2, R=r512))
+print(f"M=512 K=256: store-only {ka:.1f} us   residual load+store {kb:.1f} us", flush=True)
