@@ -26,7 +26,7 @@ def timed(fn, reps=10):
 
 
 ref = None
-for flags, name in [(2 | 4, "1cta g1"), (2, "1cta g2"), (2 | 12, "1cta g4"), (4, "2cta g1"), (0, "2cta g2 (default)")]:
+for flags, name in [(2, "1cta g2"), (4, "2cta g1"), (0, "2cta g2 (default)")]:
     _lib.lib().wesep_b200_set_tc_flags(flags)
     k2 = timed(lambda: ops.conv1x1_raw(x256, W1, False, 512, Y=y512, out_stats=stats, out_alpha=al))
     k4 = timed(lambda: ops.conv1x1_raw(x512, W3, False, 256, Y=y256, epi=2, R=x256))
@@ -37,8 +37,13 @@ for flags, name in [(2 | 4, "1cta g1"), (2, "1cta g2"), (2 | 12, "1cta g4"), (4,
     print(f"{name}: K2 {k2:.1f} us  K4 {k4:.1f} us  maxdiff vs first {err:.2e}", flush=True)
 _lib.lib().wesep_b200_set_tc_flags(0)
 
-# epilogue-pattern experiment: same GEMM as K2 (M=512, K=256) with (a) plain store, (b) residual load+store (EPI 2)
+# epilogue-pattern experiment: same GEMM as K2 (M=512, K=256) with (a) plain store, (b) residual load+store (EPI 2),
+# under the debug flags of the 2-CTA kernel (bit4 no epilogue loads, bit5 no epilogue stores, bit6 no transform work)
 r512 = ops.new_act(n, 512, K, DEV); r512.normal_()
-ka = timed(lambda: ops.conv1x1_raw(x256, W1, False, 512, Y=y512))
-kb = timed(lambda: ops.conv1x1_raw(x256, W1, False, 512, Y=y512, epi=2, R=r512))
-print(f"M=512 K=256: store-only {ka:.1f} us   residual load+store {kb:.1f} us", flush=True)
+for dbg in [0, 1, 2, 3, 4, 7]:
+    _lib.lib().wesep_b200_set_tc_flags(dbg << 4)
+    ka = timed(lambda: ops.conv1x1_raw(x256, W1, False, 512, Y=y512))
+    kb = timed(lambda: ops.conv1x1_raw(x256, W1, False, 512, Y=y512, epi=2, R=r512))
+    kc = timed(lambda: ops.conv1x1_raw(x512, W3, False, 256, Y=y256, epi=2, R=x256))
+    print(f"dbg={dbg} (1 noload 2 nostore 4 noxf)  M=512 K=256: store-only {ka:.1f} us  load+store {kb:.1f} us ;  M=256 K=512 load+store {kc:.1f} us", flush=True)
+_lib.lib().wesep_b200_set_tc_flags(0)

@@ -103,6 +103,25 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
 
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+// TMA store of one box (shared -> global), bulk-group completion
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];\n" ::"l"(map), "r"(src), "r"(c0),
+               "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
+
 // Shared-memory matrix descriptor: MN-major 32-bit (tf32) operand.  For MN-major tf32 the only legal smem layout
 // is SWIZZLE_128B_BASE32B (cutlass sm100_common.inl:92; cute Layout_MN_SW128_32B_Atom = Swizzle<2,5,2> over
 // 32 floats x 4 K-rows): 128-byte rows, 32-byte swizzle granules, K atoms of 4 rows (512 B).  The matching TMA mode
@@ -143,6 +162,7 @@ struct TcParams {
   int n_ob, n_tt, n_tiles;
   int skip_hi_store;   // PRO 0 only: leave the raw fp32 tile as the "hi" operand (valid iff the MMA truncates to tf32)
   int xf_groups;       // transform warps split into this many groups (1, 2, 4); group g handles stages with it % groups == g
+  int dbg;             // timing experiments only (2-CTA kernel): 1 = no epilogue loads, 2 = no epilogue stores, 4 = no transform
 };
 int g_tc_flags = 0;
 
@@ -600,6 +620,7 @@ int launch_gemm_wx_tc(const GemmWxP& p, bool a_trans, int pro, int epi, void* ws
   {
     const int sel = (g_tc_flags >> 2) & 3;
     P.xf_groups = sel == 1 ? 1 : sel == 3 ? 4 : 2;
+    P.dbg = (g_tc_flags >> 4) & 7;
   }
   if (gemm_wx_tc2_eligible(p, pro, epi)) {      // 2-CTA (cta_group::2) kernel for 256-channel multiples
     int rc = launch_gemm_wx_tc2(mh, ml, mx2, P, pro, epi, st);
@@ -802,8 +823,8 @@ __global__ void __launch_bounds__(DW_THREADS, 1)
   }
 }
 
-static int encode_map_sw(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                         const uint32_t* box, CUtensorMapSwizzle sw) {
+int encode_map_sw(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box, CUtensorMapSwizzle sw) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(-3, "cuTensorMapEncodeTiled entry point not available");
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
@@ -876,12 +897,21 @@ int launch_gemm_dw_tc(const GemmDwP& p, int pro_b, cudaStream_t st) {
 // ================================================================================================
 namespace wb {
 
-constexpr int T2_STAGES = 6;
+// Ring depth NS and epilogue staging (2 KB boxes of 32 channels x 16 frames, 64-byte swizzle, per epilogue warp):
+//   EPI 0     : NS = 6, one store box per warp                       (192 + 16 KB)
+//   EPI 2, 10 : NS = 4, T2_NL load boxes (R / d prefetch) + one store box per warp   (128 + 64 KB)
+// The epilogue moves its global traffic with TMA (coalesced 64-byte row segments) instead of one 16-byte access per
+// lane per row, which was measured to cost more than the MMAs themselves (profiles/r01_*: 448 vs 183 us).
+constexpr int T2_NL = 3;
+constexpr int T2_EBOX = 2048, T2_ECOLS = 16;
+__host__ __device__ constexpr int t2_nbuf(int epi) { return (epi == 2 || epi == 10) ? 1 + T2_NL : 1; }
+__host__ __device__ constexpr int t2_stages(int epi) { return (epi == 2 || epi == 10) ? 4 : 6; }
+constexpr int T2_BAR_BYTES = 512;
 constexpr int T2_XH_BYTES = (TC_BN / 2 / 32) * TC_BOX_BYTES;  // this CTA's half of the X tile: 4 boxes = 8192
 constexpr int T2_OFF_WHI = 0, T2_OFF_WLO = TC_W_BYTES, T2_OFF_XHI = 2 * TC_W_BYTES, T2_OFF_XLO = 2 * TC_W_BYTES + T2_XH_BYTES;
 constexpr int T2_STAGE_BYTES = 2 * TC_W_BYTES + 2 * T2_XH_BYTES;  // 32768
 constexpr int T2_TX_BYTES = 2 * TC_W_BYTES + T2_XH_BYTES;          // per CTA per stage
-constexpr int T2_SMEM_BYTES = T2_STAGES * T2_STAGE_BYTES + TC_SMEM_AUX + 1024;
+__host__ __device__ constexpr int t2_smem_bytes(int ns, int nbuf) { return ns * T2_STAGE_BYTES + 8 * nbuf * T2_EBOX + 2 * TC_MAXK * 4 + T2_BAR_BYTES + 1024; }
 // D=f32, A=B=tf32, both MN-major, N=256, M=256 (cta_group::2)
 constexpr uint32_t T2_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(TC_BN >> 3) << 17) |
                               ((uint32_t)(256 >> 4) << 24);
@@ -922,24 +952,30 @@ __device__ __forceinline__ void tc_mma_tf32_2cta(uint32_t d_tmem, uint64_t adesc
       : "memory");
 }
 
-template <int PRO, int EPI>
+template <int PRO, int EPI, int NS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     gemm_wx_tc2_kernel(const __grid_constant__ CUtensorMap map_whi, const __grid_constant__ CUtensorMap map_wlo,
-                       const __grid_constant__ CUtensorMap map_x2, const TcParams P) {
+                       const __grid_constant__ CUtensorMap map_x2, const __grid_constant__ CUtensorMap map_y,
+                       const __grid_constant__ CUtensorMap map_r, const TcParams P) {
+  constexpr int T2_STAGES = NS;
+  constexpr int NBUF = t2_nbuf(EPI);
+  constexpr int EB_OFF = NS * T2_STAGE_BYTES;                 // epilogue staging boxes
+  constexpr int AUX_OFF = EB_OFF + 8 * NBUF * T2_EBOX;        // sc / sh, then the barriers
   extern __shared__ uint8_t smem_raw[];
   const GemmWxP& p = P.g;
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - raw);
-  float* sc = reinterpret_cast<float*>(gbase + T2_STAGES * T2_STAGE_BYTES);
+  float* sc = reinterpret_cast<float*>(gbase + AUX_OFF);
   float* sh = sc + TC_MAXK;
-  const uint32_t bar0 = base + T2_STAGES * T2_STAGE_BYTES + 2 * TC_MAXK * 4;
+  const uint32_t bar0 = base + AUX_OFF + 2 * TC_MAXK * 4;
   auto bar_full = [&](int s) { return bar0 + 8u * s; };
   auto bar_ready = [&](int s) { return bar0 + 8u * (T2_STAGES + s); };
   auto bar_empty = [&](int s) { return bar0 + 8u * (2 * T2_STAGES + s); };
   auto bar_accf = [&](int a) { return bar0 + 8u * (3 * T2_STAGES + a); };
   auto bar_acce = [&](int a) { return bar0 + 8u * (3 * T2_STAGES + 2 + a); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + T2_STAGES * T2_STAGE_BYTES + 2 * TC_MAXK * 4 + 8 * (3 * T2_STAGES + 4));
+  auto bar_ld = [&](int w, int b_) { return bar0 + 8u * (3 * T2_STAGES + 4 + w * T2_NL + b_); };   // per epilogue warp
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + AUX_OFF + 2 * TC_MAXK * 4 + 8 * (3 * T2_STAGES + 4 + 8 * T2_NL));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();       // 0 = leader
@@ -956,6 +992,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       mbar_init(bar_accf(a), 1);     // multicast tcgen05.commit
       mbar_init(bar_acce(a), 16);    // (leader's copy is used) 8 epilogue warps x 2 CTAs
     }
+    for (int w = 0; w < 8; ++w)
+      for (int b_ = 0; b_ < T2_NL; ++b_) mbar_init(bar_ld(w, b_), 1);   // epilogue R / d prefetch boxes
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     fence_proxy_async();
   }
@@ -1059,7 +1097,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
         mbar_wait(bar_full(s), ph);
         uint8_t* xs_hi = gbase + s * T2_STAGE_BYTES + T2_OFF_XHI;
         uint8_t* xs_lo = gbase + s * T2_STAGE_BYTES + T2_OFF_XLO;
-        for (int i = 0; i < T2_XH_BYTES / 16 / xf_nthr; ++i) {
+        for (int i = 0; i < ((P.dbg & 4) ? 0 : T2_XH_BYTES / 16 / xf_nthr); ++i) {
           const int off = (xf_tid + xf_nthr * i) * 16;
           float4 v = *reinterpret_cast<const float4*>(xs_hi + off);
           if constexpr (PRO >= 1) {
@@ -1095,10 +1133,44 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       }
     }
   } else {
-    // epilogue warps 0..7 (identical to the 1-CTA kernel, on this CTA's 128 channels)
+    // epilogue warps 0..7: TMEM -> registers (lane = channel, 16 frames per pass) -> fused epilogue -> swizzled 2 KB
+    // box in shared memory -> TMA store.  The R / d operand of EPI 2 / 10 arrives the same way (TMA load boxes,
+    // prefetched T2_NL passes ahead, across tile boundaries), so every global access of the epilogue is a full
+    // 64-byte row segment issued by the TMA unit rather than 32 scattered 16-byte accesses per warp instruction.
+    constexpr bool HAS_LD = (EPI == 2 || EPI == 10);
     const int q = warp & 3;
     const int chalf = warp >> 2;
     const EpiP& e = p.ep;
+    uint8_t* sbox = gbase + EB_OFF + warp * (NBUF * T2_EBOX);          // store box; load boxes follow it
+    const uint32_t sbox_u = base + EB_OFF + warp * (NBUF * T2_EBOX);
+    const uint32_t lrow = (uint32_t)lane * 64u, lsw = (uint32_t)(lane >> 1) & 3u;   // 64-byte swizzle: chunk ^= (row / 2) % 4
+    const bool ld_on = HAS_LD && !(P.dbg & 1);
+    // prefetch iterator over this warp's (tile, pass) sequence; passes whose first frame is >= T do not exist
+    int p_tile = cluster_id, p_j = 0;
+    uint32_t li = 0, lc = 0;
+    auto issue_next = [&]() {
+      while (p_tile < P.n_tiles) {
+        int po0, pt0, pn;
+        decode(p_tile, po0, pt0, pn);
+        const int pc0 = chalf * (TC_BN / 2) + T2_ECOLS * p_j;
+        if (p_j < (TC_BN / 2) / T2_ECOLS && pt0 + pc0 < p.T) {
+          const int b_ = (int)(li % T2_NL);
+          if (lane == 0) {
+            mbar_expect_tx(bar_ld(warp, b_), T2_EBOX);
+            tma_load_3d(sbox_u + (1 + b_) * T2_EBOX, &map_r, bar_ld(warp, b_), pt0 + pc0, po0 + q * 32, pn);
+          }
+          ++li;
+          ++p_j;
+          return;
+        }
+        p_j = 0;
+        p_tile += n_clusters;
+      }
+    };
+    if (ld_on) {
+#pragma unroll 1
+      for (int b_ = 0; b_ < T2_NL; ++b_) issue_next();
+    }
     uint32_t ti = 0;
     for (int tile = cluster_id; tile < P.n_tiles; tile += n_clusters, ++ti) {
       int o0, t0, n;
@@ -1129,79 +1201,94 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       }
       mbar_wait(bar_accf(a), aph);
       tc_fence_after();
-      float* yrow = e.Y + n * e.bsy + (int64_t)o * e.ldy;
 #pragma unroll 1
-      for (int c0 = chalf * (TC_BN / 2); c0 < (chalf + 1) * (TC_BN / 2); c0 += 32) {
+      for (int c0 = chalf * (TC_BN / 2); c0 < (chalf + 1) * (TC_BN / 2); c0 += T2_ECOLS) {
         if (t0 + c0 >= p.T) break;
-        const bool edge_chunk = (EPI == 10) && ((t0 + c0 < e.dil) || (t0 + c0 + 32 > p.T - e.dil));
-        float4 gop[8];
-        if constexpr (EPI == 2 || EPI == 10) {
-          const float* gsrc = (EPI == 10) ? (e.d + n * e.bsd + (int64_t)o * e.ldd) : (e.R + n * e.bsr + (int64_t)o * e.ldr);
+        const bool edge_chunk = (EPI == 10) && ((t0 + c0 < e.dil) || (t0 + c0 + T2_ECOLS > p.T - e.dil));
+        float4 gop[4];
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const int t = t0 + c0 + 4 * g;
-            gop[g] = (t < p.T) ? *reinterpret_cast<const float4*>(gsrc + t) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int g = 0; g < 4; ++g) gop[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if constexpr (HAS_LD) {
+          if (ld_on) {
+            const int b_ = (int)(lc % T2_NL);
+            mbar_wait(bar_ld(warp, b_), (lc / T2_NL) & 1);
+            const uint8_t* lb = sbox + (1 + b_) * T2_EBOX + lrow;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) gop[g] = *reinterpret_cast<const float4*>(lb + (((uint32_t)g ^ lsw) << 4));
+            ++lc;
+            __syncwarp();      // every lane has read the box: it can be refilled
+            issue_next();
           }
         }
-        uint32_t r[32];
-        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TC_BN + c0), r);
+        uint32_t r[16];
+        tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TC_BN + c0), r);
+        float4 outv[4];
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
+        for (int g = 0; g < 4; ++g) {
           const int t = t0 + c0 + 4 * g;
-          if (t < p.T) {
-            float v[4] = {__uint_as_float(r[4 * g]) + bias_o, __uint_as_float(r[4 * g + 1]) + bias_o,
-                          __uint_as_float(r[4 * g + 2]) + bias_o, __uint_as_float(r[4 * g + 3]) + bias_o};
-            if constexpr (EPI == 0) {
-              *reinterpret_cast<float4*>(yrow + t) = make_float4(v[0], v[1], v[2], v[3]);
-              if (e.out_stats) {
+          float v[4] = {__uint_as_float(r[4 * g]) + bias_o, __uint_as_float(r[4 * g + 1]) + bias_o,
+                        __uint_as_float(r[4 * g + 2]) + bias_o, __uint_as_float(r[4 * g + 3]) + bias_o};
+          if constexpr (EPI == 0) {
+            outv[g] = make_float4(v[0], v[1], v[2], v[3]);
+            if (e.out_stats) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const float y = (t + i < p.T) ? prelu_f(v[i], out_alpha) : 0.f;
-                  s0 += y;
-                  s1 = fmaf(y, y, s1);
-                }
+              for (int i = 0; i < 4; ++i) {
+                const float y = (t + i < p.T) ? prelu_f(v[i], out_alpha) : 0.f;
+                s0 += y;
+                s1 = fmaf(y, y, s1);
               }
-            } else if constexpr (EPI == 2) {
-              const float4 rr = gop[g];
-              *reinterpret_cast<float4*>(yrow + t) = make_float4(v[0] + rr.x, v[1] + rr.y, v[2] + rr.z, v[3] + rr.w);
-            } else if constexpr (EPI == 10) {
-              const float4 d4 = gop[g];
-              const float draw[4] = {d4.x, d4.y, d4.z, d4.w};
-              float dd[4];
-              if (!edge_chunk) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const float dvi = draw[i];
-                  const bool pos = dvi > 0.f;
-                  const float y2 = pos ? dvi : a2 * dvi;
-                  const float dy2 = fmaf(cA, v[i], fmaf(cB, y2, cC));
-                  const float ddv = pos ? dy2 : a2 * dy2;
-                  dd[i] = ddv;
-                  s0 += ddv;
-                  s1 = fmaf(ddv, dvi, s1);
-                  s3 += pos ? 0.f : dy2 * dvi;
-                }
-              } else {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const int tt_ = t + i;
-                  const bool ok = tt_ < p.T;
-                  const float dvi = ok ? draw[i] : 1.f;
-                  const bool pos = dvi > 0.f;
-                  const float y2 = pos ? dvi : a2 * dvi;
-                  const float dy2 = ok ? fmaf(cA, v[i], fmaf(cB, y2, cC)) : 0.f;
-                  const float ddv = pos ? dy2 : a2 * dy2;
-                  dd[i] = ddv;
-                  s0 += ddv;
-                  s1 = fmaf(ddv, dvi, s1);
-                  s3 += pos ? 0.f : dy2 * dvi;
-                  sL += tt_ < e.dil ? ddv : 0.f;
-                  sR += tt_ >= p.T - e.dil ? ddv : 0.f;
-                }
-              }
-              *reinterpret_cast<float4*>(yrow + t) = make_float4(dd[0], dd[1], dd[2], dd[3]);
             }
+          } else if constexpr (EPI == 2) {
+            const float4 rr = gop[g];
+            outv[g] = make_float4(v[0] + rr.x, v[1] + rr.y, v[2] + rr.z, v[3] + rr.w);
+          } else if constexpr (EPI == 10) {
+            const float4 d4 = gop[g];
+            const float draw[4] = {d4.x, d4.y, d4.z, d4.w};
+            float dd[4];
+            if (!edge_chunk) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float dvi = draw[i];
+                const bool pos = dvi > 0.f;
+                const float y2 = pos ? dvi : a2 * dvi;
+                const float dy2 = fmaf(cA, v[i], fmaf(cB, y2, cC));
+                const float ddv = pos ? dy2 : a2 * dy2;
+                dd[i] = ddv;
+                s0 += ddv;
+                s1 = fmaf(ddv, dvi, s1);
+                s3 += pos ? 0.f : dy2 * dvi;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int tt_ = t + i;
+                const bool ok = tt_ < p.T;
+                const float dvi = ok ? draw[i] : 1.f;
+                const bool pos = dvi > 0.f;
+                const float y2 = pos ? dvi : a2 * dvi;
+                const float dy2 = ok ? fmaf(cA, v[i], fmaf(cB, y2, cC)) : 0.f;
+                const float ddv = pos ? dy2 : a2 * dy2;
+                dd[i] = ddv;
+                s0 += ddv;
+                s1 = fmaf(ddv, dvi, s1);
+                s3 += pos ? 0.f : dy2 * dvi;
+                sL += tt_ < e.dil ? ddv : 0.f;
+                sR += tt_ >= p.T - e.dil ? ddv : 0.f;
+              }
+            }
+            outv[g] = make_float4(dd[0], dd[1], dd[2], dd[3]);
           }
+        }
+        // registers -> store box (previous TMA store must have finished READING it) -> TMA store (frames >= T are clipped)
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) *reinterpret_cast<float4*>(sbox + lrow + (((uint32_t)g ^ lsw) << 4)) = outv[g];
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0 && !(P.dbg & 2)) {
+          tma_store_3d(&map_y, sbox_u, t0 + c0, o0 + q * 32, n);
+          bulk_commit();
         }
       }
       tc_fence_before();
@@ -1235,6 +1322,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
         }
       }
     }
+    if (lane == 0) bulk_wait0();   // all of this warp's TMA stores are complete before the CTA may exit
   }
 
   tc_fence_before();
@@ -1251,13 +1339,18 @@ bool gemm_wx_tc2_eligible(const GemmWxP& p, int pro, int epi) {
   if (p.M % 256) return false;
   if (!(epi == 0 || epi == 2 || epi == 10)) return false;
   if (epi == 0 && p.ep.ch_stats) return false;
-  return gemm_wx_tc_eligible(p, pro, epi);
+  return gemm_wx_tc_eligible(p, pro, epi);       // includes the 16-byte alignment of Y / R / d the TMA boxes need
 }
 
 template <int PRO, int EPI>
-static int launch_tc2_t(const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& mx, const TcParams& P, cudaStream_t st) {
-  auto k = gemm_wx_tc2_kernel<PRO, EPI>;
-  WB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
+static int launch_tc2_t(const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& mx, const CUtensorMap& my,
+                        const CUtensorMap& mr, const TcParams& P, cudaStream_t st) {
+  constexpr int NS = t2_stages(EPI);
+  constexpr int SMEM = t2_smem_bytes(NS, t2_nbuf(EPI));
+  static_assert(SMEM <= 232448, "2-CTA kernel exceeds the 227 KB shared-memory limit");
+  static_assert((3 * NS + 4 + 8 * T2_NL) * 8 + 4 <= T2_BAR_BYTES, "barrier area too small");
+  auto k = gemm_wx_tc2_kernel<PRO, EPI, NS>;
+  WB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
   static int n_sm = 0;
   if (!n_sm) {
     int dev = 0;
@@ -1265,22 +1358,40 @@ static int launch_tc2_t(const CUtensorMap& mh, const CUtensorMap& ml, const CUte
     WB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   }
   int clusters = P.n_tiles < n_sm / 2 ? P.n_tiles : n_sm / 2;
-  k<<<2 * clusters, TC_THREADS, T2_SMEM_BYTES, st>>>(mh, ml, mx, P);
+  k<<<2 * clusters, TC_THREADS, SMEM, st>>>(mh, ml, mx, my, mr, P);
   WB_LAUNCH_CHECK("gemm_wx_tc2");
   return 0;
 }
 
 int launch_gemm_wx_tc2(const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& mx, TcParams P, int pro, int epi,
                        cudaStream_t st) {
-  if (T2_STAGES % P.xf_groups) P.xf_groups = 2;   // must divide the ring depth (see launch_gemm_wx_tc)
+  if (!((pro == 0 && (epi == 0 || epi == 2 || epi == 10)) || (pro == 2 && epi == 2) || (pro == 3 && epi == 0)))
+    return -100;                                // not instantiated: caller falls back to the 1-CTA kernel
+  if (t2_stages(epi) % P.xf_groups) P.xf_groups = 2;   // must divide the ring depth (see launch_gemm_wx_tc)
   P.n_ob = P.g.M / 256;                       // channel PAIRS
   P.n_tiles = P.n_ob * P.n_tt * P.g.n;
-  if (pro == 0 && epi == 0) return launch_tc2_t<0, 0>(mh, ml, mx, P, st);
-  if (pro == 0 && epi == 2) return launch_tc2_t<0, 2>(mh, ml, mx, P, st);
-  if (pro == 0 && epi == 10) return launch_tc2_t<0, 10>(mh, ml, mx, P, st);
-  if (pro == 2 && epi == 2) return launch_tc2_t<2, 2>(mh, ml, mx, P, st);
-  if (pro == 3 && epi == 0) return launch_tc2_t<3, 0>(mh, ml, mx, P, st);
-  return -100;                                // not instantiated: caller falls back to the 1-CTA kernel
+  // epilogue boxes: (16 frames, 32 channels, 1 row) with the 64-byte swizzle; frames >= T are clipped / zero-filled
+  const GemmWxP& p = P.g;
+  CUtensorMap my, mr;
+  const uint32_t ebox[3] = {T2_ECOLS, 32, 1};
+  {
+    uint64_t dims[3] = {(uint64_t)p.T, (uint64_t)p.M, (uint64_t)p.n};
+    uint64_t strides[2] = {(uint64_t)p.ep.ldy * 4, (uint64_t)p.ep.bsy * 4};
+    if (int rc = encode_map_sw(&my, p.ep.Y, 3, dims, strides, ebox, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
+    mr = my;
+    if (epi == 2) {
+      uint64_t sr[2] = {(uint64_t)p.ep.ldr * 4, (uint64_t)p.ep.bsr * 4};
+      if (int rc = encode_map_sw(&mr, p.ep.R, 3, dims, sr, ebox, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
+    } else if (epi == 10) {
+      uint64_t sd[2] = {(uint64_t)p.ep.ldd * 4, (uint64_t)p.ep.bsd * 4};
+      if (int rc = encode_map_sw(&mr, p.ep.d, 3, dims, sd, ebox, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
+    }
+  }
+  if (pro == 0 && epi == 0) return launch_tc2_t<0, 0>(mh, ml, mx, my, mr, P, st);
+  if (pro == 0 && epi == 2) return launch_tc2_t<0, 2>(mh, ml, mx, my, mr, P, st);
+  if (pro == 0 && epi == 10) return launch_tc2_t<0, 10>(mh, ml, mx, my, mr, P, st);
+  if (pro == 2 && epi == 2) return launch_tc2_t<2, 2>(mh, ml, mx, my, mr, P, st);
+  return launch_tc2_t<3, 0>(mh, ml, mx, my, mr, P, st);
 }
 
 }  // namespace wb
