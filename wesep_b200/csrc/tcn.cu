@@ -177,78 +177,102 @@ __global__ void __launch_bounds__(ST_THREADS) tcn_dw_bwd_generic_kernel(const St
 
 
 // ------------------------------------------------------------------------------------ vectorised stencils
-// Same math as the *_generic kernels above, 4 consecutive time steps per thread: 128-bit global loads / stores,
-// 128-bit shared-memory tap loads.  DM = 0: dilation is a multiple of 4 (taps are 16-byte aligned);
-// DM = 1,2,3: dilation == DM (taps assembled from the previous / centre / next vectors).
+// Same math as the *_generic kernels above, 4 consecutive time steps per thread, taps read straight from global
+// memory as 128-bit loads: the centre vector comes from DRAM once, the two tap vectors hit L1 / L2 (another
+// thread's centre), so there is no shared-memory fill phase and no barrier.  DM = 0: dilation is a multiple of 4
+// (taps are 16-byte aligned); DM = 1,2,3: dilation == DM (taps assembled from the previous / centre / next vectors).
+// Pad columns [T, ld) of the inputs hold arbitrary bits (possibly NaN): every element >= T is replaced, never scaled.
+__device__ __forceinline__ void ld4(const float* p, float (&v)[4]) {
+  const float4 q = __ldg(reinterpret_cast<const float4*>(p));
+  v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+}
+// L / C / R = x[t + k - dil], x[t + k], x[t + k + dil] (k < 4) with `fill` outside [0, T)
 template <int DM>
-__device__ __forceinline__ void taps4(const float* c_ptr, int dil, float (&L)[4], float (&C)[4], float (&R)[4]) {
-  const float4 c = *reinterpret_cast<const float4*>(c_ptr);
-  C[0] = c.x; C[1] = c.y; C[2] = c.z; C[3] = c.w;
+__device__ __forceinline__ void taps4g(const float* row, int t, int T, int dil, float fill, float (&L)[4], float (&C)[4],
+                                       float (&R)[4]) {
+  ld4(row + t, C);
   if constexpr (DM == 0) {
-    const float4 l = *reinterpret_cast<const float4*>(c_ptr - dil);
-    const float4 r = *reinterpret_cast<const float4*>(c_ptr + dil);
-    L[0] = l.x; L[1] = l.y; L[2] = l.z; L[3] = l.w;
-    R[0] = r.x; R[1] = r.y; R[2] = r.z; R[3] = r.w;
-  } else {
-    const float4 p = *reinterpret_cast<const float4*>(c_ptr - 4);
-    const float4 n = *reinterpret_cast<const float4*>(c_ptr + 4);
-    const float a[12] = {p.x, p.y, p.z, p.w, c.x, c.y, c.z, c.w, n.x, n.y, n.z, n.w};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      L[i] = a[4 + i - DM];
-      R[i] = a[4 + i + DM];
+    for (int k = 0; k < 4; ++k) { L[k] = fill; R[k] = fill; }
+    if (t - dil >= 0) ld4(row + t - dil, L);
+    if (t + dil < T) ld4(row + t + dil, R);
+    if (t + dil + 3 >= T) {   // right edge: at most the last vectors of a row
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (t + k >= T) C[k] = fill;
+        if (t + dil + k >= T) R[k] = fill;
+      }
+    }
+  } else {
+    float a[12];
+    float P[4] = {fill, fill, fill, fill}, N[4] = {fill, fill, fill, fill};
+    if (t >= 4) ld4(row + t - 4, P);
+    if (t + 4 < T) ld4(row + t + 4, N);
+    if (t + 7 >= T) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (t + k >= T) C[k] = fill;
+        if (t + 4 + k >= T) N[k] = fill;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { a[k] = P[k]; a[4 + k] = C[k]; a[8 + k] = N[k]; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      L[k] = a[4 + k - DM];
+      R[k] = a[4 + k + DM];
     }
   }
 }
 
 template <int DM>
 __global__ void __launch_bounds__(ST_THREADS) tcn_dw_fwd_kernel(const StFwdP p) {
-  extern __shared__ __align__(16) float z[];  // [ST_CH][RW], RW = ST_TT + 2*halo
   __shared__ float red[2 * 32];
   const int tid = threadIdx.x, sub = tid & 63, chl = tid >> 6;
   const int t0 = blockIdx.x * ST_TT, c = blockIdx.y * ST_CH + chl, n = blockIdx.z;
-  const int dil = p.dil, halo = DM == 0 ? dil : 4, RW = ST_TT + 2 * halo;
+  const int dil = p.dil;
   float s = 0.f, q = 0.f;
-  float* zr = z + chl * RW;
   if (c < p.H) {
     float mu, r;
     gln_mean_rstd(p.stats1 + 2 * n, p.count, GLN_EPS, mu, r);
     const float a1 = __ldg(p.a1), gm = __ldg(p.g1 + c), bt = __ldg(p.be1 + c);
     const float sc = gm * r, sh = bt - gm * mu * r;
-    const float* urow = p.u + ((int64_t)n * p.H + c) * p.ld;
-    for (int j = 4 * sub; j < RW; j += 256) {
-      const int t = t0 - halo + j;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (t >= 0 && t < p.T) {
-        const float4 u4 = __ldg(reinterpret_cast<const float4*>(urow + t));
-        v.x = fmaf(sc, prelu_f(u4.x, a1), sh);
-        v.y = t + 1 < p.T ? fmaf(sc, prelu_f(u4.y, a1), sh) : 0.f;
-        v.z = t + 2 < p.T ? fmaf(sc, prelu_f(u4.z, a1), sh) : 0.f;
-        v.w = t + 3 < p.T ? fmaf(sc, prelu_f(u4.w, a1), sh) : 0.f;
-      }
-      *reinterpret_cast<float4*>(zr + j) = v;
-    }
-  }
-  __syncthreads();
-  if (c < p.H) {
+    // z1 = sc*prelu(u) + sh inside [0,T) and 0 outside: edge vectors take the masked path below
     const float w0 = __ldg(p.wd + 3 * c), w1 = __ldg(p.wd + 3 * c + 1), w2 = __ldg(p.wd + 3 * c + 2);
     const float bd = __ldg(p.bd + c), a2 = __ldg(p.a2);
+    const float* urow = p.u + ((int64_t)n * p.H + c) * p.ld;
     float* drow = p.d + ((int64_t)n * p.H + c) * p.ld;
 #pragma unroll 2
     for (int i = 4 * sub; i < ST_TT; i += 256) {
       const int t = t0 + i;
-      if (t < p.T) {
-        float L[4], C[4], R[4], o[4];
-        taps4<DM>(zr + halo + i, dil, L, C, R);
+      if (t >= p.T) break;
+      float L[4], C[4], R[4], o[4];
+      taps4g<DM>(urow, t, p.T, dil, 0.f, L, C, R);
+      const bool interior = (t - dil >= 0) && (t + dil + 3 < p.T);
+      if (interior) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          o[k] = fmaf(w0, L[k], fmaf(w1, C[k], fmaf(w2, R[k], bd)));
-          const float y = (t + k < p.T) ? prelu_f(o[k], a2) : 0.f;
+          const float zl = fmaf(sc, prelu_f(L[k], a1), sh), zc = fmaf(sc, prelu_f(C[k], a1), sh),
+                      zr = fmaf(sc, prelu_f(R[k], a1), sh);
+          o[k] = fmaf(w0, zl, fmaf(w1, zc, fmaf(w2, zr, bd)));
+          const float y = prelu_f(o[k], a2);
           s += y;
           q = fmaf(y, y, q);
         }
-        *reinterpret_cast<float4*>(drow + t) = make_float4(o[0], o[1], o[2], o[3]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int e = t + k;
+          const float zl = (e - dil >= 0) ? fmaf(sc, prelu_f(L[k], a1), sh) : 0.f;
+          const float zc = (e < p.T) ? fmaf(sc, prelu_f(C[k], a1), sh) : 0.f;
+          const float zr = (e + dil < p.T) ? fmaf(sc, prelu_f(R[k], a1), sh) : 0.f;
+          o[k] = fmaf(w0, zl, fmaf(w1, zc, fmaf(w2, zr, bd)));
+          const float y = (e < p.T) ? prelu_f(o[k], a2) : 0.f;
+          s += y;
+          q = fmaf(y, y, q);
+        }
       }
+      *reinterpret_cast<float4*>(drow + t) = make_float4(o[0], o[1], o[2], o[3]);
     }
   }
   float v[2] = {s, q};
@@ -259,94 +283,66 @@ __global__ void __launch_bounds__(ST_THREADS) tcn_dw_fwd_kernel(const StFwdP p) 
   }
 }
 
+// Backward: the weight gradients are re-indexed so that only dd needs taps:
+//   dwd[c][0] = sum_t dd[t] z1[t - dil] = sum_t z1[t] dd[t + dil],  dwd[c][2] = sum_t z1[t] dd[t - dil]
+// (dd == 0 outside [0,T)), so u is read once, at the centre.
 template <int DM>
 __global__ void __launch_bounds__(ST_THREADS) tcn_dw_bwd_kernel(const StBwdP p) {
-  extern __shared__ __align__(16) float sm[];  // dds[CH][RW], z1s[CH][RW], us[CH][TTB]
   __shared__ float red[32];
   __shared__ float chred[ST_CH][2][8];
   const int tid = threadIdx.x, sub = tid & 63, chl = tid >> 6, lane = tid & 31;
   const int t0 = blockIdx.x * ST_TTB, c = blockIdx.y * ST_CH + chl, n = blockIdx.z;
-  const int dil = p.dil, halo = DM == 0 ? dil : 4, RW = ST_TTB + 2 * halo;
-  float* dds = sm + chl * RW;
-  float* z1s = sm + ST_CH * RW + chl * RW;
-  float* us = sm + 2 * ST_CH * RW + chl * ST_TTB;
-  float mu = 0.f, r = 1.f, a1 = 1.f, gm = 0.f;
-  if (c < p.H) {
-    gln_mean_rstd(p.stats1 + 2 * n, p.count, GLN_EPS, mu, r);
-    a1 = __ldg(p.a1);
-    gm = __ldg(p.g1 + c);
-    const float bt = __ldg(p.be1 + c);
-    const float sc = gm * r, sh = bt - gm * mu * r;
-    const float* urow = p.u + ((int64_t)n * p.H + c) * p.ld;
-    const float* drow = p.dd + ((int64_t)n * p.H + c) * p.ld;
-    for (int j = 4 * sub; j < RW; j += 256) {
-      const int t = t0 - halo + j;
-      float4 dv = make_float4(0.f, 0.f, 0.f, 0.f), zv = dv, uv = dv;
-      if (t >= 0 && t < p.T) {
-        const float4 d4 = __ldg(reinterpret_cast<const float4*>(drow + t));
-        uv = __ldg(reinterpret_cast<const float4*>(urow + t));
-        const bool k1 = t + 1 < p.T, k2 = t + 2 < p.T, k3 = t + 3 < p.T;
-        dv.x = d4.x; dv.y = k1 ? d4.y : 0.f; dv.z = k2 ? d4.z : 0.f; dv.w = k3 ? d4.w : 0.f;
-        zv.x = fmaf(sc, prelu_f(uv.x, a1), sh);
-        zv.y = k1 ? fmaf(sc, prelu_f(uv.y, a1), sh) : 0.f;
-        zv.z = k2 ? fmaf(sc, prelu_f(uv.z, a1), sh) : 0.f;
-        zv.w = k3 ? fmaf(sc, prelu_f(uv.w, a1), sh) : 0.f;
-        if (!k1) uv.y = 1.f;   // padding: harmless finite values
-        if (!k2) uv.z = 1.f;
-        if (!k3) uv.w = 1.f;
-      }
-      *reinterpret_cast<float4*>(dds + j) = dv;
-      *reinterpret_cast<float4*>(z1s + j) = zv;
-      const int jc = j - halo;
-      if (jc >= 0 && jc < ST_TTB) *reinterpret_cast<float4*>(us + jc) = uv;
-    }
-  }
-  __syncthreads();
+  const int dil = p.dil;
   float acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
   float dal = 0.f;
   if (c < p.H) {
+    float mu, r;
+    gln_mean_rstd(p.stats1 + 2 * n, p.count, GLN_EPS, mu, r);
+    const float a1 = __ldg(p.a1), gm = __ldg(p.g1 + c), bt = __ldg(p.be1 + c);
+    const float sc = gm * r, sh = bt - gm * mu * r;
     const double Mc = p.count;
     const float m1 = (float)(p.rowacc[8 * n + 2] / Mc);
     const float m2 = (float)((p.rowacc[8 * n + 3] - p.rowacc[8 * n + 4]) / Mc);
     const float w0 = __ldg(p.wd + 3 * c), w1 = __ldg(p.wd + 3 * c + 1), w2 = __ldg(p.wd + 3 * c + 2);
+    const float* urow = p.u + ((int64_t)n * p.H + c) * p.ld;
+    const float* drow = p.dd + ((int64_t)n * p.H + c) * p.ld;
     float* durow = p.du + ((int64_t)n * p.H + c) * p.ld;
     // dy = r*(g1*dz - m1 - yhat1*m2) = cA*dz + cB*y1 + cC with y1 = prelu(u)
     const float cA = r * gm, cB = -r * r * m2, cC = -r * m1 + r * r * m2 * mu;
+#pragma unroll 2
     for (int i = 4 * sub; i < ST_TTB; i += 256) {
       const int t = t0 + i;
-      if (t < p.T) {
-        float dL[4], dC[4], dR[4], zL[4], zC[4], zR[4], o[4];
-        taps4<DM>(dds + halo + i, dil, dL, dC, dR);
-        taps4<DM>(z1s + halo + i, dil, zL, zC, zR);
-        const float4 u4 = *reinterpret_cast<const float4*>(us + i);
-        const float uu[4] = {u4.x, u4.y, u4.z, u4.w};
-        const bool full = t + 3 < p.T;   // only the last vector of a row can be partial
+      if (t >= p.T) break;
+      float dL[4], dC[4], dR[4], uu[4], o[4];
+      taps4g<DM>(drow, t, p.T, dil, 0.f, dL, dC, dR);   // dd outside [0,T) is 0
+      ld4(urow + t, uu);
+      const bool full = t + 3 < p.T;   // only the last vector of a row can be partial
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const bool ok = full || (t + k < p.T);
-          const float ddv = dC[k];                                      // 0 beyond T (masked at fill)
-          const float dz = fmaf(w0, dR[k], fmaf(w1, ddv, w2 * dL[k]));  // dz1[t] = sum_j w[j] dd[t - (j-1) dil]
-          const float uv = uu[k];
-          const bool pos = uv > 0.f;
-          const float y1 = pos ? uv : a1 * uv;
-          const float dy = fmaf(cA, dz, fmaf(cB, y1, cC));
-          float duv = pos ? dy : a1 * dy;
-          float dzy = dz * y1, dyu = pos ? 0.f : dy * uv, dzm = dz;
-          if (!ok) { duv = 0.f; dzy = 0.f; dyu = 0.f; dzm = 0.f; }
-          o[k] = duv;
-          acc[0] += dzm;                       // sum dz            -> dbeta1
-          acc[1] += dzy;                       // sum dz*y1         -> dgamma1 = r*(sum dz*y1 - mu*sum dz)
-          acc[2] = fmaf(ddv, zL[k], acc[2]);
-          acc[3] = fmaf(ddv, zC[k], acc[3]);
-          acc[4] = fmaf(ddv, zR[k], acc[4]);
-          acc[5] += ddv;
-          acc[6] += duv;
-          dal += dyu;
-        }
-        *reinterpret_cast<float4*>(durow + t) = make_float4(o[0], o[1], o[2], o[3]);
+      for (int k = 0; k < 4; ++k) {
+        const bool ok = full || (t + k < p.T);
+        const float ddv = dC[k];
+        const float dz = fmaf(w0, dR[k], fmaf(w1, ddv, w2 * dL[k]));  // dz1[t] = sum_j w[j] dd[t - (j-1) dil]
+        const float uv = ok ? uu[k] : 1.f;
+        const bool pos = uv > 0.f;
+        const float y1 = pos ? uv : a1 * uv;
+        const float z1 = ok ? fmaf(sc, y1, sh) : 0.f;
+        const float dy = fmaf(cA, dz, fmaf(cB, y1, cC));
+        float duv = pos ? dy : a1 * dy;
+        float dzy = dz * y1, dyu = pos ? 0.f : dy * uv, dzm = dz;
+        if (!ok) { duv = 0.f; dzy = 0.f; dyu = 0.f; dzm = 0.f; }
+        o[k] = duv;
+        acc[0] += dzm;                       // sum dz            -> dbeta1
+        acc[1] += dzy;                       // sum dz*y1         -> dgamma1 = r*(sum dz*y1 - mu*sum dz)
+        acc[2] = fmaf(z1, dR[k], acc[2]);
+        acc[3] = fmaf(z1, ddv, acc[3]);
+        acc[4] = fmaf(z1, dL[k], acc[4]);
+        acc[5] += ddv;
+        acc[6] += duv;
+        dal += dyu;
       }
+      *reinterpret_cast<float4*>(durow + t) = make_float4(o[0], o[1], o[2], o[3]);
     }
     acc[1] = r * (acc[1] - mu * acc[0]);
   }
@@ -381,11 +377,8 @@ static int launch_dw_fwd(const StFwdP& p, cudaStream_t st) {
     WB_CUDA(cudaFuncSetAttribute(tcn_dw_fwd_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     tcn_dw_fwd_generic_kernel<<<grid, ST_THREADS, smem, st>>>(p);
   } else {
-    const int halo = dm == 0 ? p.dil : 4;
-    size_t smem = (size_t)ST_CH * (ST_TT + 2 * halo) * sizeof(float);
     auto launch = [&](auto k) -> int {
-      WB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k<<<grid, ST_THREADS, smem, st>>>(p);
+      k<<<grid, ST_THREADS, 0, st>>>(p);
       return 0;
     };
     int rc = dm == 0 ? launch(tcn_dw_fwd_kernel<0>) : dm == 1 ? launch(tcn_dw_fwd_kernel<1>)
@@ -404,11 +397,8 @@ static int launch_dw_bwd(const StBwdP& p, cudaStream_t st) {
     WB_CUDA(cudaFuncSetAttribute(tcn_dw_bwd_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     tcn_dw_bwd_generic_kernel<<<grid, ST_THREADS, smem, st>>>(p);
   } else {
-    const int halo = dm == 0 ? p.dil : 4;
-    size_t smem = (size_t)ST_CH * (2 * (ST_TTB + 2 * halo) + ST_TTB) * sizeof(float);
     auto launch = [&](auto k) -> int {
-      WB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k<<<grid, ST_THREADS, smem, st>>>(p);
+      k<<<grid, ST_THREADS, 0, st>>>(p);
       return 0;
     };
     int rc = dm == 0 ? launch(tcn_dw_bwd_kernel<0>) : dm == 1 ? launch(tcn_dw_bwd_kernel<1>)
