@@ -120,6 +120,7 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t sr
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
 
 // Shared-memory matrix descriptor: MN-major 32-bit (tf32) operand.  For MN-major tf32 the only legal smem layout
@@ -620,7 +621,7 @@ int launch_gemm_wx_tc(const GemmWxP& p, bool a_trans, int pro, int epi, void* ws
   {
     const int sel = (g_tc_flags >> 2) & 3;
     P.xf_groups = sel == 1 ? 1 : sel == 3 ? 4 : 2;
-    P.dbg = (g_tc_flags >> 4) & 7;
+    P.dbg = (g_tc_flags >> 4) & 15;
   }
   if (gemm_wx_tc2_eligible(p, pro, epi)) {      // 2-CTA (cta_group::2) kernel for 256-channel multiples
     int rc = launch_gemm_wx_tc2(mh, ml, mx2, P, pro, epi, st);
@@ -676,10 +677,15 @@ constexpr uint32_t DW_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(D
 
 struct DwTcParams {
   GemmDwP g;
-  int n_ob, n_cb, ksplit, kb_per_split;
+  int n_ob, n_cb, n_tiles;
   int skip_hi_store;
 };
 
+// Stream-K over (tile, k-block) units: the grid is one CTA per SM and CTA i owns the contiguous unit range
+// [i*U/G, (i+1)*U/G) of the flattened (tile-major) space, so all SMs carry the same number of k-blocks no matter
+// how the tile count divides the SM count (128 tiles on 148 SMs left 14 % of the machine idle).  A range may span
+// tiles; every (tile, k-range) segment ends with an atomic add of its partial D into C, which the accumulate-into-C
+// contract already required.  The two TMEM accumulators let a segment's epilogue overlap the next segment's MMAs.
 template <int PRO_B>
 __global__ void __launch_bounds__(DW_THREADS, 1)
     gemm_dw_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const DwTcParams P) {
@@ -692,20 +698,21 @@ __global__ void __launch_bounds__(DW_THREADS, 1)
   auto bar_full = [&](int s) { return bar0 + 8u * s; };
   auto bar_ready = [&](int s) { return bar0 + 8u * (DW_STAGES + s); };
   auto bar_empty = [&](int s) { return bar0 + 8u * (2 * DW_STAGES + s); };
-  const uint32_t bar_accf = bar0 + 8u * (3 * DW_STAGES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + DW_STAGES * DW_STAGE_BYTES + 8 * (3 * DW_STAGES + 1));
+  auto bar_accf = [&](int a) { return bar0 + 8u * (3 * DW_STAGES + a); };
+  auto bar_acce = [&](int a) { return bar0 + 8u * (3 * DW_STAGES + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + DW_STAGES * DW_STAGE_BYTES + 8 * (3 * DW_STAGES + 4));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // tile decode: blockIdx.x = ((row * ksplit + ks) * n_cb + cb) * n_ob + ob
-  int b = blockIdx.x;
-  const int ob = b % P.n_ob; b /= P.n_ob;
-  const int cb = b % P.n_cb; b /= P.n_cb;
-  const int ksp = b % P.ksplit;
-  const int row = b / P.ksplit;
   const int KBT = (p.T + DW_BK - 1) / DW_BK;
-  const int kb0 = ksp * P.kb_per_split;
-  const int kb1 = min(kb0 + P.kb_per_split, KBT);
-  const int KB = max(kb1 - kb0, 0);
+  const int64_t units = (int64_t)P.n_tiles * KBT;
+  const int64_t u0 = units * blockIdx.x / gridDim.x, u1 = units * (blockIdx.x + 1) / gridDim.x;
+  // unit -> (tile, k-block); tile = (row * n_cb + cb) * n_ob + ob
+  auto decode = [&](int tile, int& ob, int& cb, int& row) {
+    ob = tile % P.n_ob;
+    const int rest = tile / P.n_ob;
+    cb = rest % P.n_cb;
+    row = rest / P.n_cb;
+  };
 
   if (tid == 0) {
     for (int s = 0; s < DW_STAGES; ++s) {
@@ -713,12 +720,15 @@ __global__ void __launch_bounds__(DW_THREADS, 1)
       mbar_init(bar_ready(s), 4);   // 2 transform groups of 4 warps; group g owns stages with it % 2 == g
       mbar_init(bar_empty(s), 1);
     }
-    mbar_init(bar_accf, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_accf(a), 1);
+      mbar_init(bar_acce(a), 4);    // 4 epilogue warps
+    }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     fence_proxy_async();
   }
   if (warp == 4) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
   tc_fence_before();
@@ -726,23 +736,37 @@ __global__ void __launch_bounds__(DW_THREADS, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (KB > 0) {
-    if (warp == 4) {
-      if (lane == 0) {
-        for (int it = 0; it < KB; ++it) {
+  if (warp == 4) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int64_t u = u0; u < u1;) {
+        const int tile = (int)(u / KBT), kb_lo = (int)(u % KBT);
+        const int kb_hi = (int)min((int64_t)KBT, (int64_t)kb_lo + (u1 - u));
+        int ob, cb, row;
+        decode(tile, ob, cb, row);
+        for (int kb = kb_lo; kb < kb_hi; ++kb, ++it) {
           const int s = it % DW_STAGES;
           const uint32_t ph = (it / DW_STAGES) & 1;
           mbar_wait(bar_empty(s), ph ^ 1);
           const uint32_t sb = base + s * DW_STAGE_BYTES;
           mbar_expect_tx(bar_full(s), DW_TX_BYTES);
-          const int t0 = (kb0 + it) * DW_BK;
-          tma_load_3d(sb + DW_OFF_AHI, &map_a, bar_full(s), t0, ob * DW_BM, row);
-          tma_load_3d(sb + DW_OFF_BHI, &map_b, bar_full(s), t0, cb * DW_BN, row);
+          tma_load_3d(sb + DW_OFF_AHI, &map_a, bar_full(s), kb * DW_BK, ob * DW_BM, row);
+          tma_load_3d(sb + DW_OFF_BHI, &map_b, bar_full(s), kb * DW_BK, cb * DW_BN, row);
         }
+        u += kb_hi - kb_lo;
       }
-    } else if (warp == 5) {
-      if (lane == 0) {
-        for (int it = 0; it < KB; ++it) {
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      uint32_t it = 0, sg = 0;
+      for (int64_t u = u0; u < u1; ++sg) {
+        const int kb_lo = (int)(u % KBT);
+        const int kb_hi = (int)min((int64_t)KBT, (int64_t)kb_lo + (u1 - u));
+        const int a = sg & 1;
+        mbar_wait(bar_acce(a), ((sg >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + a * DW_BN;
+        for (int kb = kb_lo; kb < kb_hi; ++kb, ++it) {
           const int s = it % DW_STAGES;
           const uint32_t ph = (it / DW_STAGES) & 1;
           mbar_wait(bar_ready(s), ph);
@@ -754,72 +778,86 @@ __global__ void __launch_bounds__(DW_THREADS, 1)
             const uint64_t a_lo = make_desc_k_sw64(sb + DW_OFF_ALO + ks * 32);
             const uint64_t b_hi = make_desc_k_sw64(sb + DW_OFF_BHI + ks * 32);
             const uint64_t b_lo = make_desc_k_sw64(sb + DW_OFF_BLO + ks * 32);
-            tc_mma_tf32(tmem_base, a_lo, b_hi, DW_IDESC, (it | ks) != 0 ? 1u : 0u);
-            tc_mma_tf32(tmem_base, a_hi, b_lo, DW_IDESC, 1u);
-            tc_mma_tf32(tmem_base, a_hi, b_hi, DW_IDESC, 1u);
+            tc_mma_tf32(d_tmem, a_lo, b_hi, DW_IDESC, (kb != kb_lo || ks != 0) ? 1u : 0u);
+            tc_mma_tf32(d_tmem, a_hi, b_lo, DW_IDESC, 1u);
+            tc_mma_tf32(d_tmem, a_hi, b_hi, DW_IDESC, 1u);
           }
           tc_commit(bar_empty(s));
         }
-        tc_commit(bar_accf);
+        tc_commit(bar_accf(a));
+        u += kb_hi - kb_lo;
       }
-    } else if (warp >= 6) {
-      const int tt_id = tid - 6 * 32;
-      float alpha = 1.f;
-      if constexpr (PRO_B == 1) alpha = p.xb.alpha ? __ldg(p.xb.alpha) : 1.f;
-      const int xf_gid = tt_id >> 7, xf_tid = tt_id & 127;   // DW_STAGES % 2 == 0: a slot always belongs to the same group
-      for (int it = xf_gid; it < KB; it += 2) {
-        const int s = it % DW_STAGES;
-        const uint32_t ph = (it / DW_STAGES) & 1;
-        mbar_wait(bar_full(s), ph);
-        uint8_t* st = gbase + s * DW_STAGE_BYTES;
+    }
+  } else if (warp >= 6) {
+    const int tt_id = tid - 6 * 32;
+    float alpha = 1.f;
+    if constexpr (PRO_B == 1) alpha = p.xb.alpha ? __ldg(p.xb.alpha) : 1.f;
+    const int xf_gid = tt_id >> 7, xf_tid = tt_id & 127;   // DW_STAGES % 2 == 0: a slot always belongs to the same group
+    const int n_it = (int)(u1 - u0);
+    for (int it = xf_gid; it < n_it; it += 2) {
+      const int s = it % DW_STAGES;
+      const uint32_t ph = (it / DW_STAGES) & 1;
+      mbar_wait(bar_full(s), ph);
+      uint8_t* st = gbase + s * DW_STAGE_BYTES;
 #pragma unroll
-        for (int i = 0; i < (DW_A_BYTES + DW_B_BYTES) / 16 / 128; ++i) {
-          const int idx = xf_tid + 128 * i;             // float4 index over [A tile | B tile]
-          const bool is_b = idx >= DW_A_BYTES / 16;
-          const int off = is_b ? (idx * 16 - DW_A_BYTES) : idx * 16;
-          uint8_t* hi_p = st + (is_b ? DW_OFF_BHI : DW_OFF_AHI) + off;
-          uint8_t* lo_p = st + (is_b ? DW_OFF_BLO : DW_OFF_ALO) + off;
-          float4 v = *reinterpret_cast<const float4*>(hi_p);
-          if constexpr (PRO_B == 1) {
-            if (is_b) { v.x = prelu_f(v.x, alpha); v.y = prelu_f(v.y, alpha); v.z = prelu_f(v.z, alpha); v.w = prelu_f(v.w, alpha); }
-          }
-          float4 h, l;
-          h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
-          h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
-          h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
-          h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
-          if (!P.skip_hi_store || (PRO_B == 1 && is_b)) *reinterpret_cast<float4*>(hi_p) = h;
-          *reinterpret_cast<float4*>(lo_p) = l;
+      for (int i = 0; i < (DW_A_BYTES + DW_B_BYTES) / 16 / 128; ++i) {
+        const int idx = xf_tid + 128 * i;             // float4 index over [A tile | B tile]
+        const bool is_b = idx >= DW_A_BYTES / 16;
+        const int off = is_b ? (idx * 16 - DW_A_BYTES) : idx * 16;
+        uint8_t* hi_p = st + (is_b ? DW_OFF_BHI : DW_OFF_AHI) + off;
+        uint8_t* lo_p = st + (is_b ? DW_OFF_BLO : DW_OFF_ALO) + off;
+        float4 v = *reinterpret_cast<const float4*>(hi_p);
+        if constexpr (PRO_B == 1) {
+          if (is_b) { v.x = prelu_f(v.x, alpha); v.y = prelu_f(v.y, alpha); v.z = prelu_f(v.z, alpha); v.w = prelu_f(v.w, alpha); }
         }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_ready(s));
+        float4 h, l;
+        h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+        h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+        h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+        h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+        if (!P.skip_hi_store || (PRO_B == 1 && is_b)) *reinterpret_cast<float4*>(hi_p) = h;
+        *reinterpret_cast<float4*>(lo_p) = l;
       }
-    } else {
-      // epilogue warps 0..3: C[o][c] += D
-      const int q = warp;
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_ready(s));
+    }
+  } else {
+    // epilogue warps 0..3: C[o][c] += D for every segment of this CTA's range
+    const int q = warp;
+    uint32_t sg = 0;
+    for (int64_t u = u0; u < u1; ++sg) {
+      const int tile = (int)(u / KBT), kb_lo = (int)(u % KBT);
+      const int kb_hi = (int)min((int64_t)KBT, (int64_t)kb_lo + (u1 - u));
+      u += kb_hi - kb_lo;
+      int ob, cb, row;
+      decode(tile, ob, cb, row);
+      const int a = sg & 1;
       const int o = ob * DW_BM + q * 32 + lane;
       const bool o_ok = o < p.M;                      // rows beyond M were zero-filled by the TMA
       float* C = p.C + (p.per_row ? (int64_t)row * p.M * p.ldc : 0) + (int64_t)(o_ok ? o : 0) * p.ldc + cb * DW_BN;
       const int ncols = min(DW_BN, p.N - cb * DW_BN);
-      mbar_wait(bar_accf, 0);
+      mbar_wait(bar_accf(a), (sg >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
       for (int c0 = 0; c0 < DW_BN; c0 += 32) {
         if (c0 >= ncols) break;                       // warp-uniform
         uint32_t r[32];
-        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * DW_BN + c0), r);
 #pragma unroll
         for (int i = 0; i < 32; ++i)
           if (o_ok && c0 + i < ncols) atomicAdd(C + c0 + i, __uint_as_float(r[i]));
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_acce(a));
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 4) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(256u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -863,14 +901,22 @@ int launch_gemm_dw_tc(const GemmDwP& p, int pro_b, cudaStream_t st) {
   P.g = p;
   P.n_ob = cdiv(p.M, DW_BM);
   P.n_cb = cdiv(p.N, DW_BN);
-  const int tiles = P.n_ob * P.n_cb * p.n;
-  const int KBT = cdiv(p.T, DW_BK);
-  int ksplit = tiles >= 100 ? 1 : (148 + tiles - 1) / tiles;
-  if (ksplit > KBT / 8) ksplit = KBT / 8 > 0 ? KBT / 8 : 1;     // keep >= 8 k-blocks per CTA
-  P.kb_per_split = cdiv(KBT, ksplit);
-  P.ksplit = cdiv(KBT, P.kb_per_split);
+  P.n_tiles = P.n_ob * P.n_cb * p.n;
   P.skip_hi_store = (g_tc_flags & 1) ? 0 : 1;
-  const int grid = tiles * P.ksplit;
+  static int n_sm = 0;
+  if (!n_sm) {
+    int dev = 0;
+    WB_CUDA(cudaGetDevice(&dev));
+    WB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  }
+  // stream-K grid: one CTA per SM, but never fewer than 8 k-blocks per CTA
+  const int64_t units = (int64_t)P.n_tiles * cdiv(p.T, DW_BK);
+  int grid = n_sm;
+  if (units < (int64_t)grid * 8) grid = (int)(units / 8 > 0 ? units / 8 : 1);
+  // measured (tools/ab_block.py): with 128 tiles on 148 SMs, one whole tile per CTA is 6 % FASTER than the balanced
+  // 148-CTA split (the machine is power-capped; fewer partial-tile epilogues and better L2 sharing of the operand
+  // tiles win), so stream-K is kept for the cases that would leave most of the SMs idle.  bit 8 of the flags forces it.
+  if (!(g_tc_flags & 256) && P.n_tiles <= n_sm && P.n_tiles * 4 >= n_sm * 3) grid = P.n_tiles;
   if (pro_b == 0) {
     auto k = gemm_dw_tc_kernel<0>;
     WB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM_BYTES));
@@ -898,20 +944,23 @@ int launch_gemm_dw_tc(const GemmDwP& p, int pro_b, cudaStream_t st) {
 namespace wb {
 
 // Ring depth NS and epilogue staging (2 KB boxes of 32 channels x 16 frames, 64-byte swizzle, per epilogue warp):
-//   EPI 0     : NS = 6, one store box per warp                       (192 + 16 KB)
-//   EPI 2, 10 : NS = 4, T2_NL load boxes (R / d prefetch) + one store box per warp   (128 + 64 KB)
+//   PRO 0, EPI 0 : NS = 6, two store boxes per warp (no gLN scale/shift tables)               (192 + 32 KB)
+//   otherwise    : NS = 4, two store boxes + (EPI 2, 10) T2_NL load boxes (R / d prefetch)    (128 + 32..80 KB)
 // The epilogue moves its global traffic with TMA (coalesced 64-byte row segments) instead of one 16-byte access per
 // lane per row, which was measured to cost more than the MMAs themselves (profiles/r01_*: 448 vs 183 us).
-constexpr int T2_NL = 3;
+constexpr int T2_NL = 3, T2_NSB = 2;
 constexpr int T2_EBOX = 2048, T2_ECOLS = 16;
-__host__ __device__ constexpr int t2_nbuf(int epi) { return (epi == 2 || epi == 10) ? 1 + T2_NL : 1; }
-__host__ __device__ constexpr int t2_stages(int epi) { return (epi == 2 || epi == 10) ? 4 : 6; }
+__host__ __device__ constexpr int t2_nbuf(int epi) { return (epi == 2 || epi == 10) ? T2_NSB + T2_NL : T2_NSB; }
+__host__ __device__ constexpr int t2_stages(int pro, int epi) { return (pro == 0 && epi == 0) ? 6 : 4; }
+__host__ __device__ constexpr int t2_scsh_bytes(int pro) { return pro >= 2 ? 2 * TC_MAXK * 4 : 0; }
 constexpr int T2_BAR_BYTES = 512;
 constexpr int T2_XH_BYTES = (TC_BN / 2 / 32) * TC_BOX_BYTES;  // this CTA's half of the X tile: 4 boxes = 8192
 constexpr int T2_OFF_WHI = 0, T2_OFF_WLO = TC_W_BYTES, T2_OFF_XHI = 2 * TC_W_BYTES, T2_OFF_XLO = 2 * TC_W_BYTES + T2_XH_BYTES;
 constexpr int T2_STAGE_BYTES = 2 * TC_W_BYTES + 2 * T2_XH_BYTES;  // 32768
 constexpr int T2_TX_BYTES = 2 * TC_W_BYTES + T2_XH_BYTES;          // per CTA per stage
-__host__ __device__ constexpr int t2_smem_bytes(int ns, int nbuf) { return ns * T2_STAGE_BYTES + 8 * nbuf * T2_EBOX + 2 * TC_MAXK * 4 + T2_BAR_BYTES + 1024; }
+__host__ __device__ constexpr int t2_smem_bytes(int pro, int epi) {
+  return t2_stages(pro, epi) * T2_STAGE_BYTES + 8 * t2_nbuf(epi) * T2_EBOX + t2_scsh_bytes(pro) + T2_BAR_BYTES + 1024;
+}
 // D=f32, A=B=tf32, both MN-major, N=256, M=256 (cta_group::2)
 constexpr uint32_t T2_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(TC_BN >> 3) << 17) |
                               ((uint32_t)(256 >> 4) << 24);
@@ -966,16 +1015,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - raw);
-  float* sc = reinterpret_cast<float*>(gbase + AUX_OFF);
+  constexpr int SCSH = t2_scsh_bytes(PRO);
+  float* sc = reinterpret_cast<float*>(gbase + AUX_OFF);   // only PRO >= 2 has (and touches) the tables
   float* sh = sc + TC_MAXK;
-  const uint32_t bar0 = base + AUX_OFF + 2 * TC_MAXK * 4;
+  const uint32_t bar0 = base + AUX_OFF + SCSH;
   auto bar_full = [&](int s) { return bar0 + 8u * s; };
   auto bar_ready = [&](int s) { return bar0 + 8u * (T2_STAGES + s); };
   auto bar_empty = [&](int s) { return bar0 + 8u * (2 * T2_STAGES + s); };
   auto bar_accf = [&](int a) { return bar0 + 8u * (3 * T2_STAGES + a); };
   auto bar_acce = [&](int a) { return bar0 + 8u * (3 * T2_STAGES + 2 + a); };
   auto bar_ld = [&](int w, int b_) { return bar0 + 8u * (3 * T2_STAGES + 4 + w * T2_NL + b_); };   // per epilogue warp
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + AUX_OFF + 2 * TC_MAXK * 4 + 8 * (3 * T2_STAGES + 4 + 8 * T2_NL));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + AUX_OFF + SCSH + 8 * (3 * T2_STAGES + 4 + 8 * T2_NL));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();       // 0 = leader
@@ -1141,8 +1191,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     const int q = warp & 3;
     const int chalf = warp >> 2;
     const EpiP& e = p.ep;
-    uint8_t* sbox = gbase + EB_OFF + warp * (NBUF * T2_EBOX);          // store box; load boxes follow it
+    uint8_t* sbox = gbase + EB_OFF + warp * (NBUF * T2_EBOX);          // T2_NSB store boxes, then the load boxes
     const uint32_t sbox_u = base + EB_OFF + warp * (NBUF * T2_EBOX);
+    uint32_t sc_i = 0;                                                 // store passes issued by this warp
     const uint32_t lrow = (uint32_t)lane * 64u, lsw = (uint32_t)(lane >> 1) & 3u;   // 64-byte swizzle: chunk ^= (row / 2) % 4
     const bool ld_on = HAS_LD && !(P.dbg & 1);
     // prefetch iterator over this warp's (tile, pass) sequence; passes whose first frame is >= T do not exist
@@ -1157,7 +1208,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           const int b_ = (int)(li % T2_NL);
           if (lane == 0) {
             mbar_expect_tx(bar_ld(warp, b_), T2_EBOX);
-            tma_load_3d(sbox_u + (1 + b_) * T2_EBOX, &map_r, bar_ld(warp, b_), pt0 + pc0, po0 + q * 32, pn);
+            tma_load_3d(sbox_u + (T2_NSB + b_) * T2_EBOX, &map_r, bar_ld(warp, b_), pt0 + pc0, po0 + q * 32, pn);
           }
           ++li;
           ++p_j;
@@ -1186,9 +1237,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
       float mu2 = 0.f, r2 = 1.f, a2 = 1.f, gam2 = 0.f, mh = 0.f, mhy = 0.f, gam1 = 0.f, bet1 = 0.f, bdm = 0.f, w0 = 0.f, w1 = 0.f,
             w2 = 0.f;
       if constexpr (EPI == 10) {
-        gln_mean_rstd(e.stats2 + 2 * n, e.count2, e.eps2, mu2, r2);
+        // per-row scalars were finalised by tcn_f2a_kernel (rowsc[6] = mean2, rowsc[7] = rstd2): no fp64 division /
+        // sqrt per thread per tile here
+        mu2 = (float)e.rowsc[8 * n + 6]; r2 = (float)e.rowsc[8 * n + 7];
         a2 = __ldg(e.a2); gam2 = __ldg(e.g2 + o);
-        mh = (float)(e.rowsc[8 * n + 0] / e.count2); mhy = (float)(e.rowsc[8 * n + 1] / e.count2);
+        const float inv_cnt = 1.f / (float)e.count2;
+        mh = (float)e.rowsc[8 * n + 0] * inv_cnt; mhy = (float)e.rowsc[8 * n + 1] * inv_cnt;
         gam1 = __ldg(e.g1 + o); bet1 = __ldg(e.be1 + o); bdm = __ldg(e.bd + o);
         w0 = __ldg(e.wd + 3 * o); w1 = __ldg(e.wd + 3 * o + 1); w2 = __ldg(e.wd + 3 * o + 2);
       }
@@ -1212,7 +1266,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           if (ld_on) {
             const int b_ = (int)(lc % T2_NL);
             mbar_wait(bar_ld(warp, b_), (lc / T2_NL) & 1);
-            const uint8_t* lb = sbox + (1 + b_) * T2_EBOX + lrow;
+            const uint8_t* lb = sbox + (T2_NSB + b_) * T2_EBOX + lrow;
 #pragma unroll
             for (int g = 0; g < 4; ++g) gop[g] = *reinterpret_cast<const float4*>(lb + (((uint32_t)g ^ lsw) << 4));
             ++lc;
@@ -1279,15 +1333,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
             outv[g] = make_float4(dd[0], dd[1], dd[2], dd[3]);
           }
         }
-        // registers -> store box (previous TMA store must have finished READING it) -> TMA store (frames >= T are clipped)
-        if (lane == 0) bulk_wait_read0();
+        // registers -> store box (the TMA store issued two passes ago must have finished READING it) -> TMA store
+        // (frames >= T are clipped)
+        const uint32_t sb_off = (P.dbg & 8) ? 0u : (sc_i & 1u) * T2_EBOX;   // dbg 8: single store box (A/B timing)
+        ++sc_i;
+        if (lane == 0) {
+          if (P.dbg & 8) bulk_wait_read0();
+          else bulk_wait_read1();
+        }
         __syncwarp();
 #pragma unroll
-        for (int g = 0; g < 4; ++g) *reinterpret_cast<float4*>(sbox + lrow + (((uint32_t)g ^ lsw) << 4)) = outv[g];
+        for (int g = 0; g < 4; ++g) *reinterpret_cast<float4*>(sbox + sb_off + lrow + (((uint32_t)g ^ lsw) << 4)) = outv[g];
         fence_proxy_async();
         __syncwarp();
         if (lane == 0 && !(P.dbg & 2)) {
-          tma_store_3d(&map_y, sbox_u, t0 + c0, o0 + q * 32, n);
+          tma_store_3d(&map_y, sbox_u + sb_off, t0 + c0, o0 + q * 32, n);
           bulk_commit();
         }
       }
@@ -1345,8 +1405,8 @@ bool gemm_wx_tc2_eligible(const GemmWxP& p, int pro, int epi) {
 template <int PRO, int EPI>
 static int launch_tc2_t(const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& mx, const CUtensorMap& my,
                         const CUtensorMap& mr, const TcParams& P, cudaStream_t st) {
-  constexpr int NS = t2_stages(EPI);
-  constexpr int SMEM = t2_smem_bytes(NS, t2_nbuf(EPI));
+  constexpr int NS = t2_stages(PRO, EPI);
+  constexpr int SMEM = t2_smem_bytes(PRO, EPI);
   static_assert(SMEM <= 232448, "2-CTA kernel exceeds the 227 KB shared-memory limit");
   static_assert((3 * NS + 4 + 8 * T2_NL) * 8 + 4 <= T2_BAR_BYTES, "barrier area too small");
   auto k = gemm_wx_tc2_kernel<PRO, EPI, NS>;
@@ -1367,7 +1427,7 @@ int launch_gemm_wx_tc2(const CUtensorMap& mh, const CUtensorMap& ml, const CUten
                        cudaStream_t st) {
   if (!((pro == 0 && (epi == 0 || epi == 2 || epi == 10)) || (pro == 2 && epi == 2) || (pro == 3 && epi == 0)))
     return -100;                                // not instantiated: caller falls back to the 1-CTA kernel
-  if (t2_stages(epi) % P.xf_groups) P.xf_groups = 2;   // must divide the ring depth (see launch_gemm_wx_tc)
+  if (t2_stages(pro, epi) % P.xf_groups) P.xf_groups = 2;   // must divide the ring depth (see launch_gemm_wx_tc)
   P.n_ob = P.g.M / 256;                       // channel PAIRS
   P.n_tiles = P.n_ob * P.n_tt * P.g.n;
   // epilogue boxes: (16 frames, 32 channels, 1 row) with the 64-byte swizzle; frames >= T are clipped / zero-filled

@@ -121,9 +121,9 @@ __global__ void __launch_bounds__(ST_THREADS) tcn_dw_bwd_generic_kernel(const St
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
   float dal = 0.f;
   if (c < p.H) {
-    const double Mc = p.count;
-    const float m1 = (float)(p.rowacc[8 * n + 2] / Mc);
-    const float m2 = (float)((p.rowacc[8 * n + 3] - p.rowacc[8 * n + 4]) / Mc);
+    const double iMc = __drcp_rn(p.count);
+    const float m1 = (float)(p.rowacc[8 * n + 2] * iMc);
+    const float m2 = (float)((p.rowacc[8 * n + 3] - p.rowacc[8 * n + 4]) * iMc);
     const float w0 = __ldg(p.wd + 3 * c), w1 = __ldg(p.wd + 3 * c + 1), w2 = __ldg(p.wd + 3 * c + 2);
     float* durow = p.du + ((int64_t)n * p.H + c) * p.ld;
     const float* dc = dds + dil;
@@ -302,9 +302,9 @@ __global__ void __launch_bounds__(ST_THREADS) tcn_dw_bwd_kernel(const StBwdP p) 
     gln_mean_rstd(p.stats1 + 2 * n, p.count, GLN_EPS, mu, r);
     const float a1 = __ldg(p.a1), gm = __ldg(p.g1 + c), bt = __ldg(p.be1 + c);
     const float sc = gm * r, sh = bt - gm * mu * r;
-    const double Mc = p.count;
-    const float m1 = (float)(p.rowacc[8 * n + 2] / Mc);
-    const float m2 = (float)((p.rowacc[8 * n + 3] - p.rowacc[8 * n + 4]) / Mc);
+    const double iMc = __drcp_rn(p.count);
+    const float m1 = (float)(p.rowacc[8 * n + 2] * iMc);
+    const float m2 = (float)((p.rowacc[8 * n + 3] - p.rowacc[8 * n + 4]) * iMc);
     const float w0 = __ldg(p.wd + 3 * c), w1 = __ldg(p.wd + 3 * c + 1), w2 = __ldg(p.wd + 3 * c + 2);
     const float* urow = p.u + ((int64_t)n * p.H + c) * p.ld;
     const float* drow = p.dd + ((int64_t)n * p.H + c) * p.ld;
