@@ -82,3 +82,64 @@ def test_conv1x1_dw_backends(backend, n, M, N, T, pro, per_row):
     if not per_row:
         ref = ref.sum(0)
     check("C", C, ref, 1e-4 if n * T > 100000 else 1e-5)   # 2e5-term fp32 sums (tensor-core accumulation truncates)
+
+
+@pytest.mark.parametrize("n,M,N,T,pro,stats", [(2, 256, 256, 2133, 3, False), (3, 256, 512, 711, 3, False),
+                                                (2, 128, 256, 1000, 2, True), (2, 512, 512, 2133, 3, False)])
+def test_conv1x1_dw_scale_shift_prologues(backend, n, M, N, T, pro, stats):
+    """pro_b 2: sc*prelu(b)+sh (gLN apply, per-row statistics); pro_b 3: prelu(sc*b+sh) (BatchNorm apply, then PReLU)
+    — the ResBlock weight gradients (wesep/modules/tasnet/speaker.py:31-45)."""
+    from wesep_b200 import ops
+    A = ops.new_act(n, M, T, DEV)
+    A.copy_(rnd(n, M, T, seed=1))
+    B = ops.new_act(n, N, T, DEV)
+    B.copy_(rnd(n, N, T, seed=2))
+    alpha = torch.tensor([0.3], device=DEV)
+    gm = (1.0 + 0.1 * rnd(N, seed=3)).to(DEV)
+    bt = (0.1 * rnd(N, seed=4)).to(DEV)
+    st = None
+    Bd = B.double()
+    prelu = lambda x: torch.where(x > 0, x, 0.3 * x)
+    if stats:
+        y = prelu(Bd)
+        cnt = float(N * T)
+        st = torch.stack([y.sum((1, 2)), (y * y).sum((1, 2))], 1).contiguous()
+        mu = (st[:, 0] / cnt).view(n, 1, 1)
+        r = 1.0 / torch.sqrt(st[:, 1].view(n, 1, 1) / cnt - mu * mu + 1e-5)
+    else:
+        mu, r, cnt = 0.0, 1.0, 1.0
+    g, b_ = gm.double().view(1, N, 1), bt.double().view(1, N, 1)
+    if pro == 2:
+        f = g * (prelu(Bd) - mu) * r + b_
+    else:
+        f = prelu(g * r * (Bd - mu) + b_) if stats else prelu(g * Bd + b_)
+    C = torch.zeros((M, N), device=DEV)
+    ops.conv1x1_dw_raw(A, B, C, pro_b=pro, alpha_b=alpha, ch_scale_b=gm, ch_shift_b=bt, row_stats_b=st,
+                       stat_count=cnt, stat_eps=1e-5 if stats else 0.0)
+    ref = torch.einsum("nmt,nkt->mk", A.double(), f)
+    check("C", C, ref, 1e-5)
+
+
+@pytest.mark.parametrize("n,Kd,M,T", [(2, 256, 768, 6399), (3, 256, 256, 517), (2, 128, 512, 2133)])
+def test_conv1x1_relu_mask_and_channel_stats_epilogues(backend, n, Kd, M, T):
+    """epi 1 (ReLU, encoder.py:99), epi 3 (decoder masks: Y2 = relu(v), Y = aux * relu(v), decoder.py:96-102) and the
+    BatchNorm channel statistics by-product of epi 0 (speaker.py:31-45), on channel counts the 2-CTA kernel takes."""
+    from wesep_b200 import ops
+    x = ops.new_act(n, Kd, T, DEV)
+    x.copy_(rnd(n, Kd, T, seed=1))
+    W = rnd(M, Kd, seed=2, scale=1 / math.sqrt(Kd))
+    b = rnd(M, seed=3)
+    v = torch.einsum("mk,nkt->nmt", W.double(), x.double()) + b.double()[None, :, None]
+    y1 = ops.conv1x1_raw(x, W, False, M, bias=b, epi=1)
+    check("relu", y1, v.clamp_min(0), 1e-5)
+    aux = ops.new_act(n, M, T, DEV)
+    aux.copy_(rnd(n, M, T, seed=5))
+    Y2 = ops.new_act(n, M, T, DEV)
+    y3 = ops.conv1x1_raw(x, W, False, M, bias=b, epi=3, R=aux, Y2=Y2)
+    check("masks", Y2, v.clamp_min(0), 1e-5)
+    check("masked", y3, aux.double() * v.clamp_min(0), 1e-5)
+    chs = torch.zeros(M, 2, dtype=torch.float64, device=DEV)
+    y0 = ops.conv1x1_raw(x, W, False, M, bias=b, epi=0, ch_stats=chs)
+    check("y", y0, v, 1e-5)
+    check("ch_sum", chs[:, 0], v.sum((0, 2)), 1e-4)
+    check("ch_sumsq", chs[:, 1], (v * v).sum((0, 2)), 1e-5)

@@ -188,12 +188,17 @@ static int launch_gemm_dw_t(const GemmDwP& p, cudaStream_t st) {
   return 0;
 }
 
+bool gemm_dw_uses_tc(const GemmDwP& p, int pro_b) {
+  return g_gemm_backend == 1 && g_gemm_mode == 0 && gemm_dw_tc_eligible(p, pro_b);
+}
+
 int launch_gemm_dw(const GemmDwP& pin, int pro_b, cudaStream_t st) {
   GemmDwP p = pin;
   if (p.n <= 0 || p.M <= 0 || p.N <= 0 || p.T <= 0) return fail(-1, "gemm_dw: empty shape");
   if ((p.lda & 3) || (p.ldb & 3) || !aligned16(p.A) || !aligned16(p.B)) return fail(-1, "gemm_dw: lda/ldb/base alignment");
   if (p.ldc < p.N) return fail(-1, "gemm_dw: ldc < N");
-  if (g_gemm_backend == 1 && g_gemm_mode == 0 && gemm_dw_tc_eligible(p, pro_b)) return launch_gemm_dw_tc(p, pro_b, st);
+  if (gemm_dw_uses_tc(p, pro_b)) return launch_gemm_dw_tc(p, pro_b, st);
+  if (p.a_rowsum) return fail(-2, "gemm_dw: a_rowsum is only produced by the tcgen05 path");
   if (p.t_chunk <= 0) {
     // aim for >= ~2 waves of CTAs (296 resident) without making chunks tiny
     int tiles = cdiv(p.M, G_BM) * cdiv(p.N, G_BN) * p.n;

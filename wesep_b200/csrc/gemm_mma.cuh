@@ -412,8 +412,10 @@ struct GemmDwP {
   float* C; int64_t ldc; int per_row;
   XformP xb;   // prologue on B: v = sc[c]*prelu(b)+sh[c] with sc = ch_scale*r_n, sh = ch_shift - ch_scale*mu_n*r_n
   int t_chunk; // time steps per CTA (multiple of G_BK)
+  float* a_rowsum;  // optional, tcgen05 path only: += [n][M] sum_t A[n][m][t] (a by-product of the operand transform)
 };
 int launch_gemm_dw(const GemmDwP& p, int pro_b, cudaStream_t st);
+bool gemm_dw_uses_tc(const GemmDwP& p, int pro_b);   // true when launch_gemm_dw will take the tcgen05 path
 bool gemm_dw_tc_eligible(const GemmDwP& p, int pro_b);
 int launch_gemm_dw_tc(const GemmDwP& p, int pro_b, cudaStream_t st);
 

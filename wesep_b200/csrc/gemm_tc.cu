@@ -791,37 +791,104 @@ __global__ void __launch_bounds__(DW_THREADS, 1)
   } else if (warp >= 6) {
     const int tt_id = tid - 6 * 32;
     float alpha = 1.f;
-    if constexpr (PRO_B == 1) alpha = p.xb.alpha ? __ldg(p.xb.alpha) : 1.f;
+    if constexpr (PRO_B >= 1) alpha = p.xb.alpha ? __ldg(p.xb.alpha) : 1.f;
     const int xf_gid = tt_id >> 7, xf_tid = tt_id & 127;   // DW_STAGES % 2 == 0: a slot always belongs to the same group
     const int n_it = (int)(u1 - u0);
+    // optional by-product: row sums of A over time.  A float4 at index idx of the (swizzled) A tile always belongs
+    // to tile row idx / 4, and this thread meets the same 4 rows in every stage, so the partial sums live in
+    // registers and are flushed when the CTA's range moves to another tile.  Only column-block 0 tiles contribute
+    // (the other column blocks see the same A rows again); frames >= T were zero-filled by the TMA.
+    constexpr int A_F4 = DW_A_BYTES / 16 / 128;       // A float4s per transform thread per stage (4)
+    constexpr int B_F4 = DW_B_BYTES / 16 / 128;       // B float4s per transform thread per stage (8)
+    float rs[A_F4];
+#pragma unroll
+    for (int i = 0; i < A_F4; ++i) rs[i] = 0.f;
+    auto flush_rs = [&](int tile) {
+      int ob, cb, row;
+      decode(tile, ob, cb, row);
+      if (p.a_rowsum && cb == 0) {
+#pragma unroll
+        for (int i = 0; i < A_F4; ++i) {
+          const int o = ob * DW_BM + (xf_tid + 128 * i) / 4;
+          if (o < p.M) atomicAdd(p.a_rowsum + (int64_t)row * p.M + o, rs[i]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < A_F4; ++i) rs[i] = 0.f;
+    };
+    // PRO_B 2 / 3: per-channel (= per B-tile row) scale / shift of this thread's 8 rows, rebuilt per tile
+    float bsc[B_F4], bsh[B_F4];
+#pragma unroll
+    for (int j = 0; j < B_F4; ++j) { bsc[j] = 1.f; bsh[j] = 0.f; }
+    auto load_scsh = [&](int tile) {
+      if constexpr (PRO_B >= 2) {
+        int ob, cb, row;
+        decode(tile, ob, cb, row);
+        float mu = 0.f, r = 1.f;
+        if (p.xb.row_stats) gln_mean_rstd(p.xb.row_stats + 2 * row, p.xb.count, p.xb.eps, mu, r);
+#pragma unroll
+        for (int j = 0; j < B_F4; ++j) {
+          const int c = cb * DW_BN + (xf_tid + 128 * j) / 4;
+          const float gm = (p.xb.ch_scale && c < p.N) ? __ldg(p.xb.ch_scale + c) : 1.f;
+          const float bt = (p.xb.ch_shift && c < p.N) ? __ldg(p.xb.ch_shift + c) : 0.f;
+          bsc[j] = gm * r;
+          bsh[j] = bt - gm * mu * r;
+        }
+      }
+    };
+    int cur_tile = (int)(u0 / KBT);
+    int next_b = KBT - (int)(u0 % KBT);               // first `it` that belongs to the next tile
+    load_scsh(cur_tile);
     for (int it = xf_gid; it < n_it; it += 2) {
       const int s = it % DW_STAGES;
       const uint32_t ph = (it / DW_STAGES) & 1;
+      while (it >= next_b) {
+        if (p.a_rowsum) flush_rs(cur_tile);
+        ++cur_tile;
+        next_b += KBT;
+        load_scsh(cur_tile);
+      }
       mbar_wait(bar_full(s), ph);
       uint8_t* st = gbase + s * DW_STAGE_BYTES;
 #pragma unroll
-      for (int i = 0; i < (DW_A_BYTES + DW_B_BYTES) / 16 / 128; ++i) {
+      for (int i = 0; i < A_F4 + B_F4; ++i) {
         const int idx = xf_tid + 128 * i;             // float4 index over [A tile | B tile]
-        const bool is_b = idx >= DW_A_BYTES / 16;
+        const bool is_b = i >= A_F4;
         const int off = is_b ? (idx * 16 - DW_A_BYTES) : idx * 16;
         uint8_t* hi_p = st + (is_b ? DW_OFF_BHI : DW_OFF_AHI) + off;
         uint8_t* lo_p = st + (is_b ? DW_OFF_BLO : DW_OFF_ALO) + off;
         float4 v = *reinterpret_cast<const float4*>(hi_p);
+        if (!is_b) rs[is_b ? 0 : i] += (v.x + v.y) + (v.z + v.w);
         if constexpr (PRO_B == 1) {
           if (is_b) { v.x = prelu_f(v.x, alpha); v.y = prelu_f(v.y, alpha); v.z = prelu_f(v.z, alpha); v.w = prelu_f(v.w, alpha); }
+        }
+        if constexpr (PRO_B == 2) {
+          if (is_b) {
+            const float c_ = bsc[is_b ? i - A_F4 : 0], d_ = bsh[is_b ? i - A_F4 : 0];
+            v.x = fmaf(c_, prelu_f(v.x, alpha), d_); v.y = fmaf(c_, prelu_f(v.y, alpha), d_);
+            v.z = fmaf(c_, prelu_f(v.z, alpha), d_); v.w = fmaf(c_, prelu_f(v.w, alpha), d_);
+          }
+        }
+        if constexpr (PRO_B == 3) {
+          if (is_b) {
+            const float c_ = bsc[is_b ? i - A_F4 : 0], d_ = bsh[is_b ? i - A_F4 : 0];
+            v.x = prelu_f(fmaf(c_, v.x, d_), alpha); v.y = prelu_f(fmaf(c_, v.y, d_), alpha);
+            v.z = prelu_f(fmaf(c_, v.z, d_), alpha); v.w = prelu_f(fmaf(c_, v.w, d_), alpha);
+          }
         }
         float4 h, l;
         h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
         h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
         h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
         h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
-        if (!P.skip_hi_store || (PRO_B == 1 && is_b)) *reinterpret_cast<float4*>(hi_p) = h;
+        if (!P.skip_hi_store || (PRO_B >= 1 && is_b)) *reinterpret_cast<float4*>(hi_p) = h;
         *reinterpret_cast<float4*>(lo_p) = l;
       }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_ready(s));
     }
+    if (p.a_rowsum && n_it > 0) flush_rs(cur_tile);
   } else {
     // epilogue warps 0..3: C[o][c] += D for every segment of this CTA's range
     const int q = warp;
@@ -877,7 +944,7 @@ int encode_map_sw(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dim
 }
 
 bool gemm_dw_tc_eligible(const GemmDwP& p, int pro_b) {
-  if (!(pro_b == 0 || pro_b == 1)) return false;
+  if (pro_b < 0 || pro_b > 3) return false;
   if ((p.lda & 3) || (p.ldb & 3) || (p.bsa & 3) || (p.bsb & 3) || !aligned16(p.A) || !aligned16(p.B)) return false;
   return true;
 }
@@ -917,15 +984,14 @@ int launch_gemm_dw_tc(const GemmDwP& p, int pro_b, cudaStream_t st) {
   // 148-CTA split (the machine is power-capped; fewer partial-tile epilogues and better L2 sharing of the operand
   // tiles win), so stream-K is kept for the cases that would leave most of the SMs idle.  bit 8 of the flags forces it.
   if (!(g_tc_flags & 256) && P.n_tiles <= n_sm && P.n_tiles * 4 >= n_sm * 3) grid = P.n_tiles;
-  if (pro_b == 0) {
-    auto k = gemm_dw_tc_kernel<0>;
+  auto launch = [&](auto k) -> int {
     WB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM_BYTES));
     k<<<grid, DW_THREADS, DW_SMEM_BYTES, st>>>(ma, mb, P);
-  } else {
-    auto k = gemm_dw_tc_kernel<1>;
-    WB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM_BYTES));
-    k<<<grid, DW_THREADS, DW_SMEM_BYTES, st>>>(ma, mb, P);
-  }
+    return 0;
+  };
+  if (int rc = pro_b == 0 ? launch(gemm_dw_tc_kernel<0>) : pro_b == 1 ? launch(gemm_dw_tc_kernel<1>)
+               : pro_b == 2 ? launch(gemm_dw_tc_kernel<2>) : launch(gemm_dw_tc_kernel<3>))
+    return rc;
   WB_LAUNCH_CHECK("gemm_dw_tc");
   return 0;
 }
@@ -950,7 +1016,7 @@ namespace wb {
 // lane per row, which was measured to cost more than the MMAs themselves (profiles/r01_*: 448 vs 183 us).
 constexpr int T2_NL = 3, T2_NSB = 2;
 constexpr int T2_EBOX = 2048, T2_ECOLS = 16;
-__host__ __device__ constexpr int t2_nbuf(int epi) { return (epi == 2 || epi == 10) ? T2_NSB + T2_NL : T2_NSB; }
+__host__ __device__ constexpr int t2_nbuf(int epi) { return (epi == 2 || epi == 3 || epi == 10) ? T2_NSB + T2_NL : T2_NSB; }
 __host__ __device__ constexpr int t2_stages(int pro, int epi) { return (pro == 0 && epi == 0) ? 6 : 4; }
 __host__ __device__ constexpr int t2_scsh_bytes(int pro) { return pro >= 2 ? 2 * TC_MAXK * 4 : 0; }
 constexpr int T2_BAR_BYTES = 512;
@@ -1005,7 +1071,8 @@ template <int PRO, int EPI, int NS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     gemm_wx_tc2_kernel(const __grid_constant__ CUtensorMap map_whi, const __grid_constant__ CUtensorMap map_wlo,
                        const __grid_constant__ CUtensorMap map_x2, const __grid_constant__ CUtensorMap map_y,
-                       const __grid_constant__ CUtensorMap map_r, const TcParams P) {
+                       const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_y2,
+                       const TcParams P) {
   constexpr int T2_STAGES = NS;
   constexpr int NBUF = t2_nbuf(EPI);
   constexpr int EB_OFF = NS * T2_STAGE_BYTES;                 // epilogue staging boxes
@@ -1187,7 +1254,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     // box in shared memory -> TMA store.  The R / d operand of EPI 2 / 10 arrives the same way (TMA load boxes,
     // prefetched T2_NL passes ahead, across tile boundaries), so every global access of the epilogue is a full
     // 64-byte row segment issued by the TMA unit rather than 32 scattered 16-byte accesses per warp instruction.
-    constexpr bool HAS_LD = (EPI == 2 || EPI == 10);
+    constexpr bool HAS_LD = (EPI == 2 || EPI == 3 || EPI == 10);
     const int q = warp & 3;
     const int chalf = warp >> 2;
     const EpiP& e = p.ep;
@@ -1277,6 +1344,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
         uint32_t r[16];
         tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TC_BN + c0), r);
         float4 outv[4];
+        [[maybe_unused]] float4 outv2[4];
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const int t = t0 + c0 + 4 * g;
@@ -1292,6 +1360,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
                 s1 = fmaf(y, y, s1);
               }
             }
+            if (e.ch_stats) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float y = (t + i < p.T) ? v[i] : 0.f;
+                s2 += y;
+                s3 = fmaf(y, y, s3);
+              }
+            }
+          } else if constexpr (EPI == 1) {
+            outv[g] = make_float4(fmaxf(v[0], 0.f), fmaxf(v[1], 0.f), fmaxf(v[2], 0.f), fmaxf(v[3], 0.f));
+          } else if constexpr (EPI == 3) {   // decoder masks: Y2 = relu(v) (stored first), Y = aux * relu(v)
+            const float4 rr = gop[g];
+            const float m0 = fmaxf(v[0], 0.f), m1 = fmaxf(v[1], 0.f), m2 = fmaxf(v[2], 0.f), m3 = fmaxf(v[3], 0.f);
+            outv2[g] = make_float4(m0, m1, m2, m3);
+            outv[g] = make_float4(rr.x * m0, rr.y * m1, rr.z * m2, rr.w * m3);
           } else if constexpr (EPI == 2) {
             const float4 rr = gop[g];
             outv[g] = make_float4(v[0] + rr.x, v[1] + rr.y, v[2] + rr.z, v[3] + rr.w);
@@ -1333,6 +1416,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
             outv[g] = make_float4(dd[0], dd[1], dd[2], dd[3]);
           }
         }
+        if constexpr (EPI == 3) {   // second output (the masks themselves) goes out through the other store box
+          const uint32_t sb2 = (sc_i & 1u) * T2_EBOX;
+          ++sc_i;
+          if (lane == 0) bulk_wait_read1();
+          __syncwarp();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) *reinterpret_cast<float4*>(sbox + sb2 + lrow + (((uint32_t)g ^ lsw) << 4)) = outv2[g];
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&map_y2, sbox_u + sb2, t0 + c0, o0 + q * 32, n);
+            bulk_commit();
+          }
+        }
         // registers -> store box (the TMA store issued two passes ago must have finished READING it) -> TMA store
         // (frames >= T are clipped)
         const uint32_t sb_off = (P.dbg & 8) ? 0u : (sc_i & 1u) * T2_EBOX;   // dbg 8: single store box (A/B timing)
@@ -1366,6 +1463,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
             atomicAdd(e.out_stats + 2 * n + 1, (double)s1);
           }
         }
+        if (e.ch_stats) {   // BatchNorm batch statistics: this lane owns channel o
+          atomicAdd(e.ch_stats + 2 * o, (double)s2);
+          atomicAdd(e.ch_stats + 2 * o + 1, (double)s3);
+        }
       }
       if constexpr (EPI == 10) {
         const float S = s0, SD = s1;
@@ -1397,14 +1498,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 bool gemm_wx_tc2_eligible(const GemmWxP& p, int pro, int epi) {
   if (g_tc_flags & 2) return false;              // debug switch: force the 1-CTA kernel
   if (p.M % 256) return false;
-  if (!(epi == 0 || epi == 2 || epi == 10)) return false;
-  if (epi == 0 && p.ep.ch_stats) return false;
+  if (!(epi == 0 || epi == 1 || epi == 2 || epi == 3 || epi == 10)) return false;
   return gemm_wx_tc_eligible(p, pro, epi);       // includes the 16-byte alignment of Y / R / d the TMA boxes need
 }
 
 template <int PRO, int EPI>
 static int launch_tc2_t(const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& mx, const CUtensorMap& my,
-                        const CUtensorMap& mr, const TcParams& P, cudaStream_t st) {
+                        const CUtensorMap& mr, const CUtensorMap& my2, const TcParams& P, cudaStream_t st) {
   constexpr int NS = t2_stages(PRO, EPI);
   constexpr int SMEM = t2_smem_bytes(PRO, EPI);
   static_assert(SMEM <= 232448, "2-CTA kernel exceeds the 227 KB shared-memory limit");
@@ -1418,28 +1518,34 @@ static int launch_tc2_t(const CUtensorMap& mh, const CUtensorMap& ml, const CUte
     WB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   }
   int clusters = P.n_tiles < n_sm / 2 ? P.n_tiles : n_sm / 2;
-  k<<<2 * clusters, TC_THREADS, SMEM, st>>>(mh, ml, mx, my, mr, P);
+  k<<<2 * clusters, TC_THREADS, SMEM, st>>>(mh, ml, mx, my, mr, my2, P);
   WB_LAUNCH_CHECK("gemm_wx_tc2");
   return 0;
 }
 
 int launch_gemm_wx_tc2(const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& mx, TcParams P, int pro, int epi,
                        cudaStream_t st) {
-  if (!((pro == 0 && (epi == 0 || epi == 2 || epi == 10)) || (pro == 2 && epi == 2) || (pro == 3 && epi == 0)))
+  if (!((pro == 0 && (epi == 0 || epi == 1 || epi == 2 || epi == 3 || epi == 10)) || (pro == 2 && epi == 2) ||
+        (pro == 3 && epi == 0)))
     return -100;                                // not instantiated: caller falls back to the 1-CTA kernel
   if (t2_stages(pro, epi) % P.xf_groups) P.xf_groups = 2;   // must divide the ring depth (see launch_gemm_wx_tc)
   P.n_ob = P.g.M / 256;                       // channel PAIRS
   P.n_tiles = P.n_ob * P.n_tt * P.g.n;
   // epilogue boxes: (16 frames, 32 channels, 1 row) with the 64-byte swizzle; frames >= T are clipped / zero-filled
   const GemmWxP& p = P.g;
-  CUtensorMap my, mr;
+  CUtensorMap my, mr, my2;
   const uint32_t ebox[3] = {T2_ECOLS, 32, 1};
   {
     uint64_t dims[3] = {(uint64_t)p.T, (uint64_t)p.M, (uint64_t)p.n};
     uint64_t strides[2] = {(uint64_t)p.ep.ldy * 4, (uint64_t)p.ep.bsy * 4};
     if (int rc = encode_map_sw(&my, p.ep.Y, 3, dims, strides, ebox, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
     mr = my;
-    if (epi == 2) {
+    my2 = my;
+    if (epi == 3) {
+      uint64_t s2[2] = {(uint64_t)p.ep.ldy2 * 4, (uint64_t)p.ep.bsy2 * 4};
+      if (int rc = encode_map_sw(&my2, p.ep.Y2, 3, dims, s2, ebox, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
+    }
+    if (epi == 2 || epi == 3) {
       uint64_t sr[2] = {(uint64_t)p.ep.ldr * 4, (uint64_t)p.ep.bsr * 4};
       if (int rc = encode_map_sw(&mr, p.ep.R, 3, dims, sr, ebox, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
     } else if (epi == 10) {
@@ -1447,11 +1553,13 @@ int launch_gemm_wx_tc2(const CUtensorMap& mh, const CUtensorMap& ml, const CUten
       if (int rc = encode_map_sw(&mr, p.ep.d, 3, dims, sd, ebox, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
     }
   }
-  if (pro == 0 && epi == 0) return launch_tc2_t<0, 0>(mh, ml, mx, my, mr, P, st);
-  if (pro == 0 && epi == 2) return launch_tc2_t<0, 2>(mh, ml, mx, my, mr, P, st);
-  if (pro == 0 && epi == 10) return launch_tc2_t<0, 10>(mh, ml, mx, my, mr, P, st);
-  if (pro == 2 && epi == 2) return launch_tc2_t<2, 2>(mh, ml, mx, my, mr, P, st);
-  return launch_tc2_t<3, 0>(mh, ml, mx, my, mr, P, st);
+  if (pro == 0 && epi == 0) return launch_tc2_t<0, 0>(mh, ml, mx, my, mr, my2, P, st);
+  if (pro == 0 && epi == 1) return launch_tc2_t<0, 1>(mh, ml, mx, my, mr, my2, P, st);
+  if (pro == 0 && epi == 2) return launch_tc2_t<0, 2>(mh, ml, mx, my, mr, my2, P, st);
+  if (pro == 0 && epi == 3) return launch_tc2_t<0, 3>(mh, ml, mx, my, mr, my2, P, st);
+  if (pro == 0 && epi == 10) return launch_tc2_t<0, 10>(mh, ml, mx, my, mr, my2, P, st);
+  if (pro == 2 && epi == 2) return launch_tc2_t<2, 2>(mh, ml, mx, my, mr, my2, P, st);
+  return launch_tc2_t<3, 0>(mh, ml, mx, my, mr, my2, P, st);
 }
 
 }  // namespace wb

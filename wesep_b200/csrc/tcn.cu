@@ -528,13 +528,15 @@ __global__ void tcn_bwd_tail_kernel(const TailP p) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < p.H) {
     float s = 0.f;
+#pragma unroll 8
     for (int n = 0; n < p.n; ++n) s += p.sdu[(int64_t)n * p.H + i];
     atomicAdd(p.db1 + i, s);
   }
-  if (i == 0) {
+  if (blockIdx.x == 0 && threadIdx.x < 32) {   // da2 = sum_n rowacc[n][5]: one warp, independent loads
     double s = 0.0;
-    for (int n = 0; n < p.n; ++n) s += p.rowacc[8 * n + 5];
-    atomicAdd(p.da2, (float)s);
+    for (int n = threadIdx.x; n < p.n; n += 32) s += p.rowacc[8 * n + 5];
+    s = warp_sum(s);
+    if (threadIdx.x == 0) atomicAdd(p.da2, (float)s);
   }
   if (p.E > 0) {
     if (i < p.n * p.E) {  // daux[n][e] = sum_h W1[h][B+e] sdu[n][h]
@@ -615,18 +617,21 @@ extern "C" int wesep_b200_tcn_block_bwd(const WesepTcnBwdArgs* bp, void* stream)
   WB_CUDA(cudaMemsetAsync(b.Gn, 0, sizeof(float) * (size_t)a.n * a.B * a.H, st));
   WB_CUDA(cudaMemsetAsync(b.sdu, 0, sizeof(float) * (size_t)a.n * a.H, st));
   WB_CUDA(cudaMemsetAsync(b.rowsc, 0, sizeof(double) * 8 * a.n, st));
-  {  // sg[n][o] = sum_t g
-    int rows = a.n * a.B;
-    rowsum_kernel<<<cdiv((int64_t)rows * 32, 256), 256, 0, st>>>(b.gout, a.ld, rows, a.T, b.sg);
-    WB_LAUNCH_CHECK("rowsum");
-  }
-  {  // Gn[n][o][c] = sum_t g[o][t] * prelu(d[c][t], a2)
+  {  // Gn[n][o][c] = sum_t g[o][t] * prelu(d[c][t], a2)  and  sg[n][o] = sum_t g[o][t]
     GemmDwP p{};
     p.n = a.n; p.M = a.B; p.N = a.H; p.T = a.T;
     p.A = b.gout; p.lda = a.ld; p.bsa = (int64_t)a.B * a.ld;
     p.B = a.d; p.ldb = a.ld; p.bsb = (int64_t)a.H * a.ld;
     p.C = b.Gn; p.ldc = a.H; p.per_row = 1;
     p.xb = XformP{a.a2, nullptr, nullptr, nullptr, 1.0, 0.f};
+    if (gemm_dw_uses_tc(p, 1)) {   // the tcgen05 kernel sums the rows of g while it splits the operand tiles
+      WB_CUDA(cudaMemsetAsync(b.sg, 0, sizeof(float) * (size_t)a.n * a.B, st));
+      p.a_rowsum = b.sg;
+    } else {
+      int rows = a.n * a.B;
+      rowsum_kernel<<<cdiv((int64_t)rows * 32, 256), 256, 0, st>>>(b.gout, a.ld, rows, a.T, b.sg);
+      WB_LAUNCH_CHECK("rowsum");
+    }
     if (int rc = launch_gemm_dw(p, 1, st)) return rc;
   }
   {
