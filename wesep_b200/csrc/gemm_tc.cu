@@ -686,7 +686,7 @@ struct DwTcParams {
 // how the tile count divides the SM count (128 tiles on 148 SMs left 14 % of the machine idle).  A range may span
 // tiles; every (tile, k-range) segment ends with an atomic add of its partial D into C, which the accumulate-into-C
 // contract already required.  The two TMEM accumulators let a segment's epilogue overlap the next segment's MMAs.
-template <int PRO_B>
+template <int PRO_B, bool RS>
 __global__ void __launch_bounds__(DW_THREADS, 1)
     gemm_dw_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const DwTcParams P) {
   extern __shared__ uint8_t smem_raw[];
@@ -806,7 +806,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1)
     auto flush_rs = [&](int tile) {
       int ob, cb, row;
       decode(tile, ob, cb, row);
-      if (p.a_rowsum && cb == 0) {
+      if (RS && cb == 0) {
 #pragma unroll
         for (int i = 0; i < A_F4; ++i) {
           const int o = ob * DW_BM + (xf_tid + 128 * i) / 4;
@@ -843,7 +843,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1)
       const int s = it % DW_STAGES;
       const uint32_t ph = (it / DW_STAGES) & 1;
       while (it >= next_b) {
-        if (p.a_rowsum) flush_rs(cur_tile);
+        if constexpr (RS) flush_rs(cur_tile);
         ++cur_tile;
         next_b += KBT;
         load_scsh(cur_tile);
@@ -858,7 +858,9 @@ __global__ void __launch_bounds__(DW_THREADS, 1)
         uint8_t* hi_p = st + (is_b ? DW_OFF_BHI : DW_OFF_AHI) + off;
         uint8_t* lo_p = st + (is_b ? DW_OFF_BLO : DW_OFF_ALO) + off;
         float4 v = *reinterpret_cast<const float4*>(hi_p);
-        if (!is_b) rs[is_b ? 0 : i] += (v.x + v.y) + (v.z + v.w);
+        if constexpr (RS) {
+          if (!is_b) rs[is_b ? 0 : i] += (v.x + v.y) + (v.z + v.w);
+        }
         if constexpr (PRO_B == 1) {
           if (is_b) { v.x = prelu_f(v.x, alpha); v.y = prelu_f(v.y, alpha); v.z = prelu_f(v.z, alpha); v.w = prelu_f(v.w, alpha); }
         }
@@ -888,7 +890,9 @@ __global__ void __launch_bounds__(DW_THREADS, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_ready(s));
     }
-    if (p.a_rowsum && n_it > 0) flush_rs(cur_tile);
+    if constexpr (RS) {
+      if (n_it > 0) flush_rs(cur_tile);
+    }
   } else {
     // epilogue warps 0..3: C[o][c] += D for every segment of this CTA's range
     const int q = warp;
@@ -949,8 +953,12 @@ bool gemm_dw_tc_eligible(const GemmDwP& p, int pro_b) {
   return true;
 }
 
+bool gemm_dw_tc2_eligible(const GemmDwP& p, int pro_b);
+int launch_gemm_dw_tc2(const GemmDwP& p, int pro_b, cudaStream_t st);
+
 int launch_gemm_dw_tc(const GemmDwP& p, int pro_b, cudaStream_t st) {
   if (!gemm_dw_tc_eligible(p, pro_b)) return fail(-2, "gemm_dw_tc: not eligible");
+  if (gemm_dw_tc2_eligible(p, pro_b)) return launch_gemm_dw_tc2(p, pro_b, st);   // 2-CTA kernel for 256-row multiples
   CUtensorMap ma, mb;
   {
     uint64_t dims[3] = {(uint64_t)p.T, (uint64_t)p.M, (uint64_t)p.n};
@@ -989,9 +997,15 @@ int launch_gemm_dw_tc(const GemmDwP& p, int pro_b, cudaStream_t st) {
     k<<<grid, DW_THREADS, DW_SMEM_BYTES, st>>>(ma, mb, P);
     return 0;
   };
-  if (int rc = pro_b == 0 ? launch(gemm_dw_tc_kernel<0>) : pro_b == 1 ? launch(gemm_dw_tc_kernel<1>)
-               : pro_b == 2 ? launch(gemm_dw_tc_kernel<2>) : launch(gemm_dw_tc_kernel<3>))
-    return rc;
+  int rc;
+  if (p.a_rowsum) {   // row sums of A are only wired for the two prologues the TCN block uses
+    if (pro_b > 1) return fail(-2, "gemm_dw_tc: a_rowsum needs pro_b 0 or 1");
+    rc = pro_b == 0 ? launch(gemm_dw_tc_kernel<0, true>) : launch(gemm_dw_tc_kernel<1, true>);
+  } else {
+    rc = pro_b == 0 ? launch(gemm_dw_tc_kernel<0, false>) : pro_b == 1 ? launch(gemm_dw_tc_kernel<1, false>)
+         : pro_b == 2 ? launch(gemm_dw_tc_kernel<2, false>) : launch(gemm_dw_tc_kernel<3, false>);
+  }
+  if (rc) return rc;
   WB_LAUNCH_CHECK("gemm_dw_tc");
   return 0;
 }
@@ -1560,6 +1574,333 @@ int launch_gemm_wx_tc2(const CUtensorMap& mh, const CUtensorMap& ml, const CUten
   if (pro == 0 && epi == 10) return launch_tc2_t<0, 10>(mh, ml, mx, my, mr, my2, P, st);
   if (pro == 2 && epi == 2) return launch_tc2_t<2, 2>(mh, ml, mx, my, mr, my2, P, st);
   return launch_tc2_t<3, 0>(mh, ml, mx, my, mr, my2, P, st);
+}
+
+}  // namespace wb
+
+// ================================================================================================
+// 2-CTA variant of gemm_dw_tc (tcgen05 cta_group::2): a cluster of two CTAs accumulates a 256 x 256 tile of
+// C += A f(B)^T.  Each CTA stages ITS 128 rows of A and ITS 128 rows of B per k-block (hi + lo: 32 KB per stage
+// instead of 48 KB), so the ring is 6 deep instead of 4 and the per-SM shared-memory traffic of a stage (TMA fill +
+// hi/lo transform + MMA operand reads) drops from ~144 KB to ~96 KB per 1060-cycle stage — the 1-CTA kernel sits
+// right at the 128 B/clk limit.  Roles, stream-K unit ranges (per cluster) and barriers follow gemm_dw_tc_kernel /
+// gemm_wx_tc2_kernel: the leader's MMA thread issues for the pair, commits are multicast, the peer's transform and
+// epilogue warps signal the leader's barriers with remote arrives.
+// ================================================================================================
+namespace wb {
+
+constexpr int D2_STAGES = 6;
+constexpr int D2_A_BYTES = 128 * DW_BK * 4, D2_B_BYTES = 128 * DW_BK * 4;   // per CTA per stage: 8 KB each
+constexpr int D2_OFF_AHI = 0, D2_OFF_ALO = D2_A_BYTES, D2_OFF_BHI = 2 * D2_A_BYTES, D2_OFF_BLO = 2 * D2_A_BYTES + D2_B_BYTES;
+constexpr int D2_STAGE_BYTES = 2 * D2_A_BYTES + 2 * D2_B_BYTES;             // 32768
+constexpr int D2_TX_BYTES = D2_A_BYTES + D2_B_BYTES;
+constexpr int D2_SMEM_BYTES = D2_STAGES * D2_STAGE_BYTES + 256 + 1024;
+// D=f32, A=B=tf32, both K-major, N=256, M=256 (cta_group::2)
+constexpr uint32_t D2_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+template <int PRO_B, bool RS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DW_THREADS, 1)
+    gemm_dw_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const DwTcParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const GemmDwP& p = P.g;
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw);
+  const uint32_t bar0 = base + D2_STAGES * D2_STAGE_BYTES;
+  auto bar_full = [&](int s) { return bar0 + 8u * s; };
+  auto bar_ready = [&](int s) { return bar0 + 8u * (D2_STAGES + s); };
+  auto bar_empty = [&](int s) { return bar0 + 8u * (2 * D2_STAGES + s); };
+  auto bar_accf = [&](int a) { return bar0 + 8u * (3 * D2_STAGES + a); };
+  auto bar_acce = [&](int a) { return bar0 + 8u * (3 * D2_STAGES + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + D2_STAGES * D2_STAGE_BYTES + 8 * (3 * D2_STAGES + 4));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();       // 0 = leader
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int KBT = (p.T + DW_BK - 1) / DW_BK;
+  const int64_t units = (int64_t)P.n_tiles * KBT;
+  const int64_t u0 = units * cluster_id / n_clusters, u1 = units * (cluster_id + 1) / n_clusters;
+  // unit -> (pair tile, k-block); tile = (row * n_cb + cb) * n_ob + ob2 (n_ob counts 256-row pairs)
+  auto decode = [&](int tile, int& ob, int& cb, int& row) {
+    ob = tile % P.n_ob;
+    const int rest = tile / P.n_ob;
+    cb = rest % P.n_cb;
+    row = rest / P.n_cb;
+  };
+
+  if (tid == 0) {
+    for (int s = 0; s < D2_STAGES; ++s) {
+      mbar_init(bar_full(s), 1);     // local TMA transaction barrier
+      mbar_init(bar_ready(s), 8);    // (leader's copy is used) 4 transform warps of the owning group x 2 CTAs
+      mbar_init(bar_empty(s), 1);    // multicast tcgen05.commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_accf(a), 1);     // multicast tcgen05.commit
+      mbar_init(bar_acce(a), 8);     // (leader's copy is used) 4 epilogue warps x 2 CTAs
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    fence_proxy_async();
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int64_t u = u0; u < u1;) {
+        const int tile = (int)(u / KBT), kb_lo = (int)(u % KBT);
+        const int kb_hi = (int)min((int64_t)KBT, (int64_t)kb_lo + (u1 - u));
+        int ob, cb, row;
+        decode(tile, ob, cb, row);
+        for (int kb = kb_lo; kb < kb_hi; ++kb, ++it) {
+          const int s = it % D2_STAGES;
+          const uint32_t ph = (it / D2_STAGES) & 1;
+          mbar_wait(bar_empty(s), ph ^ 1);
+          const uint32_t sb = base + s * D2_STAGE_BYTES;
+          mbar_expect_tx(bar_full(s), D2_TX_BYTES);
+          tma_load_3d(sb + D2_OFF_AHI, &map_a, bar_full(s), kb * DW_BK, ob * 256 + (int)rank * 128, row);
+          tma_load_3d(sb + D2_OFF_BHI, &map_b, bar_full(s), kb * DW_BK, cb * 256 + (int)rank * 128, row);
+        }
+        u += kb_hi - kb_lo;
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0 && rank == 0) {   // leader CTA issues for the pair
+      uint32_t it = 0, sg = 0;
+      for (int64_t u = u0; u < u1; ++sg) {
+        const int kb_lo = (int)(u % KBT);
+        const int kb_hi = (int)min((int64_t)KBT, (int64_t)kb_lo + (u1 - u));
+        const int a = sg & 1;
+        mbar_wait(bar_acce(a), ((sg >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + a * 256;
+        for (int kb = kb_lo; kb < kb_hi; ++kb, ++it) {
+          const int s = it % D2_STAGES;
+          const uint32_t ph = (it / D2_STAGES) & 1;
+          mbar_wait(bar_ready(s), ph);
+          tc_fence_after();
+          const uint32_t sb = base + s * D2_STAGE_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < DW_BK / 8; ++ks) {
+            const uint64_t a_hi = make_desc_k_sw64(sb + D2_OFF_AHI + ks * 32);
+            const uint64_t a_lo = make_desc_k_sw64(sb + D2_OFF_ALO + ks * 32);
+            const uint64_t b_hi = make_desc_k_sw64(sb + D2_OFF_BHI + ks * 32);
+            const uint64_t b_lo = make_desc_k_sw64(sb + D2_OFF_BLO + ks * 32);
+            tc_mma_tf32_2cta(d_tmem, a_lo, b_hi, D2_IDESC, (kb != kb_lo || ks != 0) ? 1u : 0u);
+            tc_mma_tf32_2cta(d_tmem, a_hi, b_lo, D2_IDESC, 1u);
+            tc_mma_tf32_2cta(d_tmem, a_hi, b_hi, D2_IDESC, 1u);
+          }
+          tc_commit_mc2(bar_empty(s));   // frees stage s in BOTH CTAs
+        }
+        tc_commit_mc2(bar_accf(a));      // accumulators complete in BOTH CTAs
+        u += kb_hi - kb_lo;
+      }
+    }
+  } else if (warp >= 6) {
+    const int tt_id = tid - 6 * 32;
+    float alpha = 1.f;
+    if constexpr (PRO_B >= 1) alpha = p.xb.alpha ? __ldg(p.xb.alpha) : 1.f;
+    const int xf_gid = tt_id >> 7, xf_tid = tt_id & 127;   // D2_STAGES % 2 == 0: a slot always belongs to the same group
+    const int n_it = (int)(u1 - u0);
+    constexpr int A_F4 = D2_A_BYTES / 16 / 128;       // 4
+    constexpr int B_F4 = D2_B_BYTES / 16 / 128;       // 4
+    float rs[A_F4];
+#pragma unroll
+    for (int i = 0; i < A_F4; ++i) rs[i] = 0.f;
+    auto flush_rs = [&](int tile) {
+      int ob, cb, row;
+      decode(tile, ob, cb, row);
+      if (RS && cb == 0) {
+#pragma unroll
+        for (int i = 0; i < A_F4; ++i) {
+          const int o = ob * 256 + (int)rank * 128 + (xf_tid + 128 * i) / 4;
+          if (o < p.M) atomicAdd(p.a_rowsum + (int64_t)row * p.M + o, rs[i]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < A_F4; ++i) rs[i] = 0.f;
+    };
+    float bsc[B_F4], bsh[B_F4];
+#pragma unroll
+    for (int j = 0; j < B_F4; ++j) { bsc[j] = 1.f; bsh[j] = 0.f; }
+    auto load_scsh = [&](int tile) {
+      if constexpr (PRO_B >= 2) {
+        int ob, cb, row;
+        decode(tile, ob, cb, row);
+        float mu = 0.f, r = 1.f;
+        if (p.xb.row_stats) gln_mean_rstd(p.xb.row_stats + 2 * row, p.xb.count, p.xb.eps, mu, r);
+#pragma unroll
+        for (int j = 0; j < B_F4; ++j) {
+          const int c = cb * 256 + (int)rank * 128 + (xf_tid + 128 * j) / 4;
+          const float gm = (p.xb.ch_scale && c < p.N) ? __ldg(p.xb.ch_scale + c) : 1.f;
+          const float bt = (p.xb.ch_shift && c < p.N) ? __ldg(p.xb.ch_shift + c) : 0.f;
+          bsc[j] = gm * r;
+          bsh[j] = bt - gm * mu * r;
+        }
+      }
+    };
+    int cur_tile = (int)(u0 / KBT);
+    int next_b = KBT - (int)(u0 % KBT);
+    if (n_it > 0) load_scsh(cur_tile);
+    for (int it = xf_gid; it < n_it; it += 2) {
+      const int s = it % D2_STAGES;
+      const uint32_t ph = (it / D2_STAGES) & 1;
+      while (it >= next_b) {
+        if constexpr (RS) flush_rs(cur_tile);
+        ++cur_tile;
+        next_b += KBT;
+        load_scsh(cur_tile);
+      }
+      mbar_wait(bar_full(s), ph);
+      uint8_t* st = gbase + s * D2_STAGE_BYTES;
+#pragma unroll
+      for (int i = 0; i < A_F4 + B_F4; ++i) {
+        const int idx = xf_tid + 128 * i;
+        const bool is_b = i >= A_F4;
+        const int off = is_b ? (idx * 16 - D2_A_BYTES) : idx * 16;
+        uint8_t* hi_p = st + (is_b ? D2_OFF_BHI : D2_OFF_AHI) + off;
+        uint8_t* lo_p = st + (is_b ? D2_OFF_BLO : D2_OFF_ALO) + off;
+        float4 v = *reinterpret_cast<const float4*>(hi_p);
+        if constexpr (RS) {
+          if (!is_b) rs[is_b ? 0 : i] += (v.x + v.y) + (v.z + v.w);
+        }
+        if constexpr (PRO_B == 1) {
+          if (is_b) { v.x = prelu_f(v.x, alpha); v.y = prelu_f(v.y, alpha); v.z = prelu_f(v.z, alpha); v.w = prelu_f(v.w, alpha); }
+        }
+        if constexpr (PRO_B == 2) {
+          if (is_b) {
+            const float c_ = bsc[is_b ? i - A_F4 : 0], d_ = bsh[is_b ? i - A_F4 : 0];
+            v.x = fmaf(c_, prelu_f(v.x, alpha), d_); v.y = fmaf(c_, prelu_f(v.y, alpha), d_);
+            v.z = fmaf(c_, prelu_f(v.z, alpha), d_); v.w = fmaf(c_, prelu_f(v.w, alpha), d_);
+          }
+        }
+        if constexpr (PRO_B == 3) {
+          if (is_b) {
+            const float c_ = bsc[is_b ? i - A_F4 : 0], d_ = bsh[is_b ? i - A_F4 : 0];
+            v.x = prelu_f(fmaf(c_, v.x, d_), alpha); v.y = prelu_f(fmaf(c_, v.y, d_), alpha);
+            v.z = prelu_f(fmaf(c_, v.z, d_), alpha); v.w = prelu_f(fmaf(c_, v.w, d_), alpha);
+          }
+        }
+        float4 h, l;
+        h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+        h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+        h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+        h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+        if (!P.skip_hi_store || (PRO_B >= 1 && is_b)) *reinterpret_cast<float4*>(hi_p) = h;
+        *reinterpret_cast<float4*>(lo_p) = l;
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {   // signal the LEADER's ready barrier (it gates the pair's MMAs)
+        if (rank == 0) mbar_arrive(bar_ready(s));
+        else mbar_arrive_cluster(bar_ready(s), 0);
+      }
+    }
+    if constexpr (RS) {
+      if (n_it > 0) flush_rs(cur_tile);
+    }
+  } else {
+    // epilogue warps 0..3: C[o][c] += D on this CTA's 128 rows, for every segment of the cluster's range
+    const int q = warp;
+    uint32_t sg = 0;
+    for (int64_t u = u0; u < u1; ++sg) {
+      const int tile = (int)(u / KBT), kb_lo = (int)(u % KBT);
+      const int kb_hi = (int)min((int64_t)KBT, (int64_t)kb_lo + (u1 - u));
+      u += kb_hi - kb_lo;
+      int ob, cb, row;
+      decode(tile, ob, cb, row);
+      const int a = sg & 1;
+      const int o = ob * 256 + (int)rank * 128 + q * 32 + lane;   // M % 256 == 0: always valid
+      float* C = p.C + (p.per_row ? (int64_t)row * p.M * p.ldc : 0) + (int64_t)o * p.ldc + cb * 256;
+      const int ncols = min(256, p.N - cb * 256);
+      mbar_wait(bar_accf(a), (sg >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < 256; c0 += 32) {
+        if (c0 >= ncols) break;                       // warp-uniform
+        uint32_t r[32];
+        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 256 + c0), r);
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c0 + i < ncols) atomicAdd(C + c0 + i, __uint_as_float(r[i]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(bar_acce(a));
+        else mbar_arrive_cluster(bar_acce(a), 0);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // the peer may still be reading this CTA's smem / signalling its barriers until here
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+bool gemm_dw_tc2_eligible(const GemmDwP& p, int pro_b) {
+  if (g_tc_flags & (2 | 512)) return false;      // debug switches: bit 1 = all GEMMs 1-CTA, bit 9 = only the dW GEMMs
+  if (p.M % 256) return false;
+  return gemm_dw_tc_eligible(p, pro_b);
+}
+
+int launch_gemm_dw_tc2(const GemmDwP& p, int pro_b, cudaStream_t st) {
+  CUtensorMap ma, mb;
+  const uint32_t box[3] = {DW_BK, 128, 1};
+  {
+    uint64_t dims[3] = {(uint64_t)p.T, (uint64_t)p.M, (uint64_t)p.n};
+    uint64_t strides[2] = {(uint64_t)p.lda * 4, (uint64_t)p.bsa * 4};
+    if (int rc = encode_map_sw(&ma, p.A, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)p.T, (uint64_t)p.N, (uint64_t)p.n};
+    uint64_t strides[2] = {(uint64_t)p.ldb * 4, (uint64_t)p.bsb * 4};
+    if (int rc = encode_map_sw(&mb, p.B, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
+  }
+  DwTcParams P;
+  P.g = p;
+  P.n_ob = p.M / 256;
+  P.n_cb = cdiv(p.N, 256);
+  P.n_tiles = P.n_ob * P.n_cb * p.n;
+  P.skip_hi_store = (g_tc_flags & 1) ? 0 : 1;
+  static int n_sm = 0;
+  if (!n_sm) {
+    int dev = 0;
+    WB_CUDA(cudaGetDevice(&dev));
+    WB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int max_clusters = n_sm / 2;
+  const int64_t units = (int64_t)P.n_tiles * cdiv(p.T, DW_BK);
+  int clusters = max_clusters;
+  if (units < (int64_t)clusters * 8) clusters = (int)(units / 8 > 0 ? units / 8 : 1);
+  // whole tiles per cluster when they nearly fill the machine (see launch_gemm_dw_tc); bit 8 of the flags forces stream-K
+  if (!(g_tc_flags & 256) && P.n_tiles <= max_clusters && P.n_tiles * 4 >= max_clusters * 3) clusters = P.n_tiles;
+  auto launch = [&](auto k) -> int {
+    WB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, D2_SMEM_BYTES));
+    k<<<2 * clusters, DW_THREADS, D2_SMEM_BYTES, st>>>(ma, mb, P);
+    return 0;
+  };
+  int rc;
+  if (p.a_rowsum) {
+    if (pro_b > 1) return fail(-2, "gemm_dw_tc2: a_rowsum needs pro_b 0 or 1");
+    rc = pro_b == 0 ? launch(gemm_dw_tc2_kernel<0, true>) : launch(gemm_dw_tc2_kernel<1, true>);
+  } else {
+    rc = pro_b == 0 ? launch(gemm_dw_tc2_kernel<0, false>) : pro_b == 1 ? launch(gemm_dw_tc2_kernel<1, false>)
+         : pro_b == 2 ? launch(gemm_dw_tc2_kernel<2, false>) : launch(gemm_dw_tc2_kernel<3, false>);
+  }
+  if (rc) return rc;
+  WB_LAUNCH_CHECK("gemm_dw_tc2");
+  return 0;
 }
 
 }  // namespace wb

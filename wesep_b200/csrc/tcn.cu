@@ -225,55 +225,68 @@ __device__ __forceinline__ void taps4g(const float* row, int t, int T, int dil, 
   }
 }
 
+// PReLU with slope a <= 1 is max(x, a*x) (2 instructions instead of compare + multiply + select); the kernels pick
+// the FAST instantiation when the (kernel-uniform) learned slopes allow it.
+template <bool FAST>
+__device__ __forceinline__ float prelu_t(float x, float a) {
+  if constexpr (FAST) return fmaxf(x, a * x);
+  else return prelu_f(x, a);
+}
+
+template <int DM, bool FAST>
+__device__ __forceinline__ void dw_fwd_body(const StFwdP& p, int sub, int t0, int c, int n, float& s, float& q) {
+  const int dil = p.dil;
+  float mu, r;
+  gln_mean_rstd(p.stats1 + 2 * n, p.count, GLN_EPS, mu, r);
+  const float a1 = __ldg(p.a1), gm = __ldg(p.g1 + c), bt = __ldg(p.be1 + c);
+  const float sc = gm * r, sh = bt - gm * mu * r;
+  const float w0 = __ldg(p.wd + 3 * c), w1 = __ldg(p.wd + 3 * c + 1), w2 = __ldg(p.wd + 3 * c + 2);
+  const float bd = __ldg(p.bd + c), a2 = __ldg(p.a2);
+  // interior: d = sum_j w_j (sc*y_j + sh) + bd = sum_j (w_j sc) y_j + (bd + sh sum_j w_j),  y = prelu(u)
+  const float v0 = w0 * sc, v1 = w1 * sc, v2 = w2 * sc, bdp = fmaf(sh, w0 + w1 + w2, bd);
+  const float* urow = p.u + ((int64_t)n * p.H + c) * p.ld;
+  float* drow = p.d + ((int64_t)n * p.H + c) * p.ld;
+#pragma unroll 2
+  for (int i = 4 * sub; i < ST_TT; i += 256) {
+    const int t = t0 + i;
+    if (t >= p.T) break;
+    float L[4], C[4], R[4], o[4];
+    taps4g<DM>(urow, t, p.T, dil, 0.f, L, C, R);
+    const bool interior = (t - dil >= 0) && (t + dil + 3 < p.T);
+    if (interior) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        o[k] = fmaf(v0, prelu_t<FAST>(L[k], a1), fmaf(v1, prelu_t<FAST>(C[k], a1), fmaf(v2, prelu_t<FAST>(R[k], a1), bdp)));
+        const float y = prelu_t<FAST>(o[k], a2);
+        s += y;
+        q = fmaf(y, y, q);
+      }
+    } else {   // z1 = sc*prelu(u) + sh inside [0,T) and 0 outside
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int e = t + k;
+        const float zl = (e - dil >= 0) ? fmaf(sc, prelu_f(L[k], a1), sh) : 0.f;
+        const float zc = (e < p.T) ? fmaf(sc, prelu_f(C[k], a1), sh) : 0.f;
+        const float zr = (e + dil < p.T) ? fmaf(sc, prelu_f(R[k], a1), sh) : 0.f;
+        o[k] = fmaf(w0, zl, fmaf(w1, zc, fmaf(w2, zr, bd)));
+        const float y = (e < p.T) ? prelu_f(o[k], a2) : 0.f;
+        s += y;
+        q = fmaf(y, y, q);
+      }
+    }
+    *reinterpret_cast<float4*>(drow + t) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 template <int DM>
 __global__ void __launch_bounds__(ST_THREADS) tcn_dw_fwd_kernel(const StFwdP p) {
   __shared__ float red[2 * 32];
   const int tid = threadIdx.x, sub = tid & 63, chl = tid >> 6;
   const int t0 = blockIdx.x * ST_TT, c = blockIdx.y * ST_CH + chl, n = blockIdx.z;
-  const int dil = p.dil;
   float s = 0.f, q = 0.f;
   if (c < p.H) {
-    float mu, r;
-    gln_mean_rstd(p.stats1 + 2 * n, p.count, GLN_EPS, mu, r);
-    const float a1 = __ldg(p.a1), gm = __ldg(p.g1 + c), bt = __ldg(p.be1 + c);
-    const float sc = gm * r, sh = bt - gm * mu * r;
-    // z1 = sc*prelu(u) + sh inside [0,T) and 0 outside: edge vectors take the masked path below
-    const float w0 = __ldg(p.wd + 3 * c), w1 = __ldg(p.wd + 3 * c + 1), w2 = __ldg(p.wd + 3 * c + 2);
-    const float bd = __ldg(p.bd + c), a2 = __ldg(p.a2);
-    const float* urow = p.u + ((int64_t)n * p.H + c) * p.ld;
-    float* drow = p.d + ((int64_t)n * p.H + c) * p.ld;
-#pragma unroll 2
-    for (int i = 4 * sub; i < ST_TT; i += 256) {
-      const int t = t0 + i;
-      if (t >= p.T) break;
-      float L[4], C[4], R[4], o[4];
-      taps4g<DM>(urow, t, p.T, dil, 0.f, L, C, R);
-      const bool interior = (t - dil >= 0) && (t + dil + 3 < p.T);
-      if (interior) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float zl = fmaf(sc, prelu_f(L[k], a1), sh), zc = fmaf(sc, prelu_f(C[k], a1), sh),
-                      zr = fmaf(sc, prelu_f(R[k], a1), sh);
-          o[k] = fmaf(w0, zl, fmaf(w1, zc, fmaf(w2, zr, bd)));
-          const float y = prelu_f(o[k], a2);
-          s += y;
-          q = fmaf(y, y, q);
-        }
-      } else {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int e = t + k;
-          const float zl = (e - dil >= 0) ? fmaf(sc, prelu_f(L[k], a1), sh) : 0.f;
-          const float zc = (e < p.T) ? fmaf(sc, prelu_f(C[k], a1), sh) : 0.f;
-          const float zr = (e + dil < p.T) ? fmaf(sc, prelu_f(R[k], a1), sh) : 0.f;
-          o[k] = fmaf(w0, zl, fmaf(w1, zc, fmaf(w2, zr, bd)));
-          const float y = (e < p.T) ? prelu_f(o[k], a2) : 0.f;
-          s += y;
-          q = fmaf(y, y, q);
-        }
-      }
-      *reinterpret_cast<float4*>(drow + t) = make_float4(o[0], o[1], o[2], o[3]);
-    }
+    if (__ldg(p.a1) <= 1.f && __ldg(p.a2) <= 1.f) dw_fwd_body<DM, true>(p, sub, t0, c, n, s, q);
+    else dw_fwd_body<DM, false>(p, sub, t0, c, n, s, q);
   }
   float v[2] = {s, q};
   block_sum<2>(v, red);
@@ -286,44 +299,54 @@ __global__ void __launch_bounds__(ST_THREADS) tcn_dw_fwd_kernel(const StFwdP p) 
 // Backward: the weight gradients are re-indexed so that only dd needs taps:
 //   dwd[c][0] = sum_t dd[t] z1[t - dil] = sum_t z1[t] dd[t + dil],  dwd[c][2] = sum_t z1[t] dd[t - dil]
 // (dd == 0 outside [0,T)), so u is read once, at the centre.
-template <int DM>
-__global__ void __launch_bounds__(ST_THREADS) tcn_dw_bwd_kernel(const StBwdP p) {
-  __shared__ float red[32];
-  __shared__ float chred[ST_CH][2][8];
-  const int tid = threadIdx.x, sub = tid & 63, chl = tid >> 6, lane = tid & 31;
-  const int t0 = blockIdx.x * ST_TTB, c = blockIdx.y * ST_CH + chl, n = blockIdx.z;
+template <int DM, bool FAST>
+__device__ __forceinline__ void dw_bwd_body(const StBwdP& p, int sub, int t0, int c, int n, float (&acc)[8], float& dal) {
   const int dil = p.dil;
-  float acc[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-  float dal = 0.f;
-  if (c < p.H) {
-    float mu, r;
-    gln_mean_rstd(p.stats1 + 2 * n, p.count, GLN_EPS, mu, r);
-    const float a1 = __ldg(p.a1), gm = __ldg(p.g1 + c), bt = __ldg(p.be1 + c);
-    const float sc = gm * r, sh = bt - gm * mu * r;
-    const double iMc = __drcp_rn(p.count);
-    const float m1 = (float)(p.rowacc[8 * n + 2] * iMc);
-    const float m2 = (float)((p.rowacc[8 * n + 3] - p.rowacc[8 * n + 4]) * iMc);
-    const float w0 = __ldg(p.wd + 3 * c), w1 = __ldg(p.wd + 3 * c + 1), w2 = __ldg(p.wd + 3 * c + 2);
-    const float* urow = p.u + ((int64_t)n * p.H + c) * p.ld;
-    const float* drow = p.dd + ((int64_t)n * p.H + c) * p.ld;
-    float* durow = p.du + ((int64_t)n * p.H + c) * p.ld;
-    // dy = r*(g1*dz - m1 - yhat1*m2) = cA*dz + cB*y1 + cC with y1 = prelu(u)
-    const float cA = r * gm, cB = -r * r * m2, cC = -r * m1 + r * r * m2 * mu;
+  float mu, r;
+  gln_mean_rstd(p.stats1 + 2 * n, p.count, GLN_EPS, mu, r);
+  const float a1 = __ldg(p.a1), gm = __ldg(p.g1 + c), bt = __ldg(p.be1 + c);
+  const float sc = gm * r, sh = bt - gm * mu * r;
+  const double iMc = __drcp_rn(p.count);
+  const float m1 = (float)(p.rowacc[8 * n + 2] * iMc);
+  const float m2 = (float)((p.rowacc[8 * n + 3] - p.rowacc[8 * n + 4]) * iMc);
+  const float w0 = __ldg(p.wd + 3 * c), w1 = __ldg(p.wd + 3 * c + 1), w2 = __ldg(p.wd + 3 * c + 2);
+  const float* urow = p.u + ((int64_t)n * p.H + c) * p.ld;
+  const float* drow = p.dd + ((int64_t)n * p.H + c) * p.ld;
+  float* durow = p.du + ((int64_t)n * p.H + c) * p.ld;
+  // dy = r*(g1*dz - m1 - yhat1*m2) = cA*dz + cB*y1 + cC with y1 = prelu(u)
+  const float cA = r * gm, cB = -r * r * m2, cC = -r * m1 + r * r * m2 * mu;
 #pragma unroll 2
-    for (int i = 4 * sub; i < ST_TTB; i += 256) {
-      const int t = t0 + i;
-      if (t >= p.T) break;
-      float dL[4], dC[4], dR[4], uu[4], o[4];
-      taps4g<DM>(drow, t, p.T, dil, 0.f, dL, dC, dR);   // dd outside [0,T) is 0
-      ld4(urow + t, uu);
-      const bool full = t + 3 < p.T;   // only the last vector of a row can be partial
+  for (int i = 4 * sub; i < ST_TTB; i += 256) {
+    const int t = t0 + i;
+    if (t >= p.T) break;
+    float dL[4], dC[4], dR[4], uu[4], o[4];
+    taps4g<DM>(drow, t, p.T, dil, 0.f, dL, dC, dR);   // dd outside [0,T) is 0
+    ld4(urow + t, uu);
+    if (t + 3 < p.T) {   // full vector (all but the last vector of a row)
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const bool ok = full || (t + k < p.T);
-        const float ddv = dC[k];
+        const float ddv = dC[k], uv = uu[k];
         const float dz = fmaf(w0, dR[k], fmaf(w1, ddv, w2 * dL[k]));  // dz1[t] = sum_j w[j] dd[t - (j-1) dil]
+        const float y1 = prelu_t<FAST>(uv, a1);
+        const float z1 = fmaf(sc, y1, sh);
+        const float dy = fmaf(cA, dz, fmaf(cB, y1, cC));
+        const float duv = uv > 0.f ? dy : a1 * dy;
+        o[k] = duv;
+        acc[0] += dz;                        // sum dz            -> dbeta1
+        acc[1] = fmaf(dz, y1, acc[1]);       // sum dz*y1         -> dgamma1 = r*(sum dz*y1 - mu*sum dz)
+        acc[2] = fmaf(z1, dR[k], acc[2]);
+        acc[3] = fmaf(z1, ddv, acc[3]);
+        acc[4] = fmaf(z1, dL[k], acc[4]);
+        acc[5] += ddv;
+        acc[6] += duv;
+        dal = fmaf(dy, fminf(uv, 0.f), dal);   // sum over u <= 0 of dy*u -> dalpha1
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const bool ok = t + k < p.T;
+        const float ddv = dC[k];
+        const float dz = fmaf(w0, dR[k], fmaf(w1, ddv, w2 * dL[k]));
         const float uv = ok ? uu[k] : 1.f;
         const bool pos = uv > 0.f;
         const float y1 = pos ? uv : a1 * uv;
@@ -333,8 +356,8 @@ __global__ void __launch_bounds__(ST_THREADS) tcn_dw_bwd_kernel(const StBwdP p) 
         float dzy = dz * y1, dyu = pos ? 0.f : dy * uv, dzm = dz;
         if (!ok) { duv = 0.f; dzy = 0.f; dyu = 0.f; dzm = 0.f; }
         o[k] = duv;
-        acc[0] += dzm;                       // sum dz            -> dbeta1
-        acc[1] += dzy;                       // sum dz*y1         -> dgamma1 = r*(sum dz*y1 - mu*sum dz)
+        acc[0] += dzm;
+        acc[1] += dzy;
         acc[2] = fmaf(z1, dR[k], acc[2]);
         acc[3] = fmaf(z1, ddv, acc[3]);
         acc[4] = fmaf(z1, dL[k], acc[4]);
@@ -342,9 +365,25 @@ __global__ void __launch_bounds__(ST_THREADS) tcn_dw_bwd_kernel(const StBwdP p) 
         acc[6] += duv;
         dal += dyu;
       }
-      *reinterpret_cast<float4*>(durow + t) = make_float4(o[0], o[1], o[2], o[3]);
     }
-    acc[1] = r * (acc[1] - mu * acc[0]);
+    *reinterpret_cast<float4*>(durow + t) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+  acc[1] = r * (acc[1] - mu * acc[0]);
+}
+
+template <int DM>
+__global__ void __launch_bounds__(ST_THREADS) tcn_dw_bwd_kernel(const StBwdP p) {
+  __shared__ float red[32];
+  __shared__ float chred[ST_CH][2][8];
+  const int tid = threadIdx.x, sub = tid & 63, chl = tid >> 6, lane = tid & 31;
+  const int t0 = blockIdx.x * ST_TTB, c = blockIdx.y * ST_CH + chl, n = blockIdx.z;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  float dal = 0.f;
+  if (c < p.H) {
+    if (__ldg(p.a1) <= 1.f) dw_bwd_body<DM, true>(p, sub, t0, c, n, acc, dal);
+    else dw_bwd_body<DM, false>(p, sub, t0, c, n, acc, dal);
   }
 #pragma unroll
   for (int i = 0; i < 7; ++i) acc[i] = warp_sum(acc[i]);
