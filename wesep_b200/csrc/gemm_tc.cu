@@ -1028,9 +1028,10 @@ namespace wb {
 //   otherwise    : NS = 4, two store boxes + (EPI 2, 10) T2_NL load boxes (R / d prefetch)    (128 + 32..80 KB)
 // The epilogue moves its global traffic with TMA (coalesced 64-byte row segments) instead of one 16-byte access per
 // lane per row, which was measured to cost more than the MMAs themselves (profiles/r01_*: 448 vs 183 us).
-constexpr int T2_NL = 3, T2_NSB = 2;
+constexpr int T2_NL = 4, T2_NSB = 2;   // T2_NL = max load boxes per warp (barrier slots); t2_nl(epi) are used
 constexpr int T2_EBOX = 2048, T2_ECOLS = 16;
-__host__ __device__ constexpr int t2_nbuf(int epi) { return (epi == 2 || epi == 3 || epi == 10) ? T2_NSB + T2_NL : T2_NSB; }
+__host__ __device__ constexpr int t2_nl(int epi) { return epi == 10 ? 4 : 3; }   // EPI 10 (M = 512, K = 256) has the most epilogue per MMA
+__host__ __device__ constexpr int t2_nbuf(int epi) { return (epi == 2 || epi == 3 || epi == 10) ? T2_NSB + t2_nl(epi) : T2_NSB; }
 __host__ __device__ constexpr int t2_stages(int pro, int epi) { return (pro == 0 && epi == 0) ? 6 : 4; }
 __host__ __device__ constexpr int t2_scsh_bytes(int pro) { return pro >= 2 ? 2 * TC_MAXK * 4 : 0; }
 constexpr int T2_BAR_BYTES = 512;
@@ -1269,6 +1270,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     // prefetched T2_NL passes ahead, across tile boundaries), so every global access of the epilogue is a full
     // 64-byte row segment issued by the TMA unit rather than 32 scattered 16-byte accesses per warp instruction.
     constexpr bool HAS_LD = (EPI == 2 || EPI == 3 || EPI == 10);
+    constexpr int NLB = t2_nl(EPI);   // load boxes in flight per warp
     const int q = warp & 3;
     const int chalf = warp >> 2;
     const EpiP& e = p.ep;
@@ -1286,7 +1288,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
         decode(p_tile, po0, pt0, pn);
         const int pc0 = chalf * (TC_BN / 2) + T2_ECOLS * p_j;
         if (p_j < (TC_BN / 2) / T2_ECOLS && pt0 + pc0 < p.T) {
-          const int b_ = (int)(li % T2_NL);
+          const int b_ = (int)(li % NLB);
           if (lane == 0) {
             mbar_expect_tx(bar_ld(warp, b_), T2_EBOX);
             tma_load_3d(sbox_u + (T2_NSB + b_) * T2_EBOX, &map_r, bar_ld(warp, b_), pt0 + pc0, po0 + q * 32, pn);
@@ -1301,7 +1303,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     };
     if (ld_on) {
 #pragma unroll 1
-      for (int b_ = 0; b_ < T2_NL; ++b_) issue_next();
+      for (int b_ = 0; b_ < NLB; ++b_) issue_next();
     }
     uint32_t ti = 0;
     for (int tile = cluster_id; tile < P.n_tiles; tile += n_clusters, ++ti) {
@@ -1345,8 +1347,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
         for (int g = 0; g < 4; ++g) gop[g] = make_float4(0.f, 0.f, 0.f, 0.f);
         if constexpr (HAS_LD) {
           if (ld_on) {
-            const int b_ = (int)(lc % T2_NL);
-            mbar_wait(bar_ld(warp, b_), (lc / T2_NL) & 1);
+            const int b_ = (int)(lc % NLB);
+            mbar_wait(bar_ld(warp, b_), (lc / NLB) & 1);
             const uint8_t* lb = sbox + (T2_NSB + b_) * T2_EBOX + lrow;
 #pragma unroll
             for (int g = 0; g < 4; ++g) gop[g] = *reinterpret_cast<const float4*>(lb + (((uint32_t)g ^ lsw) << 4));

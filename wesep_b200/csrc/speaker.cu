@@ -59,7 +59,6 @@ __global__ void __launch_bounds__(256) bn_act_pool_fwd_kernel(WesepBnActPoolFwdA
 __global__ void __launch_bounds__(256) bn_act_pool_bwd_kernel(WesepBnActPoolBwdArgs a) {
   __shared__ float red[3 * 32];
   const int Tp = a.pool == 3 ? a.T / 3 : a.T;
-  const int tp = blockIdx.x * 256 + threadIdx.x;
   const int64_t row = blockIdx.y;
   const int c = (int)(row % a.C);
   const float sc = __ldg(a.scale + c), sh = __ldg(a.shift + c), al = __ldg(a.alpha);
@@ -68,13 +67,18 @@ __global__ void __launch_bounds__(256) bn_act_pool_bwd_kernel(WesepBnActPoolBwdA
   const float* r = a.res ? a.res + row * a.ldr : nullptr;
   float* gv = a.gv + row * a.ldgv;
   float s_g = 0.f, s_gx = 0.f, s_al = 0.f;
-  if (tp < Tp) {
+  // one CTA sweeps a whole slice of the row (gridDim.x slices): the block reduction + fp64 atomics are paid once per
+  // slice instead of once per 256 pooled frames
+  const int per = (Tp + gridDim.x - 1) / gridDim.x;
+  const int tp_end = min(Tp, (int)(blockIdx.x + 1) * per);
+  for (int tp = blockIdx.x * per + threadIdx.x; tp < tp_end; tp += 256) {
     const float g = __ldg(a.gy + row * a.ldgy + tp);
-    float v[3], best = -INFINITY;
+    float v[3], xs[3], best = -INFINITY;
     int arg = 0;
     for (int j = 0; j < a.pool; ++j) {
       const int t = a.pool * tp + j;
-      v[j] = fmaf(sc, __ldg(x + t), sh);
+      xs[j] = __ldg(x + t);
+      v[j] = fmaf(sc, xs[j], sh);
       if (r) v[j] += __ldg(r + t);
       const float s = prelu_f(v[j], al);
       if (s > best || s != s) { best = s; arg = j; }
@@ -86,7 +90,7 @@ __global__ void __launch_bounds__(256) bn_act_pool_bwd_kernel(WesepBnActPoolBwdA
         out = g * (v[j] > 0.f ? 1.f : al);
         s_al += v[j] > 0.f ? 0.f : g * v[j];
         s_g += out;
-        s_gx = fmaf(out, (__ldg(x + t) - mean) * rstd, s_gx);
+        s_gx = fmaf(out, (xs[j] - mean) * rstd, s_gx);
       }
       gv[t] = out;
     }
@@ -198,7 +202,8 @@ extern "C" int wesep_b200_bn_act_pool_fwd(const WesepBnActPoolFwdArgs* a, void* 
 extern "C" int wesep_b200_bn_act_pool_bwd(const WesepBnActPoolBwdArgs* a, void* stream) {
   if (a->n <= 0 || a->C <= 0 || a->T <= 0 || !(a->pool == 1 || a->pool == 3)) return fail(-1, "bn_act_pool_bwd: bad shape");
   const int Tp = a->pool == 3 ? a->T / 3 : a->T;
-  bn_act_pool_bwd_kernel<<<dim3(cdiv(Tp, 256), a->n * a->C), 256, 0, (cudaStream_t)stream>>>(*a);
+  const int slices = cdiv(Tp, 2048);   // <= 8 passes of 256 pooled frames per CTA
+  bn_act_pool_bwd_kernel<<<dim3(slices, a->n * a->C), 256, 0, (cudaStream_t)stream>>>(*a);
   WB_LAUNCH_CHECK("bn_act_pool_bwd");
   return 0;
 }

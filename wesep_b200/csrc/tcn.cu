@@ -21,6 +21,7 @@ struct StFwdP {
   const float* a1; const float* g1; const float* be1;
   const float* wd; const float* bd; const float* a2;
   const double* stats1; double* stats2; double count;
+  int tt;   // time steps per CTA of the vectorised kernels (multiple of 256; set by launch_dw_fwd)
 };
 
 __global__ void __launch_bounds__(ST_THREADS) tcn_dw_fwd_generic_kernel(const StFwdP p) {
@@ -80,6 +81,7 @@ struct StBwdP {
   const double* rowacc;          // [n][8]: [2]=P1 [3]=P2 [4]=P3
   float* dg1; float* dbe1; float* dwd; float* dbd; float* da1;  // += [H],[H],[H][3],[H],[1]
   float* sdu;                    // += [n][H] sum_t du
+  int tt;                        // time steps per CTA of the vectorised kernels (multiple of 256; set by launch_dw_bwd)
 };
 
 __global__ void __launch_bounds__(ST_THREADS) tcn_dw_bwd_generic_kernel(const StBwdP p) {
@@ -247,7 +249,7 @@ __device__ __forceinline__ void dw_fwd_body(const StFwdP& p, int sub, int t0, in
   const float* urow = p.u + ((int64_t)n * p.H + c) * p.ld;
   float* drow = p.d + ((int64_t)n * p.H + c) * p.ld;
 #pragma unroll 2
-  for (int i = 4 * sub; i < ST_TT; i += 256) {
+  for (int i = 4 * sub; i < p.tt; i += 256) {
     const int t = t0 + i;
     if (t >= p.T) break;
     float L[4], C[4], R[4], o[4];
@@ -282,7 +284,7 @@ template <int DM>
 __global__ void __launch_bounds__(ST_THREADS) tcn_dw_fwd_kernel(const StFwdP p) {
   __shared__ float red[2 * 32];
   const int tid = threadIdx.x, sub = tid & 63, chl = tid >> 6;
-  const int t0 = blockIdx.x * ST_TT, c = blockIdx.y * ST_CH + chl, n = blockIdx.z;
+  const int t0 = blockIdx.x * p.tt, c = blockIdx.y * ST_CH + chl, n = blockIdx.z;
   float s = 0.f, q = 0.f;
   if (c < p.H) {
     if (__ldg(p.a1) <= 1.f && __ldg(p.a2) <= 1.f) dw_fwd_body<DM, true>(p, sub, t0, c, n, s, q);
@@ -316,7 +318,7 @@ __device__ __forceinline__ void dw_bwd_body(const StBwdP& p, int sub, int t0, in
   // dy = r*(g1*dz - m1 - yhat1*m2) = cA*dz + cB*y1 + cC with y1 = prelu(u)
   const float cA = r * gm, cB = -r * r * m2, cC = -r * m1 + r * r * m2 * mu;
 #pragma unroll 2
-  for (int i = 4 * sub; i < ST_TTB; i += 256) {
+  for (int i = 4 * sub; i < p.tt; i += 256) {
     const int t = t0 + i;
     if (t >= p.T) break;
     float dL[4], dC[4], dR[4], uu[4], o[4];
@@ -376,7 +378,7 @@ __global__ void __launch_bounds__(ST_THREADS) tcn_dw_bwd_kernel(const StBwdP p) 
   __shared__ float red[32];
   __shared__ float chred[ST_CH][2][8];
   const int tid = threadIdx.x, sub = tid & 63, chl = tid >> 6, lane = tid & 31;
-  const int t0 = blockIdx.x * ST_TTB, c = blockIdx.y * ST_CH + chl, n = blockIdx.z;
+  const int t0 = blockIdx.x * p.tt, c = blockIdx.y * ST_CH + chl, n = blockIdx.z;
   float acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
@@ -408,8 +410,20 @@ __global__ void __launch_bounds__(ST_THREADS) tcn_dw_bwd_kernel(const StBwdP p) 
   }
 }
 
-static int launch_dw_fwd(const StFwdP& p, cudaStream_t st) {
-  dim3 grid(cdiv(p.T, ST_TT), cdiv(p.H, ST_CH), p.n);
+// Time steps per CTA of the vectorised stencils: a CTA's fixed cost (parameter / statistics loads up front, seven
+// warp reductions + atomics at the end) was ~40 % of its lifetime with 1024-step tiles, so rows are cut into as few
+// equal pieces as keep the piece <= 3584 steps (T = 6399 -> 2 x 3200).
+static int stencil_tile(int T) {
+  const int pieces = cdiv(T, 3584);
+  return cdiv(cdiv(T, pieces), 256) * 256;
+}
+
+static int launch_dw_fwd(const StFwdP& pin, cudaStream_t st) {
+  StFwdP p = pin;
+  p.tt = ST_TT;
+  const int dm_ = (p.dil % 4 == 0) ? 0 : (p.dil <= 3 ? p.dil : -1);
+  if (dm_ >= 0) p.tt = stencil_tile(p.T);
+  dim3 grid(cdiv(p.T, p.tt), cdiv(p.H, ST_CH), p.n);
   const int dm = (p.dil % 4 == 0) ? 0 : (p.dil <= 3 ? p.dil : -1);
   if (dm < 0) {
     size_t smem = (size_t)ST_CH * (ST_TT + 2 * p.dil) * sizeof(float);
@@ -428,8 +442,12 @@ static int launch_dw_fwd(const StFwdP& p, cudaStream_t st) {
   return 0;
 }
 
-static int launch_dw_bwd(const StBwdP& p, cudaStream_t st) {
-  dim3 grid(cdiv(p.T, ST_TTB), cdiv(p.H, ST_CH), p.n);
+static int launch_dw_bwd(const StBwdP& pin, cudaStream_t st) {
+  StBwdP p = pin;
+  p.tt = ST_TTB;
+  const int dm_ = (p.dil % 4 == 0) ? 0 : (p.dil <= 3 ? p.dil : -1);
+  if (dm_ >= 0) p.tt = stencil_tile(p.T);
+  dim3 grid(cdiv(p.T, p.tt), cdiv(p.H, ST_CH), p.n);
   const int dm = (p.dil % 4 == 0) ? 0 : (p.dil <= 3 ? p.dil : -1);
   if (dm < 0) {
     size_t smem = (size_t)ST_CH * (2 * (ST_TTB + 2 * p.dil) + ST_TTB) * sizeof(float);
