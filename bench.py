@@ -28,6 +28,8 @@ SPEX_ARGS = dict(B=256, H=512, L=20, N=256, P=3, R=4, X=8, spk_emb_dim=256, acti
                  encoder_type="Multi", decoder_type="Multi", joint_training=True, multi_task=True, spksInTrain=251)
 T_SAMPLES = 64000
 METRIC = "utterances/sec Spex+ train step (4s@16kHz)"
+# dram__bytes_read.sum + dram__bytes_write.sum of the K2 GEMM at n=32 (ncu --set full, profiles/r01_ncu_full_tcn_block_n32.md)
+K2_DRAM_BYTES_PER_LAUNCH = 579.5e6
 
 
 def peaks():
@@ -268,17 +270,19 @@ def run_ours(args, rank, world, local):
         config=dict(workload="Spex+ (ConvTasNet, examples/librimix/tse/v2/confs/spexplus.yaml) full train step, "
                              "4s@16kHz, %d model rows per GPU" % n,
                     rows_per_gpu=n, global_rows=n * world, samples=T_SAMPLES, parallelism="dp%d" % world,
-                    gemm_mode="3xTF32 split (fp32-grade); tcgen05.mma kind::tf32 + TMA + TMEM for the TCN GEMMs, mma.sync elsewhere", l2="inputs and activations >> L2 (126 MB)",
+                    gemm_mode="3xTF32 split (fp32-grade); tcgen05.mma kind::tf32 cta_group::2 + TMA + TMEM GEMMs, mma.sync for odd shapes", l2="inputs and activations >> L2 (126 MB)",
                     loss="0.8/0.1/0.1 SI-SDR + 0.5 CE", optimizer="per-tensor clip 5.0 + Adam(wd 1e-4), exp-decay lr"),
         e2e=dict(value=e2e, unit="utterances/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
                  ms_per_step=ms_e2e / args.steps),
         gpu_launches=launches, clocks=clocks, loss=loss_res, loss_e2e=loss_e2e,
-        roofline=dict(kernel="gemm_wx_tc_kernel<0,0> (tcgen05; K2 shape 256->512, n=%d, K=6399)" % n, bound="tensor",
-                      achieved=dom["exec_tflops"], peak=pk["tf_burst"], unit="TFLOP/s",
-                      frac=dom["exec_tflops"] / pk["tf_burst"], traffic=None,
-                      note="executed = 3x algorithmic flops (3xTF32); peak = measured bf16 burst (%s); TF32 "
-                           "tensor peak is half of it" % pk["src"], algorithmic_tflops=dom["alg_tflops"],
-                      alg_gbs=dom["alg_gbs"]),
+        roofline=dict(kernel="gemm_wx_tc2_kernel<0,0,6> (tcgen05 cta_group::2; K2 shape 256->512, n=%d, K=6399)" % n,
+                      bound="tensor", achieved=dom["exec_tflops"], peak=pk["tf_burst"], unit="TFLOP/s",
+                      frac=dom["exec_tflops"] / pk["tf_burst"], frac_of_tf32_peak=dom["exec_tflops"] / (0.5 * pk["tf_burst"]),
+                      traffic=K2_DRAM_BYTES_PER_LAUNCH if n == 32 else None,
+                      note="executed = 3x algorithmic flops (3xTF32 split, fp32-grade); peak = measured bf16 burst (%s); "
+                           "kind::tf32 runs at half the bf16 rate, so frac_of_tf32_peak is the pipe utilisation; traffic = "
+                           "dram read+write of this kernel per launch from profiles/r01_ncu_full_tcn_block_n32.md" % pk["src"],
+                      algorithmic_tflops=dom["alg_tflops"], alg_gbs=dom["alg_gbs"]),
         roofline_tcn_block=dict(bound="hbm", peak=pk["hbm"], unit="GB/s", fwd=roof["tcn_block_fwd"],
                                 bwd=roof["tcn_block_bwd"],
                                 note="algorithmic bytes per row per block: fwd (2B+4H)*K*4 = 65.5 MB, bwd (3B+8H)*K*4 = "

@@ -31,7 +31,7 @@ def launches():
     S = sum(v[1] for v in tot.values())
     ours = sum(v[1] for k, v in tot.items() if "wb::" in k)
     with open(os.path.join(out, f"{tag}_launch_list_summary.md"), "w") as f:
-        f.write(f"# {tag}: ncu launch list of `python bench.py --steps 1 --warmup 3 --rows 32` (4 train steps + the kernel micro-timings)\n\n")
+        f.write(f"# {tag}: ncu launch list of `python bench.py --steps 1 --warmup 3 --rows 32` (window: --launch-skip 3660 -c 1300 = the timed step after the 3 warm-up steps)\n\n")
         f.write("`ncu --metrics gpu__time_duration.sum --clock-control none` — per-launch times are cold-cache and serialised: read SHARES.\n\n")
         f.write(f"total kernel time {S / 1e3:.1f} ms over {sum(v[0] for v in tot.values())} launches; wesep_b200 kernels = {ours / S * 100:.1f} % of it\n\n")
         f.write("| share | avg us | launches | kernel |\n|---:|---:|---:|---|\n")
