@@ -43,7 +43,10 @@ int wesep_b200_set_gemm_mode(int mode);
 int wesep_b200_set_gemm_backend(int backend);
 /* tcgen05 debug flags. bit 0: also store the explicitly truncated "hi" operand tile (default off: the tensor core
  * ignores the 13 low mantissa bits of tf32 inputs — measured identical results — so the raw tile serves as hi).
- * bit 1: disable the 2-CTA (cta_group::2) GEMM variant.  bits 2-3: transform-warp groups (0 = default 2, 1 = one group, 2 = two, 3 = four; clamped so it divides the ring depth). */
+ * bit 1: disable the 2-CTA (cta_group::2) GEMM variants.  bits 2-3: transform-warp groups (0 = default 2, 1 = one group, 2 = two, 3 = four; clamped so it divides the ring depth).
+ * bits 4-7: timing experiments on the 2-CTA conv GEMM (16 no epilogue loads, 32 no epilogue stores, 64 no operand
+ * transform, 128 single store box) — results are WRONG with 16/32/64 set.  bit 8 (256): force the balanced stream-K
+ * split in the weight-gradient GEMMs.  bit 9 (512): weight-gradient GEMMs on the 1-CTA kernel. */
 int wesep_b200_set_tc_flags(int flags);
 /* Workspace bytes the tcgen05 GEMM needs for an [M x Kd] weight (split hi/lo copies). */
 int64_t wesep_b200_gemm_ws_bytes(int M, int Kd);
