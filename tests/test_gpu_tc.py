@@ -143,3 +143,39 @@ def test_conv1x1_relu_mask_and_channel_stats_epilogues(backend, n, Kd, M, T):
     check("y", y0, v, 1e-5)
     check("ch_sum", chs[:, 0], v.sum((0, 2)), 1e-4)
     check("ch_sumsq", chs[:, 1], (v * v).sum((0, 2)), 1e-5)
+
+
+def test_tcn_block_direct_param_grads_match_autograd():
+    """ops.direct_param_grads(): the block's kernels accumulate into the live .grad buffers (what train_step uses);
+    the result must equal the ordinary autograd path (temporary gradients + AccumulateGrad), including accumulation
+    on top of a non-zero .grad."""
+    from wesep_b200 import ops, synth
+    from wesep_b200.modules.tasnet.convs import Conv1DBlock
+    torch.manual_seed(0)
+    blk = Conv1DBlock(256, 512, 3, 4, "gLN", False, False)
+    synth.fill_state_dict_(blk.state_dict(), seed=3)
+    blk = blk.to(DEV)
+    x = ops.new_act(2, 256, 1500, DEV)
+    x.copy_(rnd(2, 256, 1500, seed=1))
+    g = ops.new_act(2, 256, 1500, DEV)
+    g.copy_(rnd(2, 256, 1500, seed=2))
+    params = list(blk.parameters())
+    base = [0.01 * torch.randn_like(p) for p in params]
+
+    def run(direct):
+        for p, b in zip(params, base):
+            p.grad = b.clone()
+        xx = x.clone().requires_grad_(True)
+        y = blk(xx)
+        if direct:
+            with ops.direct_param_grads():
+                y.backward(g)
+        else:
+            y.backward(g)
+        return [p.grad.clone() for p in params], xx.grad.clone()
+
+    ref_g, ref_dx = run(False)
+    got_g, got_dx = run(True)
+    check("dx", got_dx, ref_dx, 1e-6)
+    for (name, _), a, b in zip(blk.named_parameters(), got_g, ref_g):
+        check(name, a, b, 2e-5)

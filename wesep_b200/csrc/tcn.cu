@@ -630,8 +630,12 @@ extern "C" int wesep_b200_tcn_block_fwd(const WesepTcnFwdArgs* ap, void* stream)
   cudaStream_t st = (cudaStream_t)stream;
   if (int rc = check_tcn(a)) return rc;
   const double count = (double)a.H * (double)a.T;
-  WB_CUDA(cudaMemsetAsync(a.stats1, 0, sizeof(double) * 2 * a.n, st));
-  WB_CUDA(cudaMemsetAsync(a.stats2, 0, sizeof(double) * 2 * a.n, st));
+  if (a.stats2 == a.stats1 + 2 * a.n) {   // adjacent (the Python host allocates them as one tensor): one memset
+    WB_CUDA(cudaMemsetAsync(a.stats1, 0, sizeof(double) * 4 * a.n, st));
+  } else {
+    WB_CUDA(cudaMemsetAsync(a.stats1, 0, sizeof(double) * 2 * a.n, st));
+    WB_CUDA(cudaMemsetAsync(a.stats2, 0, sizeof(double) * 2 * a.n, st));
+  }
   if (a.aux) {
     int warps = a.n * a.H;
     fuse_rowbias_kernel<<<cdiv((int64_t)warps * 32, 256), 256, 0, st>>>(a.W1, a.ldw1, a.B, a.E, a.H, a.n, a.aux, a.row_bias);
@@ -671,9 +675,17 @@ extern "C" int wesep_b200_tcn_block_bwd(const WesepTcnBwdArgs* bp, void* stream)
   cudaStream_t st = (cudaStream_t)stream;
   if (int rc = check_tcn(a)) return rc;
   const double count = (double)a.H * (double)a.T;
-  WB_CUDA(cudaMemsetAsync(b.Gn, 0, sizeof(float) * (size_t)a.n * a.B * a.H, st));
-  WB_CUDA(cudaMemsetAsync(b.sdu, 0, sizeof(float) * (size_t)a.n * a.H, st));
-  WB_CUDA(cudaMemsetAsync(b.rowsc, 0, sizeof(double) * 8 * a.n, st));
+  // scratch the block zeroes itself: [rowsc | sdu | sg | Gn]; when the caller laid them out back to back, one memset
+  const bool packed = b.sdu == reinterpret_cast<float*>(b.rowsc + 8 * a.n) && b.sg == b.sdu + (size_t)a.n * a.H &&
+                      b.Gn == b.sg + (size_t)a.n * a.B;
+  if (packed) {
+    WB_CUDA(cudaMemsetAsync(b.rowsc, 0, sizeof(double) * 8 * a.n + sizeof(float) * ((size_t)a.n * a.H + (size_t)a.n * a.B +
+                                                                                     (size_t)a.n * a.B * a.H), st));
+  } else {
+    WB_CUDA(cudaMemsetAsync(b.Gn, 0, sizeof(float) * (size_t)a.n * a.B * a.H, st));
+    WB_CUDA(cudaMemsetAsync(b.sdu, 0, sizeof(float) * (size_t)a.n * a.H, st));
+    WB_CUDA(cudaMemsetAsync(b.rowsc, 0, sizeof(double) * 8 * a.n, st));
+  }
   {  // Gn[n][o][c] = sum_t g[o][t] * prelu(d[c][t], a2)  and  sg[n][o] = sum_t g[o][t]
     GemmDwP p{};
     p.n = a.n; p.M = a.B; p.N = a.H; p.T = a.T;
@@ -682,7 +694,7 @@ extern "C" int wesep_b200_tcn_block_bwd(const WesepTcnBwdArgs* bp, void* stream)
     p.C = b.Gn; p.ldc = a.H; p.per_row = 1;
     p.xb = XformP{a.a2, nullptr, nullptr, nullptr, 1.0, 0.f};
     if (gemm_dw_uses_tc(p, 1)) {   // the tcgen05 kernel sums the rows of g while it splits the operand tiles
-      WB_CUDA(cudaMemsetAsync(b.sg, 0, sizeof(float) * (size_t)a.n * a.B, st));
+      if (!packed) WB_CUDA(cudaMemsetAsync(b.sg, 0, sizeof(float) * (size_t)a.n * a.B, st));
       p.a_rowsum = b.sg;
     } else {
       int rows = a.n * a.B;

@@ -159,6 +159,40 @@ def frames_raw(sig, J, K, hop):
 
 
 # --------------------------------------------------------------------------- fused TCN block
+# When set (wesep_b200.utils.executor.train_step does, around loss.backward()), TCNBlockFn.backward lets its kernels
+# accumulate parameter gradients straight into the existing `.grad` buffers (the optimizer's flat arena) and returns None
+# for them: no temporary gradient, no zero-fill, and no per-parameter `grad += new` kernel from autograd's AccumulateGrad
+# (12 parameters x 32 blocks per step).  Off by default so torch.autograd.grad(...) keeps returning the gradients.
+DIRECT_PARAM_GRADS = False
+
+
+class direct_param_grads:
+    """Context manager enabling in-place accumulation into existing `.grad` buffers during backward."""
+
+    def __enter__(self):
+        global DIRECT_PARAM_GRADS
+        self.prev = DIRECT_PARAM_GRADS
+        DIRECT_PARAM_GRADS = True
+        return self
+
+    def __exit__(self, *exc):
+        global DIRECT_PARAM_GRADS
+        DIRECT_PARAM_GRADS = self.prev
+        return False
+
+
+def _grad_targets(params):
+    """Flat fp32 views of the params' existing .grad buffers, or None if any of them cannot take direct accumulation."""
+    outs = []
+    for p in params:
+        g = getattr(p, "grad", None)
+        if (g is None or not p.is_leaf or g.dtype != torch.float32 or not g.is_contiguous() or g.device != p.device
+                or g.shape != p.shape or g.data_ptr() % 16):
+            return None
+        outs.append(g.view(-1))
+    return outs
+
+
 class TCNBlockFn(torch.autograd.Function):
     """Conv1DBlock / Conv1DBlock4Fuse (wesep/modules/tasnet/convs.py:43-160) as one fused op."""
 
@@ -194,6 +228,7 @@ class TCNBlockFn(torch.autograd.Function):
         ctx.dil = int(dil)
         ctx.has_aux = aux is not None
         ctx.shapes = (W1.shape, W3.shape, None if aux is None else aux.shape)
+        ctx.param_refs = (W1, b1, a1, g1, be1, wd, bd, a2, g2, be2, W3, b3)
         ctx.save_for_backward(x, auxc, W1c, W3c, u, d, stats, *[P[k] for k in ("b1", "a1", "g1", "be1", "wd", "bd", "a2",
                                                                             "g2", "be2", "b3")])
         return out
@@ -214,14 +249,21 @@ class TCNBlockFn(torch.autograd.Function):
         dd = new_act(n, H, T, dev)
         du = new_act(n, H, T, dev)
         sizes = [H * (B + E), H, 1, H, H, 3 * H, H, 1, H, H, B * H, B]
-        flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
-        parts = list(torch.split(flat, sizes))
+        direct = _grad_targets(ctx.param_refs) if DIRECT_PARAM_GRADS else None
+        if direct is not None and [t.numel() for t in direct] == sizes:
+            parts = direct                       # kernels accumulate (+=) into the live .grad buffers
+        else:
+            direct = None
+            flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+            parts = list(torch.split(flat, sizes))
         dW1, db1, da1, dg1, dbe1, dwd, dbd, da2, dg2, dbe2, dW3, db3 = parts
         daux = torch.empty((n, E), dtype=torch.float32, device=dev) if E else None
-        Gn = torch.empty((n, B, H), dtype=torch.float32, device=dev)
-        sg = torch.empty((n, B), dtype=torch.float32, device=dev)
-        sdu = torch.empty((n, H), dtype=torch.float32, device=dev)
-        rowsc = torch.empty((n, 8), dtype=torch.float64, device=dev)
+        # scratch the kernels zero themselves: one buffer [rowsc | sdu | sg | Gn] so the C side needs ONE memset
+        scratch = torch.empty(16 * n + n * H + n * B + n * B * H, dtype=torch.float32, device=dev)
+        rowsc = scratch[:16 * n].view(torch.float64).view(n, 8)
+        sdu = scratch[16 * n:16 * n + n * H].view(n, H)
+        sg = scratch[16 * n + n * H:16 * n + n * H + n * B].view(n, B)
+        Gn = scratch[16 * n + n * H + n * B:].view(n, B, H)
         fa = _args("WesepTcnFwdArgs", n=n, B=B, H=H, T=T, dil=ctx.dil, E=E, ld=x.stride(1), x=x, aux=auxc, W1=W1c,
                    ldw1=W1c.stride(0), b1=b1, a1=a1, g1=g1, be1=be1, wd=wd, bd=bd, a2=a2, g2=g2, be2=be2, W3=W3c,
                    ldw3=W3c.stride(0), b3=b3, u=u, d=d, out=None, stats1=stats[0], stats2=stats[1], row_bias=None)
@@ -236,6 +278,8 @@ class TCNBlockFn(torch.autograd.Function):
             DEBUG_STASH.update(dd=dd, du=du, Gn=Gn, sg=sg, sdu=sdu, rowsc=rowsc, u=u, d=d, stats=stats)
         W1s, W3s, auxs = ctx.shapes
         g_aux = None if daux is None else daux.reshape(auxs)
+        if direct is not None:
+            return (dx, g_aux) + (None,) * 13
         return (dx, g_aux, dW1.view(W1s), db1, da1, dg1.view(H, 1), dbe1.view(H, 1), dwd.view(H, 1, 3), dbd, da2,
                 dg2.view(H, 1), dbe2.view(H, 1), dW3.view(W3s), db3, None)
 

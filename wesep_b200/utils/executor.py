@@ -37,7 +37,8 @@ def train_step(model, batch, optimizer, reducer=None, loss_posi=((0, 1, 2), (3,)
     optimizer.zero_grad()
     outputs = model(features, enroll)
     loss, _ = compute_loss(outputs, targets, spk_label, loss_posi, loss_weight, multi_task)
-    loss.backward()
+    with ops.direct_param_grads():  # TCN-block kernels accumulate straight into the optimizer's gradient arena
+        loss.backward()
     if reducer is not None:
         reducer.all_reduce()
         optimizer.grad_scale = reducer.grad_scale
