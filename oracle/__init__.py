@@ -6,6 +6,10 @@ wenet-e2e/wesep target-speaker-extraction *train step* (Spex+/ConvTasNet forward
 SI-SDR + CE loss, backward via torch autograd of the restated forward, per-tensor
 gradient clip, Adam).  Every function cites the reference file:line it follows.
 
+``oracle/bsrnn.py`` restates the pBSRNN forward (STFT/iSTFT, band split, BLSTM
+recurrence, mask head) the same way; it is pinned by ``tests/golden/bsrnn_*.npz`` (``make_golden_bsrnn.py``) and
+is groundwork for the next round's CUDA path — nothing in ``wesep_b200`` uses it.
+
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
 ``--impl reference`` legs may import this package — as the checker or the timed CPU
 baseline, never as part of the product path.  ``wesep_b200`` must not import it.

@@ -248,12 +248,10 @@ __device__ __forceinline__ void dw_fwd_body(const StFwdP& p, int sub, int t0, in
   const float v0 = w0 * sc, v1 = w1 * sc, v2 = w2 * sc, bdp = fmaf(sh, w0 + w1 + w2, bd);
   const float* urow = p.u + ((int64_t)n * p.H + c) * p.ld;
   float* drow = p.d + ((int64_t)n * p.H + c) * p.ld;
-#pragma unroll 2
-  for (int i = 4 * sub; i < p.tt; i += 256) {
-    const int t = t0 + i;
-    if (t >= p.T) break;
-    float L[4], C[4], R[4], o[4];
-    taps4g<DM>(urow, t, p.T, dil, 0.f, L, C, R);
+  // two vectors per pass, all six tap loads issued before the first use: the kernel is DRAM-latency bound, so the bytes
+  // in flight per thread (not the instruction count) set its speed
+  auto emit = [&](int t, const float (&L)[4], const float (&C)[4], const float (&R)[4]) {
+    float o[4];
     const bool interior = (t - dil >= 0) && (t + dil + 3 < p.T);
     if (interior) {
 #pragma unroll
@@ -277,6 +275,17 @@ __device__ __forceinline__ void dw_fwd_body(const StFwdP& p, int sub, int t0, in
       }
     }
     *reinterpret_cast<float4*>(drow + t) = make_float4(o[0], o[1], o[2], o[3]);
+  };
+#pragma unroll 1
+  for (int i = 4 * sub; i < p.tt; i += 512) {
+    const int ta = t0 + i, tb = ta + 256;
+    if (ta >= p.T) break;
+    const bool has_b = (i + 256 < p.tt) && (tb < p.T);
+    float La[4], Ca[4], Ra[4], Lb[4], Cb[4], Rb[4];
+    taps4g<DM>(urow, ta, p.T, dil, 0.f, La, Ca, Ra);
+    if (has_b) taps4g<DM>(urow, tb, p.T, dil, 0.f, Lb, Cb, Rb);
+    emit(ta, La, Ca, Ra);
+    if (has_b) emit(tb, Lb, Cb, Rb);
   }
 }
 
