@@ -215,13 +215,20 @@ def run_ours(args, rank, world, local):
             dist.barrier()
             torch.cuda.synchronize()
 
+    graphed = None
+    if args.cuda_graph:
+        if world > 1:
+            raise SystemExit("--cuda-graph is single-process (the gradient all-reduce is not captured)")
+        from wesep_b200.utils.executor import GraphedTrainStep
+        graphed = GraphedTrainStep(model, opt, resident, warmup=3)   # 3 eager steps, then ONE capture of the whole step
+
     def timed_region(batch, read_loss):
         it = [0]
 
         def one():
             sched.step(it[0])
             it[0] += 1
-            loss = train_step(model, batch, opt, reducer)
+            loss = graphed(batch) if graphed is not None else train_step(model, batch, opt, reducer)
             if read_loss:
                 return loss.item()                              # D2H of the step's result
             return loss
@@ -238,6 +245,8 @@ def run_ours(args, rank, world, local):
         barrier()
         ms = s.elapsed_time(e)
         launches = _lib.launch_count() - l0
+        if graphed is not None:                                 # replays do not pass through the host-side counter
+            launches = graphed.launches_per_step * args.steps
         if world > 1:
             tt = torch.tensor([ms], device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -271,7 +280,8 @@ def run_ours(args, rank, world, local):
                              "4s@16kHz, %d model rows per GPU" % n,
                     rows_per_gpu=n, global_rows=n * world, samples=T_SAMPLES, parallelism="dp%d" % world,
                     gemm_mode="3xTF32 split (fp32-grade); tcgen05.mma kind::tf32 cta_group::2 + TMA + TMEM GEMMs, mma.sync for odd shapes", l2="inputs and activations >> L2 (126 MB)",
-                    loss="0.8/0.1/0.1 SI-SDR + 0.5 CE", optimizer="per-tensor clip 5.0 + Adam(wd 1e-4), exp-decay lr"),
+                    loss="0.8/0.1/0.1 SI-SDR + 0.5 CE", optimizer="per-tensor clip 5.0 + Adam(wd 1e-4), exp-decay lr",
+                    launch="one CUDA-graph replay per step" if graphed is not None else "eager (one launch per kernel)"),
         e2e=dict(value=e2e, unit="utterances/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
                  ms_per_step=ms_e2e / args.steps),
         gpu_launches=launches, clocks=clocks, loss=loss_res, loss_e2e=loss_e2e,
@@ -300,6 +310,8 @@ def main():
     ap.add_argument("--rows", type=int, default=32, help="model rows (utterances) per GPU per step")
     ap.add_argument("--ref-rows", type=int, default=1, help="rows per step of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cuda-graph", action="store_true",
+                    help="capture the whole train step in a CUDA graph and time replays (single GPU)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

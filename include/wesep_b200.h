@@ -105,6 +105,8 @@ typedef struct {
   float clip;               /* <= 0 disables clipping */
   float lr, beta1, beta2, eps, weight_decay;
   int step;                 /* 1-based */
+  const float* dyn;         /* optional device [3] = {lr, 1 - beta1^step, sqrt(1 - beta2^step)}: when given, these replace
+                               `lr` / `step` so that a CUDA graph of the train step can be replayed with a moving schedule */
 } WesepClipAdamArgs;
 int wesep_b200_clip_adam(const WesepClipAdamArgs* a, void* stream);
 

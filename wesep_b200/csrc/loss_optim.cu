@@ -119,7 +119,11 @@ __global__ void __launch_bounds__(256) opt_adam_kernel(WesepClipAdamArgs a, floa
     float coef = a.clip / (norm + 1e-6f);
     if (coef < 1.f) gs *= coef;
   }
-  const float step_size = a.lr / bc1;
+  if (a.dyn) {   // graph replay: schedule-dependent scalars live in device memory
+    bc1 = __ldg(a.dyn + 1);
+    bc2_sqrt = __ldg(a.dyn + 2);
+  }
+  const float step_size = (a.dyn ? __ldg(a.dyn) : a.lr) / bc1;
   for (int64_t j = off + tid * 4; j < end; j += 1024) {
     float4 g = *reinterpret_cast<const float4*>(a.grad + j);
     float4 p = *reinterpret_cast<const float4*>(a.param + j);

@@ -6,6 +6,9 @@ import torch
 from wesep_b200 import ops
 
 
+_LOSS_W = {}
+
+
 def compute_loss(outputs, targets, spk_label, loss_posi=((0, 1, 2), (3,)), loss_weight=((0.8, 0.1, 0.1), (0.5,)),
                  multi_task=True):
     """loss = sum_j w0[j] * SISDR(outputs[posi0[j]], targets) (+ w1[j] * CE(outputs[posi1[j]], spk_label))
@@ -16,7 +19,10 @@ def compute_loss(outputs, targets, spk_label, loss_posi=((0, 1, 2), (3,)), loss_
     L = ests[0].shape[-1]
     tgt = targets if targets.shape[-1] == L else targets[:, :L]
     losses, rows = ops.sisdr_losses(ests, tgt)
-    w = torch.tensor(list(loss_weight[0]), dtype=torch.float32, device=losses.device)
+    key = (tuple(float(v) for v in loss_weight[0]), losses.device)
+    w = _LOSS_W.get(key)
+    if w is None:       # cached: a pageable host->device copy per step would also forbid CUDA-graph capture
+        w = _LOSS_W[key] = torch.tensor(list(key[0]), dtype=torch.float32, device=losses.device)
     loss = (losses * w).sum()
     if multi_task and len(loss_posi) > 1:
         for j, p in enumerate(loss_posi[1]):
@@ -44,6 +50,58 @@ def train_step(model, batch, optimizer, reducer=None, loss_posi=((0, 1, 2), (3,)
         optimizer.grad_scale = reducer.grad_scale
     optimizer.step()
     return loss
+
+
+class GraphedTrainStep:
+    """The whole train step (zero_grad, forward, loss, backward, clip + Adam) captured ONCE in a CUDA graph and replayed:
+    ~840 kernel launches per step become one graph launch, removing the inter-kernel launch gaps (~5 % of the step) and
+    all per-step Python / ctypes work.  Single-process only (the gradient all-reduce stays outside a graph: use the eager
+    `train_step` with a reducer for N > 1).  Shapes are frozen at capture: every batch must match the example batch.
+
+        step = GraphedTrainStep(model, optimizer, example_batch)     # runs `warmup` eager steps on it, then captures
+        loss = step(batch)                                            # device tensor (static storage): read or copy it
+
+    The learning rate may change between calls (`param_groups[0]["lr"]`): the optimizer kernels read the schedule-dependent
+    scalars from device memory (`FusedClipAdam.enable_device_scalars`)."""
+
+    def __init__(self, model, optimizer, example_batch, loss_posi=((0, 1, 2), (3,)), loss_weight=((0.8, 0.1, 0.1), (0.5,)),
+                 multi_task=True, warmup=3):
+        self.model, self.opt = model, optimizer
+        self.cfg = (loss_posi, loss_weight, multi_task)
+        dev = next(model.parameters()).device
+        self.static = {k: v.to(dev).clone() for k, v in example_batch.items()}
+        optimizer.enable_device_scalars()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                      # warm-up off the default stream, as graph capture requires
+            for _ in range(warmup):
+                optimizer.push_scalars()
+                self._body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        l0 = ops._lib.launch_count()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._body()
+        self.launches_per_step = ops._lib.launch_count() - l0   # kernels of this library inside one replay
+
+    def _body(self):
+        loss_posi, loss_weight, multi_task = self.cfg
+        b = self.static
+        self.opt.zero_grad()
+        outputs = self.model(b["wav_mix"], b["spk_embeds"])
+        loss, _ = compute_loss(outputs, b["wav_targets"], b["spk_label"], loss_posi, loss_weight, multi_task)
+        with ops.direct_param_grads():
+            loss.backward()
+        self.opt.launch()
+        return loss
+
+    def __call__(self, batch):
+        for k, v in self.static.items():
+            v.copy_(batch[k], non_blocking=True)            # pinned host or device source
+        self.opt.push_scalars()
+        self.graph.replay()
+        return self.loss
 
 
 class Executor:

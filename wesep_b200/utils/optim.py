@@ -67,11 +67,51 @@ class FusedClipAdam:
         self.norms = torch.empty(len(a.params), dtype=torch.float32, device=dev)
         self.step_count = 0
         self.grad_scale = 1.0
+        self._dyn = None           # device [3] {lr, 1-b1^t, sqrt(1-b2^t)} once enable_device_scalars() was called
+        self._dyn_host = None
 
     def zero_grad(self, set_to_none=False):
         self.arena.zero_grad()
 
+    # ---- CUDA-graph support: the schedule-dependent scalars move to device memory --------------------------------
+    def enable_device_scalars(self):
+        """After this, the kernels read lr and the Adam bias corrections from a 3-float device buffer that
+        `push_scalars()` refreshes (one small pinned H2D copy), so a captured `launch()` can be replayed every step."""
+        if self._dyn is None:
+            dev = self.arena.flat_p.device
+            self._dyn = torch.zeros(3, dtype=torch.float32, device=dev)
+            self._dyn_host = torch.zeros(3, dtype=torch.float32).pin_memory()
+        return self
+
+    def push_scalars(self):
+        """Advance the step counter and upload {lr, 1-beta1^t, sqrt(1-beta2^t)} for the NEXT launch()."""
+        g = self.param_groups[0]
+        self.step_count += 1
+        b1, b2 = float(g["betas"][0]), float(g["betas"][1])
+        self._dyn_host[0] = float(g["lr"])
+        self._dyn_host[1] = 1.0 - b1 ** self.step_count
+        self._dyn_host[2] = (1.0 - b2 ** self.step_count) ** 0.5
+        self._dyn.copy_(self._dyn_host, non_blocking=True)
+
+    def launch(self):
+        """The two kernels of a step, with no host-side state change (what a CUDA graph captures)."""
+        if self._dyn is None:
+            raise RuntimeError("FusedClipAdam.launch() needs enable_device_scalars()")
+        g = self.param_groups[0]
+        a = self.arena
+        args = _args("WesepClipAdamArgs", total=a.total, n_seg=len(a.params), seg_off=a.seg_off, chunk_seg=a.chunk_seg,
+                     chunk_off=a.chunk_off, n_chunk=a.n_chunk, param=a.flat_p, grad=a.flat_g, exp_avg=self.exp_avg,
+                     exp_avg_sq=self.exp_avg_sq, sumsq=self.sumsq, norms=self.norms, grad_scale=float(self.grad_scale),
+                     clip=float(g["clip"] or 0.0), lr=float(g["lr"]), beta1=float(g["betas"][0]),
+                     beta2=float(g["betas"][1]), eps=float(g["eps"]), weight_decay=float(g["weight_decay"]),
+                     step=max(self.step_count, 1), dyn=self._dyn)
+        _lib.call("wesep_b200_clip_adam", args, _stream())
+        return self.norms
+
     def step(self):
+        if self._dyn is not None:      # device-scalar mode: same arithmetic, scalars through memory
+            self.push_scalars()
+            return self.launch()
         g = self.param_groups[0]
         a = self.arena
         self.step_count += 1
