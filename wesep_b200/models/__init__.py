@@ -1,10 +1,13 @@
 """Model registry — reference wesep/models/__init__.py:10-27 (prefix dispatch by name)."""
+import wesep_b200.models.bsrnn as bsrnn
 import wesep_b200.models.convtasnet as convtasnet
 
 
 def get_model(model_name: str):
     if model_name.startswith("ConvTasNet"):
         return getattr(convtasnet, model_name)
+    if model_name == "BSRNN":          # parameter / state_dict contract only so far: forward raises NotImplementedError
+        return bsrnn.BSRNN
     for prefix in ("BSRNN_Multi", "BSRNN_Feats", "BSRNN", "DPCCN", "TFGridNet", "CMGAN"):
         if model_name.startswith(prefix):
             raise NotImplementedError(model_name + " is not built yet in wesep_b200 (Spex+/ConvTasNet only so far)")
