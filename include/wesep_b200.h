@@ -359,9 +359,70 @@ typedef struct {
   float* dx;                        /* bwd out [n][C][lddx] */
   float* dra; float* drb;           /* bwd out [n][C] (overwritten; may be NULL) */
   float* dalpha; float* dgamma; float* dbeta;  /* bwd += [1], [C], [C] */
+  float eps;                        /* variance epsilon of the normalisation; 0 = 1e-5 (gLN).  With alpha = 1 and eps =
+                                       FLT_EPSILON this is nn.GroupNorm(1, C) of pBSRNN (bsrnn.py:24,256,274) */
 } WesepFuseArgs;
 int wesep_b200_fuse_prelu_gln_fwd(const WesepFuseArgs* a, void* stream);
 int wesep_b200_fuse_prelu_gln_bwd(const WesepFuseArgs* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * pBSRNN building blocks (wesep/models/bsrnn.py).  ResRNN runs in a TIME-MAJOR layout
+ * [S][C][ld(Q)] (rows = time steps, columns = sequences) so that one step of the recurrence is a conv1x1 GEMM
+ * [4Hd x Hd] . [Hd x Q]; these entry points provide the layout change and the LSTM cell.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int nb, Q, C, S; int64_t ld_in, ld_out;
+  const float* in;    /* [nb][Q][C][ld_in],  S valid columns */
+  float* out;         /* [nb][S][C][ld_out], Q valid columns: out[b][s][c][q] = in[b][q][c][s] (+ res[b][s][c][q]) */
+  const float* res;   /* optional, laid out like `out` (the ResRNN residual, bsrnn.py:46) */
+} WesepTransposeArgs;
+int wesep_b200_swap_outer_inner(const WesepTransposeArgs* a, void* stream);
+
+/* One time step of one LSTM direction (nn.LSTM gate order i, f, g, o; bsrnn.py:25-31) for Q sequences.
+ * fwd: G = gate pre-activations in, activations out (saved); c = f*c_prev + i*g; h = o*tanh(c).
+ * bwd: G = saved activations in, d(pre-activations) out; dh / dc_in = gradients w.r.t. h_s / c_s; dc_prev out. */
+typedef struct {
+  int Hd, Q; int64_t ld;
+  float* G;               /* [4*Hd][ld] */
+  const float* c_prev;    /* [Hd][ld] or NULL (zero state) */
+  float* c;               /* [Hd][ld]: fwd out, bwd in */
+  float* h;               /* [Hd][ld]: fwd out */
+  const float* dh;        /* bwd in  [Hd][ld] */
+  const float* dc_in;     /* bwd in  [Hd][ld] or NULL */
+  float* dc_prev;         /* bwd out [Hd][ld] */
+} WesepLstmCellArgs;
+int wesep_b200_lstm_cell_fwd(const WesepLstmCellArgs* a, void* stream);
+int wesep_b200_lstm_cell_bwd(const WesepLstmCellArgs* a, void* stream);
+
+/* y = ra[n][c] * x + rb[n][c] (NULL = 1 / 0): SpeakerFuseLayer multiply / additive with the Linear hoisted out of the
+ * (band, frame) loop (wesep/modules/common/speaker.py:103-121).  bwd: dx = ra * gy, dra = sum_t gy * x, drb = sum_t gy. */
+typedef struct {
+  int n, C, T; int64_t ld;          /* x, y, gy, dx: [n][C][ld] */
+  const float* x; const float* ra; const float* rb;
+  float* y;
+  const float* gy; float* dx; float* dra; float* drb;   /* dra / drb [n][C], overwritten, may be NULL */
+} WesepRowAffineArgs;
+int wesep_b200_rowaffine_fwd(const WesepRowAffineArgs* a, void* stream);
+int wesep_b200_rowaffine_bwd(const WesepRowAffineArgs* a, void* stream);
+
+/* tanh over `rows` rows of T valid columns (mask MLP, bsrnn.py:276-280).  bwd: dx = gy * (1 - y^2). */
+typedef struct {
+  int64_t rows; int T; int64_t ld;
+  const float* x; float* y;
+  const float* gy; float* dx;
+} WesepTanhArgs;
+int wesep_b200_tanh_fwd(const WesepTanhArgs* a, void* stream);
+int wesep_b200_tanh_bwd(const WesepTanhArgs* a, void* stream);
+
+/* Mask head tail (bsrnn.py:365-379): o [n][4*bw][ldo] = (value | gate) x (re | im) x bw; m = value * sigmoid(gate);
+ * e = s * m as a complex product, s / e = band slices (bw re rows, then bw im rows) of the mixture / estimate spectra. */
+typedef struct {
+  int n, bw, T; int64_t ldo, lds, lde, bso, bss, bse;   /* row and batch strides (floats) of o, s, e */
+  const float* o; const float* s; float* e;
+  const float* ge; float* go;                           /* bwd: ge laid out like e, go like o */
+} WesepMaskApplyArgs;
+int wesep_b200_mask_apply_fwd(const WesepMaskApplyArgs* a, void* stream);
+int wesep_b200_mask_apply_bwd(const WesepMaskApplyArgs* a, void* stream);
 
 #ifdef __cplusplus
 }

@@ -398,7 +398,7 @@ def test_fuse_prelu_gln(mode, n, C, T):
     al = torch.tensor([0.2], device=DEV, requires_grad=True)
     gm = (1 + 0.1 * rnd(C, 1, seed=4)).requires_grad_(True)
     bt = (0.1 * rnd(C, 1, seed=5)).requires_grad_(True)
-    z = ops.FusePreluGlnFn.apply(x, ra, rb, al, gm, bt)
+    z = ops.FusePreluGlnFn.apply(x, ra, rb, al, gm, bt, 0.0)
     gz = rnd(n, C, T, seed=6)
     ins = [t for t in (x, ra, rb, al, gm, bt) if t is not None]
     grads = torch.autograd.grad(z, ins, gz)

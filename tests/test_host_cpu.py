@@ -70,9 +70,11 @@ def test_model_registry_and_state_dict_contract():
     assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == ospex.state_dict_spec(cfg)
     with pytest.raises(NotImplementedError):
         get_model("DPCCN")
-    with pytest.raises(NotImplementedError):           # pBSRNN: parameter contract only, no forward yet (and no fallback)
-        get_model("BSRNN")(joint_training=False, use_spk_transform=False, feature_dim=16, num_repeat=1)(
-            torch.zeros(1, 2000), torch.zeros(1, 256))
+    with pytest.raises(RuntimeError):                  # pBSRNN: CUDA only (no fallback)
+        get_model("BSRNN")(joint_training=False, use_spk_transform=False, feature_dim=16, num_repeat=1,
+                           spk_fuse_type="multiply")(torch.zeros(1, 2000), torch.zeros(1, 256))
+    with pytest.raises(NotImplementedError):           # the wespeaker encoder of joint_training=True is not built
+        get_model("BSRNN")(joint_training=True)
     with pytest.raises(RuntimeError):
         m(torch.zeros(1, 1, 100), torch.zeros(1, 100))     # >= 3-D input, convtasnet.py:163-166
 

@@ -161,7 +161,7 @@ def test_oracle_bsrnn_recipe_size_forward():
 @pytest.mark.parametrize("fuse,mf", [("multiply", False), ("concat", True), ("additive", False)])
 def test_wesep_b200_bsrnn_state_dict_contract(fuse, mf):
     """wesep_b200.models.BSRNN registers its parameters under the reference's keys, shapes and ORDER (checkpoints,
-    optimizer state); its forward is not built yet and must say so instead of falling back to PyTorch."""
+    optimizer state); on CPU tensors its forward must refuse (there is no PyTorch fallback)."""
     from wesep_b200.models import get_model
     args = dict(spk_emb_dim=256, sr=16000, win=512, stride=128, feature_dim=16, num_repeat=2, use_spk_transform=False,
                 spk_fuse_type=fuse, multi_fuse=mf, joint_training=False)
@@ -170,5 +170,5 @@ def test_wesep_b200_bsrnn_state_dict_contract(fuse, mf):
     got = m.state_dict()
     assert list(got.keys()) == list(want.keys())
     assert all(tuple(got[k].shape) == tuple(want[k].shape) for k in want)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError):
         m(torch.zeros(1, 4000), torch.zeros(1, 256))

@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(256) fuse_kernel(WesepFuseArgs a) {
   const float al = __ldg(a.alpha);
   const float* x = a.x + ((int64_t)n * a.C + c) * a.ldx;
   float mu = 0.f, r = 1.f;
-  if constexpr (MODE >= 1) gln_mean_rstd(a.stats + 2 * n, (double)a.C * a.T, FUSE_EPS, mu, r);
+  if constexpr (MODE >= 1) gln_mean_rstd(a.stats + 2 * n, (double)a.C * a.T, a.eps > 0.f ? a.eps : FUSE_EPS, mu, r);
   const float gm = __ldg(a.gamma + c), bt = __ldg(a.beta + c);
   float m1 = 0.f, m2 = 0.f;
   if constexpr (MODE == 3) {

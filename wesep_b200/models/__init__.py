@@ -6,7 +6,7 @@ import wesep_b200.models.convtasnet as convtasnet
 def get_model(model_name: str):
     if model_name.startswith("ConvTasNet"):
         return getattr(convtasnet, model_name)
-    if model_name == "BSRNN":          # parameter / state_dict contract only so far: forward raises NotImplementedError
+    if model_name == "BSRNN":          # first correct CUDA path (joint_training=False); see models/bsrnn.py
         return bsrnn.BSRNN
     for prefix in ("BSRNN_Multi", "BSRNN_Feats", "BSRNN", "DPCCN", "TFGridNet", "CMGAN"):
         if model_name.startswith(prefix):

@@ -1,15 +1,22 @@
 """pBSRNN — parameter / constructor contract of the reference wesep/models/bsrnn.py:151-298 (class name, kwargs,
 attribute paths, parameter shapes and order, hence `state_dict()` keys, checkpoint and optimizer-state layout).
 
-STATUS: contract only.  The CUDA path for this model is not built yet — the oracle
-(`oracle/bsrnn.py`) and its golden fixtures are; DESIGN.md §7.5 has the kernel plan.  `forward` raises
-NotImplementedError: there is no PyTorch / CPU fallback in this package.  The nn.GroupNorm / nn.LSTM / nn.Linear /
-nn.Conv1d objects below are parameter containers (same initialisation as the reference); their own forwards are never
-called.
+STATUS: first correct path (`joint_training=False`, fuse types multiply / additive).  The
+forward runs on libwesep_b200: STFT / iSTFT as framing + windowed-DFT GEMMs, band split as GroupNorm + one block-diagonal
+GEMM, ResRNN in a time-major layout (input / recurrent / output projections on the conv1x1 GEMMs, one GEMM + one cell
+kernel per time step — `ops.LstmTmFn`), mask MLPs as GEMMs with tanh / gating kernels.  It is launch-bound (the
+recurrence is driven from Python); DESIGN.md §7 has the plan for the persistent-cluster recurrence.  There is no PyTorch
+fallback: the nn.GroupNorm / nn.LSTM / nn.Linear / nn.Conv1d objects below are parameter containers (same initialisation
+as the reference); their own forwards are never called.  Small torch glue remains (reflect padding, weight assembly,
+concatenation of band slices, the 1 / sum(w^2) envelope).
 """
+import math
+
 import numpy as np
 import torch
 import torch.nn as nn
+
+from wesep_b200 import ops
 
 
 class _FuseFC(nn.Module):
@@ -125,6 +132,112 @@ class BSRNN(nn.Module):
                           nn.Conv1d(feature_dim * 4, feature_dim * 4, 1), nn.Tanh(),
                           nn.Conv1d(feature_dim * 4, bw * 4, 1)) for bw in self.band_width])
 
+    # ---- constant DFT bases (band-major spectrum rows: per band bw re rows then bw im rows; padded to a multiple of 4) ----
+    def _bases(self, device):
+        key = str(device)
+        cache = self.__dict__.setdefault("_basis_cache", {})
+        if key not in cache:
+            win, F = self.win, self.enc_dim
+            w = torch.hann_window(win, dtype=torch.float32).double()      # fp32-rounded window, bsrnn.py:313
+            k = torch.arange(win, dtype=torch.float64)
+            f = torch.arange(F, dtype=torch.float64)
+            ang = 2.0 * math.pi * f[:, None] * k[None, :] / win
+            rows = sum(2 * b for b in self.band_width)
+            R = (rows + 3) // 4 * 4
+            fwd = torch.zeros(R, win, dtype=torch.float64)                # spec = fwd @ frame
+            inv = torch.zeros(win, R, dtype=torch.float64)                # frame = inv @ spec  (includes the window)
+            wgt = torch.full((F,), 2.0, dtype=torch.float64)
+            wgt[0] = 1.0
+            wgt[-1] = 1.0
+            cr, ci = torch.cos(ang), -torch.sin(ang)
+            icr = wgt[:, None] * torch.cos(ang) / win
+            ici = -wgt[:, None] * torch.sin(ang) / win
+            ici[0] = 0.0
+            ici[-1] = 0.0
+            offs, lo, r = [], 0, 0
+            for bw in self.band_width:
+                offs.append(r)
+                fwd[r:r + bw] = cr[lo:lo + bw] * w
+                fwd[r + bw:r + 2 * bw] = ci[lo:lo + bw] * w
+                inv[:, r:r + bw] = (icr[lo:lo + bw] * w).t()
+                inv[:, r + bw:r + 2 * bw] = (ici[lo:lo + bw] * w).t()
+                lo += bw
+                r += 2 * bw
+            cache[key] = (fwd.float().to(device).contiguous(), inv.float().to(device).contiguous(), offs, R,
+                          (w * w).float().to(device))
+        return cache[key]
+
+    def _resrnn_args(self, m):
+        r = m.rnn
+        return (m.norm.weight, m.norm.bias,
+                [r.weight_ih_l0, r.weight_hh_l0, r.bias_ih_l0, r.bias_hh_l0, r.weight_ih_l0_reverse, r.weight_hh_l0_reverse,
+                 r.bias_ih_l0_reverse, r.bias_hh_l0_reverse], m.proj.weight, m.proj.bias)
+
+    def _fuse(self, layer, x, emb):
+        v = ops.LinearFn.apply(emb, layer.fc.linear.weight, layer.fc.linear.bias)        # [B, N], once per row
+        v = v.repeat(1, self.nband)                                                       # same vector for every band
+        if layer.fuse_type == "multiply":
+            return ops.RowAffineFn.apply(x, v, None)
+        if layer.fuse_type == "additive":
+            return ops.RowAffineFn.apply(x, None, v)
+        raise NotImplementedError("pBSRNN fuse type 'concat' is not on the CUDA path yet")
+
     def forward(self, input, embeddings):
-        raise NotImplementedError("wesep_b200.models.BSRNN: the sm_100a kernels for the pBSRNN path are not built yet "
-                                  "(DESIGN.md §2, §7.5); there is no PyTorch fallback")
+        if input.dim() != 2:
+            raise RuntimeError("BSRNN expects [batch, samples]")
+        if not (input.is_cuda and embeddings.is_cuda):
+            raise RuntimeError("wesep_b200 kernels need CUDA tensors (no CPU fallback)")
+        dev = input.device
+        B, L = input.shape
+        win, hop, N, nb = self.win, self.stride, self.feature_dim, self.nband
+        fwd_b, inv_b, offs, R, w2 = self._bases(dev)
+        T = 1 + L // hop
+        with torch.no_grad():                                   # the mixture is data: no gradient through the analysis
+            x = input.float()
+            pad = win // 2
+            xp = torch.cat([x[:, 1:pad + 1].flip(1), x, x[:, L - pad - 1:L - 1].flip(1)], 1).contiguous()
+            spec = ops.conv1x1_raw(ops.frames_raw(xp, win, T, hop), fwd_b, False, R)      # [B, R, T] band-major re | im
+        # band split: GroupNorm(1, 2bw) per band, then all 32 Conv1d(2bw, N, 1) as one block-diagonal GEMM
+        parts = [ops.group_norm1(spec[:, o:o + 2 * bw], self.BN[i][0].weight, self.BN[i][0].bias)
+                 for i, (o, bw) in enumerate(zip(offs, self.band_width))]
+        if R > offs[-1] + 2 * self.band_width[-1]:
+            parts.append(torch.zeros(B, R - offs[-1] - 2 * self.band_width[-1], T, device=dev))
+        xhat = torch.cat(parts, 1)
+        Wbig = torch.zeros(nb * N, R, device=dev)
+        for i, (o, bw) in enumerate(zip(offs, self.band_width)):
+            Wbig[i * N:(i + 1) * N, o:o + 2 * bw] = self.BN[i][1].weight[:, :, 0]
+        bbig = torch.cat([self.BN[i][1].bias for i in range(nb)])
+        x = ops.Conv1x1Fn.apply(xhat, Wbig, bbig, False, None)                            # [B, nb*N, T]
+        emb = self.spk_transform(embeddings).float()
+        sep = self.separator.separation
+        if self.separator.multi_fuse:
+            for r in range(len(sep) // 2):
+                x = self._fuse(sep[2 * r], x, emb)
+                x = ops.bsnet(x, nb, self._resrnn_args(sep[2 * r + 1].band_rnn), self._resrnn_args(sep[2 * r + 1].band_comm))
+        else:
+            x = self._fuse(sep[0], x, emb)
+            for r in range(1, len(sep)):
+                x = ops.bsnet(x, nb, self._resrnn_args(sep[r].band_rnn), self._resrnn_args(sep[r].band_comm))
+        # mask head per band -> estimate spectrum (band-major)
+        ests = []
+        for i, (o, bw) in enumerate(zip(offs, self.band_width)):
+            mk = self.mask[i]
+            y = ops.group_norm1(x[:, i * N:(i + 1) * N], mk[0].weight, mk[0].bias)
+            y = ops.TanhFn.apply(ops.Conv1x1Fn.apply(y, mk[1].weight[:, :, 0], mk[1].bias, False, None))
+            y = ops.TanhFn.apply(ops.Conv1x1Fn.apply(y, mk[3].weight[:, :, 0], mk[3].bias, False, None))
+            y = ops.Conv1x1Fn.apply(y, mk[5].weight[:, :, 0], mk[5].bias, False, None)   # [B, 4bw, T]
+            ests.append(ops.MaskApplyFn.apply(y, spec[:, o:o + 2 * bw]))
+        if R > offs[-1] + 2 * self.band_width[-1]:
+            ests.append(torch.zeros(B, R - offs[-1] - 2 * self.band_width[-1], T, device=dev))
+        est = torch.cat(ests, 1)                                                          # [B, R, T]
+        frames = ops.FixedGemmFn.apply(est, inv_b, False)                                 # [B, win, T]
+        n_out = win + hop * (T - 1)
+        y = ops.OverlapAddFn.apply(frames, hop, n_out)                                    # [B, n_out]
+        env = self.__dict__.setdefault("_env_cache", {}).get((str(dev), T))
+        if env is None:
+            e = torch.zeros(n_out, device=dev)
+            for t in range(T):
+                e[t * hop:t * hop + win] += w2
+            env = self._env_cache[(str(dev), T)] = 1.0 / e[win // 2:win // 2 + L]
+        s = y[:, win // 2:win // 2 + L] * env
+        return s, torch.tensor(0.0, device=dev)

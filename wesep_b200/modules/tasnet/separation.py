@@ -62,6 +62,6 @@ class FuseSeparation(nn.Module):
             if not isinstance(norm, GlobalChannelLayerNorm):
                 raise NotImplementedError("only norm='gLN' is accelerated")
             y0, ra, rb = fuse.prepare(x, spk_embedding)
-            x = ops.FusePreluGlnFn.apply(y0, ra, rb, act.weight, norm.weight, norm.bias)
+            x = ops.FusePreluGlnFn.apply(y0, ra, rb, act.weight, norm.weight, norm.bias, 0.0)
             x = sep(x)
         return x

@@ -764,7 +764,7 @@ class FusePreluGlnFn(torch.autograd.Function):
     concat) + the nn.PReLU and gLN that follow it in FuseSeparation (wesep/modules/tasnet/separation.py:116-126)."""
 
     @staticmethod
-    def forward(ctx, x, ra, rb, alpha, gamma, beta):
+    def forward(ctx, x, ra, rb, alpha, gamma, beta, eps):
         x = as_act(x)
         n, C, T = x.shape
         dev = x.device
@@ -775,7 +775,9 @@ class FusePreluGlnFn(torch.autograd.Function):
         y = new_act(n, C, T, dev)
         _lib.call("wesep_b200_fuse_prelu_gln_fwd", _args("WesepFuseArgs", n=n, C=C, T=T, ldx=x.stride(1), ldy=y.stride(1),
                                                          x=x, ra=ra_c, rb=rb_c, alpha=al, gamma=gm, beta=bt, stats=stats,
-                                                         y=y), _stream())
+                                                         y=y, eps=float(eps)), _stream())
+        ctx.eps = float(eps)
+        ctx.gshape = (gamma.shape, beta.shape)
         ctx.flags = (ra is not None, rb is not None, None if ra is None else ra.shape, None if rb is None else rb.shape)
         ctx.save_for_backward(x, ra_c, rb_c, al, gm, bt, stats)
         return y
@@ -795,7 +797,288 @@ class FusePreluGlnFn(torch.autograd.Function):
         _lib.call("wesep_b200_fuse_prelu_gln_bwd", _args("WesepFuseArgs", n=n, C=C, T=T, ldx=x.stride(1), ldg=gz.stride(1),
                                                          lddx=dx.stride(1), x=x, ra=ra_c, rb=rb_c, alpha=al, gamma=gm,
                                                          beta=bt, stats=stats, gz=gz, rowsums=rowsums, dx=dx, dra=dra,
-                                                         drb=drb, dalpha=acc[0:], dgamma=acc[1:], dbeta=acc[1 + C:]),
+                                                         drb=drb, dalpha=acc[0:], dgamma=acc[1:], dbeta=acc[1 + C:],
+                                                         eps=ctx.eps),
                   _stream())
         return (dx, None if dra is None else dra.view(sha), None if drb is None else drb.view(shb), acc[0:1],
-                acc[1:1 + C].view(C, 1), acc[1 + C:].view(C, 1))
+                acc[1:1 + C].view(ctx.gshape[0]), acc[1 + C:].view(ctx.gshape[1]), None)
+
+
+# --------------------------------------------------------------------------- pBSRNN building blocks
+def swap_oi_raw(x, nb=1, res=None):
+    """x: act [nb*Q, C, S] -> act [nb*S, C, Q] with out[b, s, c, q] = x[b, q, c, s] (+ res, laid out like the result)."""
+    x = as_act(x)
+    nQ, C, S = x.shape
+    if nQ % nb:
+        raise RuntimeError("swap_oi: leading dimension is not a multiple of the batch count")
+    Q = nQ // nb
+    out = new_act(nb * S, C, Q, x.device)
+    if res is not None:
+        res = as_act(res)
+        if res.shape != out.shape or res.stride(1) != out.stride(1):
+            raise RuntimeError("swap_oi: residual layout")
+    _lib.call("wesep_b200_swap_outer_inner", _args("WesepTransposeArgs", nb=nb, Q=Q, C=C, S=S, ld_in=x.stride(1),
+                                                   ld_out=out.stride(1), **{"in": x}, out=out, res=res), _stream())
+    return out
+
+
+class SwapOIFn(torch.autograd.Function):
+    """[nb][Q][C][S] -> [nb][S][C][Q] (optionally + residual): ResRNN's reference <-> time-major layout change and
+    BSNet's permute(0, 3, 2, 1) (wesep/models/bsrnn.py:38-46,70-83).  The adjoint is the same kernel."""
+
+    @staticmethod
+    def forward(ctx, x, nb, res):
+        ctx.nb = int(nb)
+        ctx.has_res = res is not None
+        return swap_oi_raw(x, ctx.nb, res)
+
+    @staticmethod
+    def backward(ctx, gy):
+        gy = as_act(gy)
+        return swap_oi_raw(gy, ctx.nb), None, (gy if ctx.has_res else None)
+
+
+def _cell_args(G, c_prev, c, h=None, dh=None, dc_in=None, dc_prev=None):
+    _, Hd4, Q = G.shape
+    return _args("WesepLstmCellArgs", Hd=Hd4 // 4, Q=Q, ld=G.stride(1), G=G, c_prev=c_prev, c=c, h=h, dh=dh, dc_in=dc_in,
+                 dc_prev=dc_prev)
+
+
+class LstmTmFn(torch.autograd.Function):
+    """Bidirectional single-layer nn.LSTM (wesep/models/bsrnn.py:25-31) on a TIME-MAJOR act tensor xn [S, C, Q]
+    (rows = time steps, columns = sequences) -> h [S, 2*Hd, Q] (forward direction in channels [0, Hd), backward in
+    [Hd, 2*Hd)).  Input projection of both directions = one GEMM; every step of the recurrence = one conv1x1 GEMM
+    (W_hh . h_{s-1}, accumulated onto the step's slice of the input projection) + the cell kernel.  The gate
+    activations overwrite the pre-activations and are what the backward (BPTT, same two launches per step) consumes."""
+
+    @staticmethod
+    def forward(ctx, xn, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_b, w_hh_b, b_ih_b, b_hh_b):
+        xn = as_act(xn)
+        S, C, Q = xn.shape
+        Hd = w_hh_f.shape[1]
+        dev = xn.device
+        Wih = torch.cat([w_ih_f, w_ih_b], 0).contiguous()
+        bias = torch.cat([b_ih_f + b_hh_f, b_ih_b + b_hh_b]).contiguous()
+        whh = (w_hh_f.contiguous(), w_hh_b.contiguous())
+        G = conv1x1_raw(xn, Wih, False, 8 * Hd, bias=bias)
+        H = new_act(S, 2 * Hd, Q, dev)
+        Cs = new_act(S, 2 * Hd, Q, dev)
+        st = _stream()
+        for d in range(2):
+            prev = None
+            for s in (range(S) if d == 0 else range(S - 1, -1, -1)):
+                Gs = G[s:s + 1, 4 * Hd * d:4 * Hd * (d + 1)]
+                if prev is not None:
+                    conv1x1_raw(H[prev:prev + 1, Hd * d:Hd * (d + 1)], whh[d], False, 4 * Hd, epi=2, R=Gs, Y=Gs)
+                _lib.call("wesep_b200_lstm_cell_fwd",
+                          _cell_args(Gs, None if prev is None else Cs[prev:prev + 1, Hd * d:Hd * (d + 1)],
+                                     Cs[s:s + 1, Hd * d:Hd * (d + 1)], h=H[s:s + 1, Hd * d:Hd * (d + 1)]), st)
+                prev = s
+        ctx.save_for_backward(xn, Wih, whh[0], whh[1], G, Cs, H)
+        return H
+
+    @staticmethod
+    def backward(ctx, gH):
+        xn, Wih, whh_f, whh_b, G, Cs, H = ctx.saved_tensors
+        S, C, Q = xn.shape
+        Hd = whh_f.shape[1]
+        dev = xn.device
+        dH = new_act(S, 2 * Hd, Q, dev)
+        dH.copy_(gH)                                   # accumulated in place below: never touch autograd's tensor
+        dc = [new_act(1, Hd, Q, dev), new_act(1, Hd, Q, dev)]
+        st = _stream()
+        whh = (whh_f, whh_b)
+        for d in range(2):
+            order = list(range(S)) if d == 0 else list(range(S - 1, -1, -1))
+            dc_in = None
+            for k in range(S - 1, -1, -1):             # reverse of the forward order of this direction
+                s = order[k]
+                prev = order[k - 1] if k > 0 else None
+                Gs = G[s:s + 1, 4 * Hd * d:4 * Hd * (d + 1)]
+                dc_out = dc[k & 1]
+                _lib.call("wesep_b200_lstm_cell_bwd",
+                          _cell_args(Gs, None if prev is None else Cs[prev:prev + 1, Hd * d:Hd * (d + 1)],
+                                     Cs[s:s + 1, Hd * d:Hd * (d + 1)], dh=dH[s:s + 1, Hd * d:Hd * (d + 1)], dc_in=dc_in,
+                                     dc_prev=dc_out), st)
+                if prev is not None:                   # dL/dh_prev += W_hh^T . d(gates_s)
+                    dHp = dH[prev:prev + 1, Hd * d:Hd * (d + 1)]
+                    conv1x1_raw(Gs, whh[d], True, Hd, epi=2, R=dHp, Y=dHp)
+                dc_in = dc_out
+        # G now holds d(pre-activations) of both directions
+        dWih = torch.zeros((8 * Hd, C), dtype=torch.float32, device=dev)
+        conv1x1_dw_raw(G, xn, dWih)
+        db = rowsum_raw(G).sum(0)
+        dWhh = [torch.zeros((4 * Hd, Hd), dtype=torch.float32, device=dev) for _ in range(2)]
+        if S > 1:
+            conv1x1_dw_raw(G[1:, :4 * Hd], H[:-1, :Hd], dWhh[0])
+            conv1x1_dw_raw(G[:-1, 4 * Hd:], H[1:, Hd:], dWhh[1])
+        dxn = conv1x1_raw(G, Wih, True, C)
+        return (dxn, dWih[:4 * Hd], dWhh[0], db[:4 * Hd], db[:4 * Hd], dWih[4 * Hd:], dWhh[1], db[4 * Hd:], db[4 * Hd:])
+
+
+_ONE = {}
+
+
+def _one(device):
+    t = _ONE.get(device)
+    if t is None:
+        t = _ONE[device] = torch.ones(1, dtype=torch.float32, device=device)
+    return t
+
+
+GN_EPS = float(torch.finfo(torch.float32).eps)
+
+
+def group_norm1(x, weight, bias, eps=GN_EPS):
+    """nn.GroupNorm(1, C, eps) of an act tensor [n, C, T] (per row over (C, T)): the gLN kernels with a unit PReLU slope."""
+    return FusePreluGlnFn.apply(x, None, None, _one(x.device), weight, bias, eps)
+
+
+def res_rnn(x, norm_w, norm_b, lstm, proj_w, proj_b):
+    """ResRNN.forward (bsrnn.py:38-46) on an act tensor x [Q, C, S] (rows = sequences): GroupNorm -> time-major ->
+    BLSTM -> Linear -> back to [Q, C, S] + x.  `lstm` = the 8 nn.LSTM parameters in (forward, reverse) order."""
+    xh = group_norm1(x, norm_w, norm_b)
+    xn = SwapOIFn.apply(xh, 1, None)                                   # [S, C, Q]
+    h = LstmTmFn.apply(xn, *lstm)                                       # [S, 2Hd, Q]
+    p = Conv1x1Fn.apply(h, proj_w, proj_b, False, None)                 # [S, C, Q]
+    return SwapOIFn.apply(p, 1, x)                                      # [Q, C, S] + residual
+
+
+def bsnet(x, nband, band_rnn, band_comm):
+    """BSNet.forward (bsrnn.py:70-83) on an act tensor x [B, nband*N, T].  band_rnn / band_comm = argument tuples of
+    res_rnn (norm_w, norm_b, lstm[8], proj_w, proj_b)."""
+    x = as_act(x)
+    B, NN, T = x.shape
+    N = NN // nband
+    ld = x.stride(1)
+    xb = x.as_strided((B * nband, N, T), (N * ld, ld, 1))            # [B*nband, N, T]: same memory, bands as rows
+    y = res_rnn(xb, *band_rnn)
+    yc = SwapOIFn.apply(y, B, None)                                    # [B*T, N, nband]  (permute(0, 3, 2, 1))
+    z = res_rnn(yc, *band_comm)
+    out = SwapOIFn.apply(z, B, None)                                   # [B*nband, N, T]
+    ld2 = out.stride(1)
+    return out.as_strided((B, NN, T), (NN * ld2, ld2, 1))
+
+
+class FixedGemmFn(torch.autograd.Function):
+    """y = W x with a constant W (the windowed inverse-DFT basis): conv1x1 without a weight gradient."""
+
+    @staticmethod
+    def forward(ctx, x, W, w_trans):
+        x = as_act(x)
+        M = W.shape[1] if w_trans else W.shape[0]
+        ctx.w_trans = bool(w_trans)
+        ctx.Kd = x.shape[1]
+        ctx.save_for_backward(W)
+        return conv1x1_raw(x, W, w_trans, M)
+
+    @staticmethod
+    def backward(ctx, gy):
+        (W,) = ctx.saved_tensors
+        return conv1x1_raw(as_act(gy), W, not ctx.w_trans, ctx.Kd), None, None
+
+
+def overlap_add_raw(F, hop, S):
+    n, J, K = F.shape
+    y = torch.empty((n, S), dtype=torch.float32, device=F.device)
+    _lib.call("wesep_b200_overlap_add", _args("WesepOlaArgs", n=n, J=J, K=K, hop=hop, S=S, F=F, ldf=F.stride(1), bias=None,
+                                              y=y, ldy=y.stride(0)), _stream())
+    return y
+
+
+class OverlapAddFn(torch.autograd.Function):
+    """y[n, s] = sum_{j + k*hop = s} F[n, j, k]  (iSTFT synthesis); the adjoint is the framing gather."""
+
+    @staticmethod
+    def forward(ctx, F, hop, S):
+        F = as_act(F)
+        ctx.meta = (F.shape[1], F.shape[2], int(hop))
+        return overlap_add_raw(F, int(hop), int(S))
+
+    @staticmethod
+    def backward(ctx, gy):
+        J, K, hop = ctx.meta
+        return frames_raw(gy.contiguous(), J, K, hop), None, None
+
+
+class RowAffineFn(torch.autograd.Function):
+    """y = ra[n, c] * x + rb[n, c] (either may be None)."""
+
+    @staticmethod
+    def forward(ctx, x, ra, rb):
+        x = as_act(x)
+        n, C, T = x.shape
+        ra_c = None if ra is None else ra.reshape(n, C).contiguous().float()
+        rb_c = None if rb is None else rb.reshape(n, C).contiguous().float()
+        y = new_act(n, C, T, x.device)
+        _lib.call("wesep_b200_rowaffine_fwd", _args("WesepRowAffineArgs", n=n, C=C, T=T, ld=x.stride(1), x=x, ra=ra_c, rb=rb_c,
+                                                    y=y), _stream())
+        ctx.shapes = (None if ra is None else ra.shape, None if rb is None else rb.shape)
+        ctx.save_for_backward(x, ra_c)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, ra_c = ctx.saved_tensors
+        n, C, T = x.shape
+        sha, shb = ctx.shapes
+        gy = as_act(gy)
+        if gy.stride(1) != x.stride(1):
+            raise RuntimeError("rowaffine backward: stride mismatch")
+        dx = new_act(n, C, T, x.device)
+        dra = torch.empty((n, C), dtype=torch.float32, device=x.device) if sha is not None else None
+        drb = torch.empty((n, C), dtype=torch.float32, device=x.device) if shb is not None else None
+        _lib.call("wesep_b200_rowaffine_bwd", _args("WesepRowAffineArgs", n=n, C=C, T=T, ld=x.stride(1), x=x, ra=ra_c, gy=gy,
+                                                    dx=dx, dra=dra, drb=drb), _stream())
+        return dx, None if dra is None else dra.view(sha), None if drb is None else drb.view(shb)
+
+
+class TanhFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = as_act(x)
+        n, C, T = x.shape
+        y = new_act(n, C, T, x.device)
+        _lib.call("wesep_b200_tanh_fwd", _args("WesepTanhArgs", rows=n * C, T=T, ld=x.stride(1), x=x, y=y), _stream())
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (y,) = ctx.saved_tensors
+        n, C, T = y.shape
+        gy = as_act(gy)
+        dx = new_act(n, C, T, y.device)
+        _lib.call("wesep_b200_tanh_bwd", _args("WesepTanhArgs", rows=n * C, T=T, ld=y.stride(1), y=y, gy=gy, dx=dx), _stream())
+        return dx
+
+
+class MaskApplyFn(torch.autograd.Function):
+    """Mask-head tail of one band (bsrnn.py:365-379): o [n, 4*bw, T] -> estimate band [n, 2*bw, T] (bw re rows, bw im rows)
+    = mixture band * (value * sigmoid(gate)) as a complex product.  `s` is a channel slice of the mixture spectrum."""
+
+    @staticmethod
+    def forward(ctx, o, s):
+        o = as_act(o)
+        n, C4, T = o.shape
+        bw = C4 // 4
+        if not is_act_slice(s) or s.shape != (n, 2 * bw, T):
+            raise RuntimeError("mask_apply: mixture band layout")
+        e = new_act(n, 2 * bw, T, o.device)
+        _lib.call("wesep_b200_mask_apply_fwd", _args("WesepMaskApplyArgs", n=n, bw=bw, T=T, ldo=o.stride(1), lds=s.stride(1),
+                                                     lde=e.stride(1), bso=o.stride(0), bss=s.stride(0), bse=e.stride(0), o=o,
+                                                     s=s, e=e), _stream())
+        ctx.save_for_backward(o, s)
+        return e
+
+    @staticmethod
+    def backward(ctx, ge):
+        o, s = ctx.saved_tensors
+        n, C4, T = o.shape
+        bw = C4 // 4
+        ge = as_act(ge)
+        go = new_act(n, C4, T, o.device)
+        _lib.call("wesep_b200_mask_apply_bwd", _args("WesepMaskApplyArgs", n=n, bw=bw, T=T, ldo=o.stride(1), lds=s.stride(1),
+                                                     lde=ge.stride(1), bso=o.stride(0), bss=s.stride(0), bse=ge.stride(0), o=o,
+                                                     s=s, ge=ge, go=go), _stream())
+        return go, None
