@@ -212,7 +212,9 @@ def test_cuda_graph_train_step_matches_eager():
     assert se == sg == 6
     assert np.allclose(lg, le, rtol=1e-3, atol=1e-3), (lg, le)
     # parameters: skip the decoder biases (their gradient is pure round-off, see ZERO_GRAD: Adam then moves them by
-    # +-lr per step in a direction that depends on the order of fp32 atomics); everything else must coincide
+    # +-lr per step in a direction that depends on the order of fp32 atomics).  Two fp32 runs differ by 1.0e-3 .. 1.6e-3
+    # in relative L2 after 6 Adam steps (measured over repeated runs: elements whose gradient is at the atomics-order
+    # noise level move +-lr either way); a wrong schedule / stale scalar in the graph would show as >= 1e-2.
     num = sum(float((pg[k].double() - pe[k].double()).pow(2).sum()) for k in pe if not ZERO_GRAD.search(k))
     den = sum(float(pe[k].double().pow(2).sum()) for k in pe if not ZERO_GRAD.search(k))
-    assert (num / den) ** 0.5 < 1e-3, (num / den) ** 0.5
+    assert (num / den) ** 0.5 < 3e-3, (num / den) ** 0.5
