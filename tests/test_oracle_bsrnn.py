@@ -172,3 +172,34 @@ def test_wesep_b200_bsrnn_state_dict_contract(fuse, mf):
     assert all(tuple(got[k].shape) == tuple(want[k].shape) for k in want)
     with pytest.raises(RuntimeError):
         m(torch.zeros(1, 4000), torch.zeros(1, 256))
+
+
+def test_wesep_b200_bsrnn_dft_bases_match_oracle_stft():
+    """The constant analysis / synthesis matrices the CUDA path multiplies with (band-major spectrum rows, window folded
+    in, models/bsrnn.py:_bases) reproduce the oracle's STFT / iSTFT when applied with plain matmuls on the CPU."""
+    from wesep_b200.models import get_model
+    m = get_model("BSRNN")(joint_training=False, use_spk_transform=False, feature_dim=16, num_repeat=1,
+                           spk_fuse_type="multiply", multi_fuse=False)
+    fwd_b, inv_b, offs, R, w2 = m._bases(torch.device("cpu"))
+    assert R == 516 and fwd_b.shape == (516, 512) and inv_b.shape == (512, 516)
+    L, win, hop = 3000, 512, 128
+    x = torch.randn(2, L, generator=torch.Generator().manual_seed(3))
+    re, im = ob.stft(x.double())
+    T = re.shape[-1]
+    xp = torch.cat([x[:, 1:257].flip(1), x, x[:, L - 257:L - 1].flip(1)], 1)
+    idx = (torch.arange(T) * hop)[:, None] + torch.arange(win)[None, :]
+    spec = torch.einsum("rk,btk->brt", fwd_b.double(), xp.double()[:, idx])         # [B, 516, T]
+    lo = 0
+    for o, bw in zip(offs, m.band_width):
+        assert float((spec[:, o:o + bw] - re[:, lo:lo + bw]).abs().max()) < 1e-4
+        assert float((spec[:, o + bw:o + 2 * bw] - im[:, lo:lo + bw]).abs().max()) < 1e-4
+        lo += bw
+    fr = torch.einsum("kr,brt->btk", inv_b.double(), spec)                          # windowed inverse-DFT frames
+    n_out = win + hop * (T - 1)
+    y = torch.zeros(2, n_out, dtype=torch.float64)
+    env = torch.zeros(n_out, dtype=torch.float64)
+    for t in range(T):
+        y[:, t * hop:t * hop + win] += fr[:, t]
+        env[t * hop:t * hop + win] += w2.double()
+    rec = y[:, 256:256 + L] / env[256:256 + L]
+    assert float((rec - x.double()).abs().max()) < 1e-4                             # analysis -> synthesis reconstructs
