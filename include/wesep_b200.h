@@ -394,6 +394,23 @@ typedef struct {
 int wesep_b200_lstm_cell_fwd(const WesepLstmCellArgs* a, void* stream);
 int wesep_b200_lstm_cell_bwd(const WesepLstmCellArgs* a, void* stream);
 
+/* The whole time loop of ONE LSTM direction in one call (time-major tensors, see above): for every step the recurrent
+ * GEMM G_s += W_hh . h_prev (conv1x1, in place on the step's gate block) and the cell.  fwd fills H / C and leaves the gate
+ * activations in G; bwd turns G into d(pre-activations) and accumulates the recurrent gradient into dH in place.
+ * EXPERIMENTAL (round 2): the Python host drives the loop step by step unless WESEP_LSTM_C_LOOP=1. */
+typedef struct {
+  int S, Q, Hd, reverse;    /* reverse = 1: the direction that runs from the last step to the first */
+  int64_t ld;               /* row stride (floats) of every tensor below */
+  int64_t bsG, bsH;         /* step strides: G blocks are [4*Hd][ld] every bsG floats; H / C / dH blocks [Hd][ld] every bsH */
+  float* G; float* H; float* C;
+  const float* Whh;         /* [4*Hd][Hd] */
+  float* dH;                /* bwd only */
+  float* dc0; float* dc1;   /* bwd only: two [Hd][ld] scratch buffers */
+  void* ws; int64_t ws_bytes;
+} WesepLstmSeqArgs;
+int wesep_b200_lstm_seq_fwd(const WesepLstmSeqArgs* a, void* stream);
+int wesep_b200_lstm_seq_bwd(const WesepLstmSeqArgs* a, void* stream);
+
 /* y = ra[n][c] * x + rb[n][c] (NULL = 1 / 0): SpeakerFuseLayer multiply / additive with the Linear hoisted out of the
  * (band, frame) loop (wesep/modules/common/speaker.py:103-121).  bwd: dx = ra * gy, dra = sum_t gy * x, drb = sum_t gy. */
 typedef struct {

@@ -164,3 +164,26 @@ def test_bsrnn_golden_small(name):
 def test_bsrnn_golden_recipe_size_forward():
     """bsrnn.yaml network (feature 128, hidden 256, 6 repeats, 32 bands) on 1 s of audio vs the reference, forward."""
     _golden_case("bsrnn_full_fwd_1s", backward=False)
+
+
+@pytest.mark.skipif(__import__("os").environ.get("WESEP_TEST_EXPERIMENTAL") != "1",
+                    reason="wesep_b200_lstm_seq_* (time loop in C) has not been validated on a GPU yet; opt in with "
+                           "WESEP_TEST_EXPERIMENTAL=1")
+def test_blstm_c_loop_matches_python_loop(monkeypatch):
+    """EXPERIMENTAL: the whole time loop of a direction in one C call must reproduce the step-by-step host loop."""
+    from wesep_b200 import ops
+    Q, C, S, Hd = 33, 32, 12, 64
+    xs = rnd(S, C, Q, seed=1)
+    ps = _lstm_params(C, Hd, 5)
+    outs = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("WESEP_LSTM_C_LOOP", flag)
+        xn = ops.new_act(S, C, Q, DEV)
+        xn.copy_(xs)
+        xn.requires_grad_(True)
+        pg = [p.clone().requires_grad_(True) for p in ps]
+        h = ops.LstmTmFn.apply(xn, *pg)
+        h.backward(rnd(S, 2 * Hd, Q, seed=9))
+        outs.append([h.detach(), xn.grad] + [p.grad for p in pg])
+    for a, b in zip(*outs):
+        check("c-loop", a, b, 1e-6)

@@ -68,6 +68,7 @@ struct GemmWxP {
   XformP xf;
   EpiP ep;
   void* ws; int64_t ws_bytes;   // optional workspace for the tcgen05 backend
+  int ws_presplit;              // tcgen05 backend: `ws` already holds this weight's hi / lo tiles (skip the split launch)
 };
 
 // tcgen05 backend (gemm_tc.cu)

@@ -587,7 +587,7 @@ int launch_gemm_wx_tc(const GemmWxP& p, bool a_trans, int pro, int epi, void* ws
   const int M32 = (p.M + 31) & ~31;
   float* whi = reinterpret_cast<float*>(ws);
   float* wlo = whi + (size_t)M32 * p.Kd;
-  {
+  if (!p.ws_presplit) {   // loops that reuse one weight (the LSTM recurrence) split it once and set ws_presplit
     int total = M32 * p.Kd;
     split_w_kernel<<<cdiv(total, 256), 256, 0, st>>>(p.W, p.ldw, a_trans ? 1 : 0, p.M, p.Kd, whi, wlo);
     WB_LAUNCH_CHECK("split_w");

@@ -6,6 +6,8 @@ tape.  All arithmetic on the hot path runs in libwesep_b200.so; there is no fall
 Activation layout ("act"): fp32 ``[n, C, T]`` views of ``[n, C, ld]`` storage with the time
 axis contiguous and ``ld = ceil32(T)`` so every row is a whole number of 128-byte TMA atoms (6399 frames -> 6400).
 """
+import os
+
 import torch
 
 from . import _lib
@@ -864,7 +866,8 @@ class LstmTmFn(torch.autograd.Function):
         H = new_act(S, 2 * Hd, Q, dev)
         Cs = new_act(S, 2 * Hd, Q, dev)
         st = _stream()
-        for d in range(2):
+        c_loop = os.environ.get("WESEP_LSTM_C_LOOP") == "1"   # EXPERIMENTAL (not validated on a GPU yet): time loop in C
+        for d in range(2 if not c_loop else 0):
             prev = None
             for s in (range(S) if d == 0 else range(S - 1, -1, -1)):
                 Gs = G[s:s + 1, 4 * Hd * d:4 * Hd * (d + 1)]
@@ -874,6 +877,13 @@ class LstmTmFn(torch.autograd.Function):
                           _cell_args(Gs, None if prev is None else Cs[prev:prev + 1, Hd * d:Hd * (d + 1)],
                                      Cs[s:s + 1, Hd * d:Hd * (d + 1)], h=H[s:s + 1, Hd * d:Hd * (d + 1)]), st)
                 prev = s
+        if c_loop:
+            ws = gemm_ws(dev)
+            for d in range(2):
+                _lib.call("wesep_b200_lstm_seq_fwd",
+                          _args("WesepLstmSeqArgs", S=S, Q=Q, Hd=Hd, reverse=d, ld=G.stride(1), bsG=G.stride(0), bsH=H.stride(0),
+                                G=G[:, 4 * Hd * d:4 * Hd * (d + 1)], H=H[:, Hd * d:Hd * (d + 1)], C=Cs[:, Hd * d:Hd * (d + 1)],
+                                Whh=whh[d], ws=ws, ws_bytes=ws.numel()), st)
         ctx.save_for_backward(xn, Wih, whh[0], whh[1], G, Cs, H)
         return H
 
@@ -888,7 +898,15 @@ class LstmTmFn(torch.autograd.Function):
         dc = [new_act(1, Hd, Q, dev), new_act(1, Hd, Q, dev)]
         st = _stream()
         whh = (whh_f, whh_b)
-        for d in range(2):
+        c_loop = os.environ.get("WESEP_LSTM_C_LOOP") == "1"
+        if c_loop:
+            ws = gemm_ws(dev)
+            for d in range(2):
+                _lib.call("wesep_b200_lstm_seq_bwd",
+                          _args("WesepLstmSeqArgs", S=S, Q=Q, Hd=Hd, reverse=d, ld=G.stride(1), bsG=G.stride(0), bsH=H.stride(0),
+                                G=G[:, 4 * Hd * d:4 * Hd * (d + 1)], H=H[:, Hd * d:Hd * (d + 1)], C=Cs[:, Hd * d:Hd * (d + 1)],
+                                Whh=whh[d], dH=dH[:, Hd * d:Hd * (d + 1)], dc0=dc[0], dc1=dc[1], ws=ws, ws_bytes=ws.numel()), st)
+        for d in range(2 if not c_loop else 0):
             order = list(range(S)) if d == 0 else list(range(S - 1, -1, -1))
             dc_in = None
             for k in range(S - 1, -1, -1):             # reverse of the forward order of this direction
