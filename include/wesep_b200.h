@@ -394,22 +394,25 @@ typedef struct {
 int wesep_b200_lstm_cell_fwd(const WesepLstmCellArgs* a, void* stream);
 int wesep_b200_lstm_cell_bwd(const WesepLstmCellArgs* a, void* stream);
 
-/* The whole time loop of ONE LSTM direction in one call (time-major tensors, see above): for every step the recurrent
- * GEMM G_s += W_hh . h_prev (conv1x1, in place on the step's gate block) and the cell.  fwd fills H / C and leaves the gate
- * activations in G; bwd turns G into d(pre-activations) and accumulates the recurrent gradient into dH in place.
- * EXPERIMENTAL (round 2): the Python host drives the loop step by step unless WESEP_LSTM_C_LOOP=1. */
+/* The LSTM recurrence of a bidirectional layer as ONE persistent cluster kernel per pass (time-major tensors, see above):
+ * replaces the recurrent half of nn.LSTM inside ResRNN (wesep/models/bsrnn.py:25-31,41-44); the input projection
+ * W_ih x + b_ih + b_hh of both directions is a GEMM done beforehand into G.  A cluster of Hd / 32 CTAs keeps W_hh (split
+ * fp16 hi / lo, per-row scaled) resident in distributed shared memory for all S steps, runs the per-step product on
+ * tcgen05 and exchanges h_t through DSMEM.  fwd: G holds the gate pre-activations on entry and the gate activations on
+ * return, H / C receive h_t / c_t.  bwd: G (activations) is overwritten by d(pre-activations); dH holds dL/dh_t from the
+ * layers above on entry (read only; the recurrent contribution stays inside the kernel).
+ * Supported: Hd = 32 * (1..8)  (wesep_b200_lstm_rec_supported). */
 typedef struct {
-  int S, Q, Hd, reverse;    /* reverse = 1: the direction that runs from the last step to the first */
-  int64_t ld;               /* row stride (floats) of every tensor below */
-  int64_t bsG, bsH;         /* step strides: G blocks are [4*Hd][ld] every bsG floats; H / C / dH blocks [Hd][ld] every bsH */
+  int S, Q, Hd;             /* steps, sequences (columns), hidden units per direction */
+  int64_t ld;               /* row stride (floats) of every tensor below, multiple of 4, >= Q */
+  int64_t bsG, bsH;         /* step strides: G blocks [8*Hd][ld] (forward dir rows [0,4Hd), reverse [4Hd,8Hd)); H / C / dH blocks [2*Hd][ld] */
   float* G; float* H; float* C;
-  const float* Whh;         /* [4*Hd][Hd] */
-  float* dH;                /* bwd only */
-  float* dc0; float* dc1;   /* bwd only: two [Hd][ld] scratch buffers */
-  void* ws; int64_t ws_bytes;
-} WesepLstmSeqArgs;
-int wesep_b200_lstm_seq_fwd(const WesepLstmSeqArgs* a, void* stream);
-int wesep_b200_lstm_seq_bwd(const WesepLstmSeqArgs* a, void* stream);
+  const float* Whh_f; const float* Whh_r;   /* [4*Hd][Hd] each, nn.LSTM weight_hh_l0 / weight_hh_l0_reverse */
+  const float* dH;          /* bwd only */
+} WesepLstmRecArgs;
+int wesep_b200_lstm_rec_supported(int Hd);
+int wesep_b200_lstm_rec_fwd(const WesepLstmRecArgs* a, void* stream);
+int wesep_b200_lstm_rec_bwd(const WesepLstmRecArgs* a, void* stream);
 
 /* y = ra[n][c] * x + rb[n][c] (NULL = 1 / 0): SpeakerFuseLayer multiply / additive with the Linear hoisted out of the
  * (band, frame) loop (wesep/modules/common/speaker.py:103-121).  bwd: dx = ra * gy, dra = sum_t gy * x, drb = sum_t gy. */

@@ -166,24 +166,35 @@ def test_bsrnn_golden_recipe_size_forward():
     _golden_case("bsrnn_full_fwd_1s", backward=False)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("WESEP_TEST_EXPERIMENTAL") != "1",
-                    reason="wesep_b200_lstm_seq_* (time loop in C) has not been validated on a GPU yet; opt in with "
-                           "WESEP_TEST_EXPERIMENTAL=1")
-def test_blstm_c_loop_matches_python_loop(monkeypatch):
-    """EXPERIMENTAL: the whole time loop of a direction in one C call must reproduce the step-by-step host loop."""
+@pytest.mark.parametrize("Q,C,S,Hd", [(5, 16, 3, 32), (64, 32, 7, 64), (100, 16, 6, 128), (130, 128, 33, 256), (512, 128, 9, 256)])
+def test_lstm_rec_matches_step_loop(Q, C, S, Hd, monkeypatch):
+    """The persistent cluster recurrence (wesep_b200_lstm_rec_fwd / _bwd) vs the step-by-step path (one fp32-grade GEMM +
+    one cell kernel per step) on the same inputs: h, dx and every parameter gradient."""
     from wesep_b200 import ops
-    Q, C, S, Hd = 33, 32, 12, 64
     xs = rnd(S, C, Q, seed=1)
     ps = _lstm_params(C, Hd, 5)
+    g = rnd(S, 2 * Hd, Q, seed=9)
     outs = []
     for flag in ("0", "1"):
-        monkeypatch.setenv("WESEP_LSTM_C_LOOP", flag)
+        monkeypatch.setenv("WESEP_LSTM_REC", flag)
         xn = ops.new_act(S, C, Q, DEV)
         xn.copy_(xs)
         xn.requires_grad_(True)
         pg = [p.clone().requires_grad_(True) for p in ps]
         h = ops.LstmTmFn.apply(xn, *pg)
-        h.backward(rnd(S, 2 * Hd, Q, seed=9))
+        h.backward(g)
         outs.append([h.detach(), xn.grad] + [p.grad for p in pg])
-    for a, b in zip(*outs):
-        check("c-loop", a, b, 1e-6)
+    names = ["h", "dx"] + ["w_ih", "w_hh", "b_ih", "b_hh"] * 2
+    for nm, a, b in zip(names, *outs):
+        check(nm, b, a.double(), 2e-5 if nm == "h" else 1e-4)
+
+
+def test_lstm_second_backward_raises():
+    from wesep_b200 import ops
+    xn = ops.new_act(3, 8, 4, DEV)
+    xn.copy_(rnd(3, 8, 4, seed=1))
+    xn.requires_grad_(True)
+    h = ops.LstmTmFn.apply(xn, *[p.requires_grad_(True) for p in _lstm_params(8, 32, 5)])
+    h.sum().backward(retain_graph=True)
+    with pytest.raises(RuntimeError):
+        h.sum().backward()

@@ -271,60 +271,3 @@ extern "C" int wesep_b200_mask_apply_bwd(const WesepMaskApplyArgs* a, void* stre
   WB_LAUNCH_CHECK("mask_apply_bwd");
   return 0;
 }
-
-// ------------------------------------------------------------------------------------ LSTM time loop in one call
-// EXPERIMENTAL: same launches as the Python-driven loop of ops.LstmTmFn (one conv1x1 GEMM + one cell kernel per step), but
-// issued from C and with W_hh split once for the whole sequence.
-static int lstm_seq(const WesepLstmSeqArgs* a, bool bwd, cudaStream_t st) {
-  if (a->S <= 0 || a->Q <= 0 || a->Hd <= 0 || (a->ld & 3) || a->ld < a->Q) return fail(-1, "lstm_seq: shape");
-  if (!a->G || !a->H || !a->C || !a->Whh || (bwd && (!a->dH || !a->dc0 || !a->dc1))) return fail(-1, "lstm_seq: pointers");
-  const int Hd = a->Hd;
-  bool split_done = false;
-  auto gemm = [&](const float* X, const float* W, bool w_trans, int M, int Kd, float* Y) -> int {
-    GemmWxP p{};
-    p.n = 1; p.M = M; p.Kd = Kd; p.T = a->Q;
-    p.W = W; p.ldw = Hd;                       // W_hh is [4Hd][Hd] in both uses
-    p.X = X; p.ldx = a->ld; p.bsx = (int64_t)Kd * a->ld;
-    p.ep.Y = Y; p.ep.ldy = a->ld; p.ep.bsy = (int64_t)M * a->ld;
-    p.ep.R = Y; p.ep.ldr = a->ld; p.ep.bsr = (int64_t)M * a->ld;
-    p.ws = a->ws; p.ws_bytes = a->ws_bytes;
-    p.ws_presplit = split_done ? 1 : 0;        // honoured by the tcgen05 path only; the first launch splits
-    if (int rc = launch_gemm_wx(p, w_trans, 0, 2, st)) return rc;
-    split_done = true;
-    return 0;
-  };
-  auto cell = [&](float* G, const float* c_prev, float* c, float* h, const float* dh, const float* dc_in, float* dc_prev) -> int {
-    WesepLstmCellArgs ca{};
-    ca.Hd = Hd; ca.Q = a->Q; ca.ld = a->ld;
-    ca.G = G; ca.c_prev = c_prev; ca.c = c; ca.h = h; ca.dh = dh; ca.dc_in = dc_in; ca.dc_prev = dc_prev;
-    return bwd ? wesep_b200_lstm_cell_bwd(&ca, st) : wesep_b200_lstm_cell_fwd(&ca, st);
-  };
-  auto step_of = [&](int k) { return a->reverse ? a->S - 1 - k : k; };   // k-th step in processing order
-  if (!bwd) {
-    for (int k = 0; k < a->S; ++k) {
-      const int s = step_of(k), prev = k > 0 ? step_of(k - 1) : -1;
-      float* Gs = a->G + (int64_t)s * a->bsG;
-      if (prev >= 0)
-        if (int rc = gemm(a->H + (int64_t)prev * a->bsH, a->Whh, false, 4 * Hd, Hd, Gs)) return rc;
-      if (int rc = cell(Gs, prev >= 0 ? a->C + (int64_t)prev * a->bsH : nullptr, a->C + (int64_t)s * a->bsH,
-                        a->H + (int64_t)s * a->bsH, nullptr, nullptr, nullptr))
-        return rc;
-    }
-    return 0;
-  }
-  const float* dc_in = nullptr;
-  for (int k = a->S - 1; k >= 0; --k) {
-    const int s = step_of(k), prev = k > 0 ? step_of(k - 1) : -1;
-    float* Gs = a->G + (int64_t)s * a->bsG;
-    float* dc_out = (k & 1) ? a->dc1 : a->dc0;
-    if (int rc = cell(Gs, prev >= 0 ? a->C + (int64_t)prev * a->bsH : nullptr, a->C + (int64_t)s * a->bsH, nullptr,
-                      a->dH + (int64_t)s * a->bsH, dc_in, dc_out))
-      return rc;
-    if (prev >= 0)   // dL/dh_prev += W_hh^T . d(gates_s)
-      if (int rc = gemm(Gs, a->Whh, true, Hd, 4 * Hd, a->dH + (int64_t)prev * a->bsH)) return rc;
-    dc_in = dc_out;
-  }
-  return 0;
-}
-extern "C" int wesep_b200_lstm_seq_fwd(const WesepLstmSeqArgs* a, void* stream) { return lstm_seq(a, false, (cudaStream_t)stream); }
-extern "C" int wesep_b200_lstm_seq_bwd(const WesepLstmSeqArgs* a, void* stream) { return lstm_seq(a, true, (cudaStream_t)stream); }

@@ -849,9 +849,12 @@ def _cell_args(G, c_prev, c, h=None, dh=None, dc_in=None, dc_prev=None):
 class LstmTmFn(torch.autograd.Function):
     """Bidirectional single-layer nn.LSTM (wesep/models/bsrnn.py:25-31) on a TIME-MAJOR act tensor xn [S, C, Q]
     (rows = time steps, columns = sequences) -> h [S, 2*Hd, Q] (forward direction in channels [0, Hd), backward in
-    [Hd, 2*Hd)).  Input projection of both directions = one GEMM; every step of the recurrence = one conv1x1 GEMM
-    (W_hh . h_{s-1}, accumulated onto the step's slice of the input projection) + the cell kernel.  The gate
-    activations overwrite the pre-activations and are what the backward (BPTT, same two launches per step) consumes."""
+    [Hd, 2*Hd)).  Input projection of both directions = one GEMM.  The recurrence of both directions and all S steps is
+    ONE persistent cluster kernel (`wesep_b200_lstm_rec_fwd`: W_hh resident in distributed shared memory, tcgen05 step
+    product, h exchanged over DSMEM) when Hd = 32 * (1..8); other sizes take the step-by-step path (one conv1x1 GEMM +
+    one cell kernel per step).  The gate activations overwrite the pre-activations and are what the backward (BPTT,
+    `wesep_b200_lstm_rec_bwd`) consumes — it overwrites them in turn with d(pre-activations), so a second backward over
+    the same graph raises."""
 
     @staticmethod
     def forward(ctx, xn, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_b, w_hh_b, b_ih_b, b_hh_b):
@@ -866,8 +869,12 @@ class LstmTmFn(torch.autograd.Function):
         H = new_act(S, 2 * Hd, Q, dev)
         Cs = new_act(S, 2 * Hd, Q, dev)
         st = _stream()
-        c_loop = os.environ.get("WESEP_LSTM_C_LOOP") == "1"   # EXPERIMENTAL (not validated on a GPU yet): time loop in C
-        for d in range(2 if not c_loop else 0):
+        rec = lstm_rec_supported(Hd)
+        if rec:
+            _lib.call("wesep_b200_lstm_rec_fwd",
+                      _args("WesepLstmRecArgs", S=S, Q=Q, Hd=Hd, ld=G.stride(1), bsG=G.stride(0), bsH=H.stride(0), G=G, H=H,
+                            C=Cs, Whh_f=whh[0], Whh_r=whh[1]), st)
+        for d in range(0 if rec else 2):
             prev = None
             for s in (range(S) if d == 0 else range(S - 1, -1, -1)):
                 Gs = G[s:s + 1, 4 * Hd * d:4 * Hd * (d + 1)]
@@ -877,36 +884,33 @@ class LstmTmFn(torch.autograd.Function):
                           _cell_args(Gs, None if prev is None else Cs[prev:prev + 1, Hd * d:Hd * (d + 1)],
                                      Cs[s:s + 1, Hd * d:Hd * (d + 1)], h=H[s:s + 1, Hd * d:Hd * (d + 1)]), st)
                 prev = s
-        if c_loop:
-            ws = gemm_ws(dev)
-            for d in range(2):
-                _lib.call("wesep_b200_lstm_seq_fwd",
-                          _args("WesepLstmSeqArgs", S=S, Q=Q, Hd=Hd, reverse=d, ld=G.stride(1), bsG=G.stride(0), bsH=H.stride(0),
-                                G=G[:, 4 * Hd * d:4 * Hd * (d + 1)], H=H[:, Hd * d:Hd * (d + 1)], C=Cs[:, Hd * d:Hd * (d + 1)],
-                                Whh=whh[d], ws=ws, ws_bytes=ws.numel()), st)
         ctx.save_for_backward(xn, Wih, whh[0], whh[1], G, Cs, H)
+        ctx.rec = rec
+        ctx.consumed = False
         return H
 
     @staticmethod
     def backward(ctx, gH):
+        if ctx.consumed:
+            raise RuntimeError("LstmTmFn: the saved gate activations were overwritten by the first backward; "
+                               "a second backward over the same graph is not supported")
+        ctx.consumed = True
         xn, Wih, whh_f, whh_b, G, Cs, H = ctx.saved_tensors
         S, C, Q = xn.shape
         Hd = whh_f.shape[1]
         dev = xn.device
-        dH = new_act(S, 2 * Hd, Q, dev)
-        dH.copy_(gH)                                   # accumulated in place below: never touch autograd's tensor
-        dc = [new_act(1, Hd, Q, dev), new_act(1, Hd, Q, dev)]
         st = _stream()
         whh = (whh_f, whh_b)
-        c_loop = os.environ.get("WESEP_LSTM_C_LOOP") == "1"
-        if c_loop:
-            ws = gemm_ws(dev)
-            for d in range(2):
-                _lib.call("wesep_b200_lstm_seq_bwd",
-                          _args("WesepLstmSeqArgs", S=S, Q=Q, Hd=Hd, reverse=d, ld=G.stride(1), bsG=G.stride(0), bsH=H.stride(0),
-                                G=G[:, 4 * Hd * d:4 * Hd * (d + 1)], H=H[:, Hd * d:Hd * (d + 1)], C=Cs[:, Hd * d:Hd * (d + 1)],
-                                Whh=whh[d], dH=dH[:, Hd * d:Hd * (d + 1)], dc0=dc[0], dc1=dc[1], ws=ws, ws_bytes=ws.numel()), st)
-        for d in range(2 if not c_loop else 0):
+        if ctx.rec:
+            gH = as_act(gH)
+            _lib.call("wesep_b200_lstm_rec_bwd",
+                      _args("WesepLstmRecArgs", S=S, Q=Q, Hd=Hd, ld=G.stride(1), bsG=G.stride(0), bsH=H.stride(0), G=G, H=H,
+                            C=Cs, Whh_f=whh[0], Whh_r=whh[1], dH=gH), st)
+        else:
+            dH = new_act(S, 2 * Hd, Q, dev)
+            dH.copy_(gH)                               # accumulated in place below: never touch autograd's tensor
+            dc = [new_act(1, Hd, Q, dev), new_act(1, Hd, Q, dev)]
+        for d in range(0 if ctx.rec else 2):
             order = list(range(S)) if d == 0 else list(range(S - 1, -1, -1))
             dc_in = None
             for k in range(S - 1, -1, -1):             # reverse of the forward order of this direction
@@ -932,6 +936,14 @@ class LstmTmFn(torch.autograd.Function):
             conv1x1_dw_raw(G[:-1, 4 * Hd:], H[1:, Hd:], dWhh[1])
         dxn = conv1x1_raw(G, Wih, True, C)
         return (dxn, dWih[:4 * Hd], dWhh[0], db[:4 * Hd], db[:4 * Hd], dWih[4 * Hd:], dWhh[1], db[4 * Hd:], db[4 * Hd:])
+
+
+def lstm_rec_supported(Hd):
+    """True when the persistent cluster recurrence covers this hidden size (WESEP_LSTM_REC=0 forces the step-by-step path:
+    A/B tests only)."""
+    if os.environ.get("WESEP_LSTM_REC") == "0":
+        return False
+    return bool(_lib.lib().wesep_b200_lstm_rec_supported(int(Hd)))
 
 
 _ONE = {}
