@@ -401,7 +401,7 @@ int wesep_b200_lstm_cell_bwd(const WesepLstmCellArgs* a, void* stream);
  * tcgen05 and exchanges h_t through DSMEM.  fwd: G holds the gate pre-activations on entry and the gate activations on
  * return, H / C receive h_t / c_t.  bwd: G (activations) is overwritten by d(pre-activations); dH holds dL/dh_t from the
  * layers above on entry (read only; the recurrent contribution stays inside the kernel).
- * Supported: Hd = 32 * (1..8)  (wesep_b200_lstm_rec_supported). */
+ * Supported: Hd in {32, 64, 128, 192, 256}  (wesep_b200_lstm_rec_supported). */
 typedef struct {
   int S, Q, Hd;             /* steps, sequences (columns), hidden units per direction */
   int64_t ld;               /* row stride (floats) of every tensor below, multiple of 4, >= Q */
@@ -409,8 +409,11 @@ typedef struct {
   float* G; float* H; float* C;
   const float* Whh_f; const float* Whh_r;   /* [4*Hd][Hd] each, nn.LSTM weight_hh_l0 / weight_hh_l0_reverse */
   const float* dH;          /* bwd only */
+  int seqs_per_cluster;     /* 0 = automatic; 32 / 64 / 128 force the grouping (tests, tuning) */
+  void* prof;               /* optional (NULL = off): int64 [16][16] SM-clock stamps of cluster 0 for 16 steps (tools/time_lstm_rec.py) */
 } WesepLstmRecArgs;
 int wesep_b200_lstm_rec_supported(int Hd);
+int wesep_b200_lstm_rec_max_clusters(int Hd, int bwd);   /* co-resident clusters on the current device (-1: query failed) */
 int wesep_b200_lstm_rec_fwd(const WesepLstmRecArgs* a, void* stream);
 int wesep_b200_lstm_rec_bwd(const WesepLstmRecArgs* a, void* stream);
 

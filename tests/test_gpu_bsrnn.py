@@ -166,8 +166,10 @@ def test_bsrnn_golden_recipe_size_forward():
     _golden_case("bsrnn_full_fwd_1s", backward=False)
 
 
-@pytest.mark.parametrize("Q,C,S,Hd", [(5, 16, 3, 32), (64, 32, 7, 64), (100, 16, 6, 128), (130, 128, 33, 256), (512, 128, 9, 256)])
-def test_lstm_rec_matches_step_loop(Q, C, S, Hd, monkeypatch):
+@pytest.mark.parametrize("seqs", [0, 32, 64, 128])
+@pytest.mark.parametrize("Q,C,S,Hd", [(5, 16, 3, 32), (64, 32, 7, 64), (100, 16, 6, 128), (70, 24, 5, 192), (130, 128, 33, 256),
+                                      (512, 128, 9, 256)])
+def test_lstm_rec_matches_step_loop(Q, C, S, Hd, seqs, monkeypatch):
     """The persistent cluster recurrence (wesep_b200_lstm_rec_fwd / _bwd) vs the step-by-step path (one fp32-grade GEMM +
     one cell kernel per step) on the same inputs: h, dx and every parameter gradient."""
     from wesep_b200 import ops
@@ -175,6 +177,7 @@ def test_lstm_rec_matches_step_loop(Q, C, S, Hd, monkeypatch):
     ps = _lstm_params(C, Hd, 5)
     g = rnd(S, 2 * Hd, Q, seed=9)
     outs = []
+    monkeypatch.setenv("WESEP_LSTM_REC_SEQS", str(seqs))
     for flag in ("0", "1"):
         monkeypatch.setenv("WESEP_LSTM_REC", flag)
         xn = ops.new_act(S, C, Q, DEV)

@@ -2,23 +2,27 @@
 //
 // The recurrence a_t = P_t + W_hh . h_{t-1} (P = input projection + biases, one big GEMM done beforehand) is serial in t
 // but independent across sequences, so ONE launch runs all S steps of both directions:
-//   * a cluster of C = Hd / 32 CTAs owns a group of NQ = 64 sequences of one direction for the whole sequence;
-//   * CTA `rank` owns hidden units [32 rank, 32 rank + 32) = 128 gate rows (i | f | g | o blocks of 32) and keeps ITS
-//     [128 x Hd] slice of W_hh resident in shared memory for all steps, split into fp16 hi + lo with a per-row power-of-two
-//     scale (22 mantissa bits; the scale is undone exactly in the epilogue);
-//   * per step it issues D[128 gate rows][64 seqs] = W_slice . h_{t-1} on tcgen05 (kind::f16, M = 128, N = 64, K = Hd,
-//     three products hi.hi + hi.lo + lo.hi, fp32 accumulate in TMEM), adds P_t, runs the cell for its 32 units and
-//     writes the gate activations / c_t / h_t the backward needs;
-//   * h_t (|h| < 1, scaled by 2^12 and split into fp16 hi + lo) is the next step's B operand: the CTA writes its
-//     [64 seqs x 32 units] slab into its own operand buffer and bulk-copies it (cp.async.bulk shared::cta ->
-//     shared::cluster, completing transaction bytes on the receiver's mbarrier) into the other C - 1 CTAs — the
-//     all-gather of h over distributed shared memory; a multicast tcgen05.commit tells every CTA of the cluster when a
-//     CTA's MMAs have finished reading its operand buffer, so it may be overwritten.
-// The backward (BPTT) mirrors it with W_hh^T: each CTA contracts over ITS 128 gate rows (K = 128, M = Hd) and the
-// partial dh is reduce-scattered over DSMEM (bf16 hi + lo operands: gradients need the fp32 exponent range).
+//   * a cluster of C = Hd / 32 CTAs owns NG groups of NQ = 32 NB sequences of one direction for the whole sequence;
+//   * CTA `rank` owns hidden units [32 rank, 32 rank + 32) = 128 gate rows (i | f | g | o blocks of 32).  ITS [128 x Hd]
+//     slice of W_hh stays resident in TENSOR MEMORY for all steps as the A operand of the step product (fp16 hi + lo with a
+//     per-row power-of-two scale: 22 mantissa bits, undone exactly in the epilogue) — shared memory then only holds the
+//     h operand, and the MMA reads 2 KB instead of 6 KB of shared memory per instruction;
+//   * per step and group: D[128 gate rows][NQ seqs] = W_slice . h_{t-1} on tcgen05 (kind::f16, M = 128, N = NQ, K = Hd,
+//     three products hi.hi + hi.lo + lo.hi, fp32 accumulate in TMEM); the 8 cell warps move D through a swizzled staging
+//     tile (lane = gate row -> lane = sequence), add P_t, run the cell for the CTA's 32 units and write the gate
+//     activations / c_t / h_t the backward needs (all global accesses coalesced along the sequence axis);
+//   * h_t (|h| < 1, scaled by 2^12, fp16 hi + lo) is the next step's B operand: the CTA writes its [NQ x 32 units] slab into
+//     its own operand buffer and bulk-copies it (cp.async.bulk shared::cta -> shared::cluster, completing transaction
+//     bytes on the receiver's mbarrier) into the other C - 1 CTAs — the all-gather of h over distributed shared memory; a
+//     multicast tcgen05.commit tells every CTA of the cluster when a CTA's MMAs have finished reading its operand buffer;
+//   * with NG = 2 the two groups are independent recurrences interleaved on the same CTA: the MMAs of one group run
+//     while the cell warps work on the other (the per-step dependency chain MMA -> cell -> exchange is latency-bound).
+// The backward (BPTT) mirrors it with W_hh^T (bf16 hi + lo in tensor memory: gradients need the fp32 exponent range):
+// each CTA contracts over ITS 128 gate rows (K = 128, M = Hd) with the d(pre-activations) it has just computed, and the
+// partial dh is reduce-scattered over DSMEM (coalesced st.shared::cluster), summed in a fixed order.
 //
 // Tensor layout (time-major act tensors of ops.LstmTmFn): G [S][8 Hd][ld] (forward direction rows [0, 4Hd), reverse
-// [4Hd, 8Hd); within a direction i | f | g | o blocks of Hd rows), H / C [S][2 Hd][ld]; columns = sequences.
+// [4Hd, 8Hd); within a direction i | f | g | o blocks of Hd rows), H / C / dH [S][2 Hd][ld]; columns = sequences.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -29,229 +33,369 @@ namespace wb {
 namespace lr {
 using namespace tcx;
 
-constexpr int NQ = 64;                 // sequences per cluster
-constexpr int ROWS = 128;              // gate rows per CTA (4 gates x 32 hidden units)
 constexpr int MAXC = 8;                // cluster size = Hd / 32
-constexpr int THREADS = 160;           // warps 0-3: epilogue / cell (TMEM lane quarters), warp 4: MMA issuer + TMEM owner
-constexpr int SLAB_W = ROWS * 64;      // 8192 B: one K block (32 hidden units) of the weight slice, hi or lo
-constexpr int SLAB_H = NQ * 64;        // 4096 B: one K block of h, hi or lo
+constexpr int THREADS = 288;           // warps 0-7: TMEM drain / cell, warp 8: MMA issuer + TMEM owner
+constexpr int EPI_THREADS = 256;
 constexpr float H_SCALE = 4096.f;      // h in (-1, 1) -> fp16 hi + lo of 4096 h
-constexpr int OFF_WHI = 0;
-constexpr int OFF_WLO = MAXC * SLAB_W;                 // 65536
-constexpr int OFF_H = 2 * MAXC * SLAB_W;               // 131072: C x [hi slab | lo slab]
-constexpr int OFF_STG = OFF_H + MAXC * 2 * SLAB_H;     // 196608: [128 rows][64 seqs] fp32, 16-byte chunks XOR-swizzled by row
-constexpr int OFF_RS = OFF_STG + ROWS * NQ * 4;        // 229376: per-row descale
-constexpr int OFF_BAR = OFF_RS + ROWS * 4;             // 229888
-constexpr int SMEM_BYTES = OFF_BAR + 64 + 1024;        // + alignment slack
-constexpr uint32_t IDESC_FWD = idesc_f16(128, NQ, 0);
+constexpr float LOG2E = 1.4426950408889634f;
+
+__host__ __device__ constexpr uint32_t pow2_cols(int need) {
+  return need <= 32 ? 32u : need <= 64 ? 64u : need <= 128 ? 128u : need <= 256 ? 256u : 512u;
+}
+
+template <int C, int NB, int NG>
+struct FwdCfg {
+  static constexpr int NQ = 32 * NB;                 // sequences per group
+  static constexpr int SLAB = NQ * 64;               // one K block (32 hidden units) of a group's h, hi or lo
+  static constexpr int HBUF = C * 2 * SLAB;          // operand buffer of one group: C x [hi slab | lo slab]
+  static constexpr int OFF_H = 0;
+  static constexpr int OFF_STG = NG * HBUF;          // [128 rows][NQ] fp32, 16-byte chunks XOR-swizzled by row
+  static constexpr int OFF_RS = OFF_STG + 128 * NQ * 4;
+  static constexpr int OFF_BAR = OFF_RS + 512;
+  static constexpr int SMEM = OFF_BAR + 128 + 1024;  // + alignment slack
+  static constexpr int COL_WHI = 0, COL_WLO = 16 * C, COL_D = 32 * C;   // TMEM columns
+  static constexpr uint32_t TCOLS = pow2_cols(32 * C + NG * NQ);
+};
 
 struct FwdParams {
   float* G; float* H; float* Cs;
   const float* Whh[2];
-  int S, Q, Hd, C;
+  int S, Q, Hd;
   int64_t ld, bsG, bsH;
+  long long* prof;
 };
 
-__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+// optional per-phase SM-clock stamps of CTA 0 (group 0) for steps [PROF_T0, PROF_T0 + PROF_N): prof[(t - T0) * 16 + slot]
+constexpr int PROF_T0 = 8, PROF_N = 16;
+#define LR_STAMP(slot)                                                                                            \
+  do {                                                                                                            \
+    if (p.prof && blockIdx.x == 0 && g == 0 && t >= PROF_T0 && t < PROF_T0 + PROF_N)                              \
+      p.prof[(t - PROF_T0) * 16 + (slot)] = clock64();                                                            \
+  } while (0)
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcpf(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+  return y;
+}
 // 1 - 2 / (1 + e^{2x}): two MUFU ops, absolute error ~1e-7 (saturates correctly at +-inf)
-__device__ __forceinline__ float tanh_fast(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return 1.f - 2.f * rcpf(1.f + ex2f(x * (2.f * LOG2E))); }
+// The four gate activations with ONE reciprocal: 1 / (1 + e_k) = (prod of the other three denominators) / (prod of all four).
+// Inputs are clamped to +-20 (sigma(-20) = 2e-9, tanh(10) = 1 - 4e-9: below fp32 resolution of the results) so that the
+// product of four denominators (<= (1 + e^20)^4 = 5.5e34) cannot overflow.  5 MUFU ops instead of 8.
+__device__ __forceinline__ void gates_fast(float ai, float af, float ag, float ao, float& i_, float& f_, float& g_, float& o_) {
+  const float di = 1.f + ex2f(fminf(fmaxf(-ai, -20.f), 20.f) * LOG2E);
+  const float df = 1.f + ex2f(fminf(fmaxf(-af, -20.f), 20.f) * LOG2E);
+  const float dO = 1.f + ex2f(fminf(fmaxf(-ao, -20.f), 20.f) * LOG2E);
+  const float dg = 1.f + ex2f(fminf(fmaxf(2.f * ag, -20.f), 20.f) * LOG2E);
+  const float pif = di * df, pog = dO * dg;
+  const float r = rcpf(pif * pog);
+  const float rp = r * pif, rq = r * pog;
+  i_ = rq * df;
+  f_ = rq * di;
+  o_ = rp * dg;
+  g_ = fmaf(-2.f * rp, dO, 1.f);
+}
 
-__device__ __forceinline__ void named_sync_epi() { asm volatile("bar.sync 1, 128;\n" ::: "memory"); }
+__device__ __forceinline__ void named_sync_epi() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
 
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tc_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_ld16_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+// D[tmem] (+)= A[tmem] . B[smem]: A = [128 lanes = rows][K = 16: 8 columns of packed 16-bit pairs]
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void fence_cluster() { asm volatile("fence.acq_rel.cluster;\n" ::: "memory"); }
+
+// ================================================================================================ forward
+template <int C, int NB, int NG>
 __global__ void __launch_bounds__(THREADS, 1) lstm_rec_fwd_kernel(const FwdParams p) {
+  using K = FwdCfg<C, NB, NG>;
+  constexpr int NQ = K::NQ, SLAB = K::SLAB, HBUF = K::HBUF, Hd = 32 * C;
+  constexpr uint32_t IDESC = idesc_f16(128, NQ, 0);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int C = p.C, Hd = p.Hd;
   const uint32_t rank = cluster_ctarank();
   const int cid = blockIdx.x / C;
-  const int dir = cid & 1, grp = cid >> 1;
-  const int q0 = grp * NQ;
-  const uint32_t bar_hfull = base + OFF_BAR, bar_hfree = base + OFF_BAR + 8, bar_acc = base + OFF_BAR + 16;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + OFF_BAR + 24);
-  float* rs = reinterpret_cast<float*>(gbase + OFF_RS);
+  const int dir = cid & 1, cgrp = cid >> 1;
+  const int S = p.S;
+  auto bar_hfull = [&](int g) { return base + K::OFF_BAR + 8u * g; };
+  auto bar_hfree = [&](int g) { return base + K::OFF_BAR + 16u + 8u * g; };
+  auto bar_acc = [&](int g) { return base + K::OFF_BAR + 32u + 8u * g; };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + K::OFF_BAR + 48);
+  float* rs = reinterpret_cast<float*>(gbase + K::OFF_RS);
 
   if (tid == 0) {
-    mbar_init(bar_hfull, 1);
-    mbar_init(bar_hfree, C);
-    mbar_init(bar_acc, 1);
+    for (int g = 0; g < NG; ++g) {
+      mbar_init(bar_hfull(g), 1);
+      mbar_init(bar_hfree(g), C);
+      mbar_init(bar_acc(g), 1);
+    }
     mbar_init_fence();
   }
-  if (warp == 4) tmem_alloc<64>(smem_u32(tmem_slot));
+  if (warp == 8) tmem_alloc<K::TCOLS>(smem_u32(tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
 
-  // ---- resident weight slice: local row r = gate * 32 + j  <->  W_hh row gate * Hd + 32 rank + j; fp16 hi / lo with a
-  //      per-row scale 2^k such that max |w| 2^k is in [2^13, 2^14)
-  {
-    const float* W = p.Whh[dir];
-    for (int r = warp; r < ROWS; r += THREADS / 32) {
-      const float* wr = W + ((int64_t)(r >> 5) * Hd + 32 * rank + (r & 31)) * Hd;
-      float w[MAXC];
-      float mx = 0.f;
-#pragma unroll
-      for (int i = 0; i < MAXC; ++i) {
-        w[i] = i < C ? __ldg(wr + 32 * i + lane) : 0.f;
-        mx = fmaxf(mx, fabsf(w[i]));
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      int e = 0;
-      if (mx > 0.f) frexpf(mx, &e);
-      e = max(e, -100);
-      const float s = ldexpf(1.f, 14 - e);
-      if (lane == 0) rs[r] = ldexpf(1.f, e - 14 - 12);   // 1 / (s * H_SCALE)
-#pragma unroll
-      for (int i = 0; i < MAXC; ++i) {
-        if (i < C) {
-          const float ws = w[i] * s;
-          const __half hi = __float2half_rn(ws);
-          const __half lo = __float2half_rn(ws - __half2float(hi));
-          const uint32_t off = i * SLAB_W + sw64_off(r, lane >> 3) + (lane & 7) * 2;
-          *reinterpret_cast<__half*>(gbase + OFF_WHI + off) = hi;
-          *reinterpret_cast<__half*>(gbase + OFF_WLO + off) = lo;
-        }
-      }
+  // ---- resident weight slice -> TMEM: lane r = gate * 32 + j  <->  W_hh row gate * Hd + 32 rank + j; column c holds the
+  //      fp16 pair (k = 2c, 2c + 1); hi and lo of 2^e w with max |w| 2^e in [2^13, 2^14) per row
+  if (warp < 4) {
+    const int r = warp * 32 + lane;
+    const float* wr = p.Whh[dir] + ((int64_t)warp * Hd + 32 * rank + lane) * Hd;
+    float mx = 0.f;
+    for (int k = 0; k < Hd; k += 4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(wr + k));
+      mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
     }
+    int e = 0;
+    if (mx > 0.f) frexpf(mx, &e);
+    e = max(e, -100);
+    const float s = ldexpf(1.f, 14 - e);
+    rs[r] = ldexpf(1.f, e - 14 - 12);                       // 1 / (s * H_SCALE)
+    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+    for (int kc = 0; kc < C; ++kc) {                         // 32 k values -> 16 columns
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(wr + 32 * kc + 4 * i));
+        const float a0 = v.x * s, a1 = v.y * s, a2 = v.z * s, a3 = v.w * s;
+        const __half2 h01 = __floats2half2_rn(a0, a1), h23 = __floats2half2_rn(a2, a3);
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        const __half2 l01 = __floats2half2_rn(a0 - f01.x, a1 - f01.y), l23 = __floats2half2_rn(a2 - f23.x, a3 - f23.y);
+        hi[2 * i] = *reinterpret_cast<const uint32_t*>(&h01);
+        hi[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+        lo[2 * i] = *reinterpret_cast<const uint32_t*>(&l01);
+        lo[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&l23);
+      }
+      tc_st16(trow + K::COL_WHI + 16 * kc, hi);
+      tc_st16(trow + K::COL_WLO + 16 * kc, lo);
+    }
+    tc_st_wait();
   }
-  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();            // every CTA's barriers are initialised before any remote traffic
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const int S = p.S;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ================================================= MMA issuer
     if (lane == 0) {
       const uint16_t mask = (uint16_t)((1u << C) - 1u);
       for (int t = 1; t < S; ++t) {
-        mbar_wait(bar_hfull, (t - 1) & 1);      // h_{t-1}: own slab written + C - 1 slabs landed
-        tc_fence_after();
-        for (int kb = 0; kb < C; ++kb) {
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            const uint64_t a_hi = desc_k_sw64(base + OFF_WHI + kb * SLAB_W + half * 32);
-            const uint64_t a_lo = desc_k_sw64(base + OFF_WLO + kb * SLAB_W + half * 32);
-            const uint64_t b_hi = desc_k_sw64(base + OFF_H + kb * 2 * SLAB_H + half * 32);
-            const uint64_t b_lo = desc_k_sw64(base + OFF_H + kb * 2 * SLAB_H + SLAB_H + half * 32);
-            tc_mma_f16(tmem_base, a_lo, b_hi, IDESC_FWD, (kb | half) ? 1u : 0u);
-            tc_mma_f16(tmem_base, a_hi, b_lo, IDESC_FWD, 1u);
-            tc_mma_f16(tmem_base, a_hi, b_hi, IDESC_FWD, 1u);
+        for (int g = 0; g < NG; ++g) {
+          mbar_wait(bar_hfull(g), (t - 1) & 1);   // h_{t-1} of group g: own slab written + C - 1 slabs landed
+          tc_fence_after();
+          LR_STAMP(8);
+          const uint32_t d = tmem_base + K::COL_D + g * NQ;
+          const uint32_t hb = base + K::OFF_H + g * HBUF;
+#pragma unroll
+          for (int j = 0; j < 2 * C; ++j) {       // K step of 16: K block j / 2, half j % 2
+            const uint64_t b_hi = desc_k_sw64(hb + (j >> 1) * 2 * SLAB + (j & 1) * 32);
+            const uint64_t b_lo = desc_k_sw64(hb + (j >> 1) * 2 * SLAB + SLAB + (j & 1) * 32);
+            const uint32_t a_hi = tmem_base + K::COL_WHI + 8 * j, a_lo = tmem_base + K::COL_WLO + 8 * j;
+            tc_mma_f16_ts(d, a_lo, b_hi, IDESC, j ? 1u : 0u);
+            tc_mma_f16_ts(d, a_hi, b_lo, IDESC, 1u);
+            tc_mma_f16_ts(d, a_hi, b_hi, IDESC, 1u);
           }
+          tc_commit(bar_acc(g));                  // accumulator ready for the cell warps
+          tc_commit_mc(bar_hfree(g), mask);       // and this CTA has finished reading its h buffer: tell the whole cluster
+          LR_STAMP(9);
         }
-        tc_commit(bar_acc);                     // accumulator ready for the epilogue
-        tc_commit_mc(bar_hfree, mask);          // and this CTA has finished reading its h buffer: tell the whole cluster
       }
     }
     __syncwarp();
   } else {
-    // ================================================= epilogue / cell warps
-    const int sl = tid & 63, uh = tid >> 6;     // phase 2: this thread = sequence sl, hidden units [16 uh, 16 uh + 16) of the CTA
-    const int q = q0 + sl;
-    const bool inb = q < p.ld, valid = q < p.Q;
-    const int row_g0 = dir * 4 * Hd + 32 * (int)rank + 16 * uh;     // G row of (gate 0, unit 0 of this thread)
-    const int row_h0 = dir * Hd + 32 * (int)rank + 16 * uh;
-    float c[16];
+    // ================================================= TMEM drain + cell warps: warp w owns hidden units [4w, 4w + 4) of the
+    // CTA, lane = sequence within a 32-sequence block
+    const int u0 = 4 * warp;
+    const int row_g0 = dir * 4 * Hd + 32 * (int)rank + u0;     // G row of (gate 0, unit 0 of this thread)
+    const int row_h0 = dir * Hd + 32 * (int)rank + u0;
+    float c[NG][NB][4];
 #pragma unroll
-    for (int u = 0; u < 16; ++u) c[u] = 0.f;
-    const float* stg = reinterpret_cast<const float*>(gbase + OFF_STG);
+    for (int g = 0; g < NG; ++g)
+#pragma unroll
+      for (int b = 0; b < NB; ++b)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) c[g][b][k] = 0.f;
+    const float* stg = reinterpret_cast<const float*>(gbase + K::OFF_STG);
+    float nxt[NB][4][4];
+    auto load_pre = [&](int t, int g) {
+      const int s = dir ? S - 1 - t : t;
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        const int q = (cgrp * NG + g) * NQ + 32 * b + lane;
+        const float* Gs = p.G + (int64_t)s * p.bsG + (int64_t)row_g0 * p.ld + q;
+#pragma unroll
+        for (int gt = 0; gt < 4; ++gt)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) nxt[b][gt][k] = q < p.Q ? __ldcs(Gs + ((int64_t)gt * Hd + k) * p.ld) : 0.f;
+      }
+    };
+    load_pre(0, 0);
     for (int t = 0; t < S; ++t) {
       const int s = dir ? S - 1 - t : t;
-      float* Gs = p.G + (int64_t)s * p.bsG + (int64_t)row_g0 * p.ld + q;
-      float pre[4][16];
 #pragma unroll
-      for (int g = 0; g < 4; ++g)
+      for (int g = 0; g < NG; ++g) {
+        float pre[NB][4][4];
 #pragma unroll
-        for (int u = 0; u < 16; ++u) pre[g][u] = valid ? __ldcs(Gs + ((int64_t)g * Hd + u) * p.ld) : 0.f;
-      if (t > 0) {
-        mbar_wait(bar_acc, (t - 1) & 1);
-        tc_fence_after();
-        {   // phase 1: lane = gate row; TMEM -> registers -> descale -> staging (so that phase 2 can read by sequence)
-          const int r = warp * 32 + lane;
-          uint32_t acc[64];
-          const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
-          tc_ld32_nowait(taddr, acc);
-          tc_ld32_nowait(taddr + 32, acc + 32);
-          tc_ld_wait();
-          const float sc = rs[r];
-          uint8_t* row = gbase + OFF_STG + r * (NQ * 4);
+        for (int b = 0; b < NB; ++b)
 #pragma unroll
-          for (int ch = 0; ch < 16; ++ch) {
-            float4 v;
-            v.x = __uint_as_float(acc[4 * ch + 0]) * sc;
-            v.y = __uint_as_float(acc[4 * ch + 1]) * sc;
-            v.z = __uint_as_float(acc[4 * ch + 2]) * sc;
-            v.w = __uint_as_float(acc[4 * ch + 3]) * sc;
-            *reinterpret_cast<float4*>(row + ((ch ^ (r & 15)) << 4)) = v;
+          for (int gt = 0; gt < 4; ++gt)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) pre[b][gt][k] = nxt[b][gt][k];
+        if (tid == 0) LR_STAMP(0);
+        if (t > 0) {
+          mbar_wait(bar_acc(g), (t - 1) & 1);
+          tc_fence_after();
+          if (tid == 0) LR_STAMP(1);
+          {   // phase 1: lane = gate row; TMEM -> registers -> descale -> staging (so that phase 2 can read by sequence)
+            constexpr int NCOL = NQ / 2;               // warps w and w + 4 share a lane quarter and split the columns
+            const int r = (warp & 3) * 32 + lane, c0 = (warp >> 2) * NCOL;
+            uint32_t acc[NCOL];
+            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + K::COL_D + g * NQ + c0;
+            if constexpr (NCOL == 32) tc_ld32_nowait(taddr, acc);
+            else tc_ld16_nowait(taddr, acc);
+            tc_ld_wait();
+            const float sc = rs[r];
+            uint8_t* row = gbase + K::OFF_STG + r * (NQ * 4);
+#pragma unroll
+            for (int ch = 0; ch < NCOL / 4; ++ch) {
+              float4 v;
+              v.x = __uint_as_float(acc[4 * ch + 0]) * sc;
+              v.y = __uint_as_float(acc[4 * ch + 1]) * sc;
+              v.z = __uint_as_float(acc[4 * ch + 2]) * sc;
+              v.w = __uint_as_float(acc[4 * ch + 3]) * sc;
+              *reinterpret_cast<float4*>(row + (((c0 / 4 + ch) ^ (r & 7)) << 4)) = v;
+            }
+          }
+          tc_fence_before();
+          if (tid == 0) LR_STAMP(2);
+          // every CTA of the cluster has finished the MMAs of (t, g) => all copies of h_{t-1} (mine included) have been
+          // consumed: my slab and the remote buffers of this group may be overwritten with h_t
+          if (tid == 0) mbar_wait(bar_hfree(g), (t - 1) & 1);
+          named_sync_epi();
+          if (tid == 0) LR_STAMP(3);
+#pragma unroll
+          for (int b = 0; b < NB; ++b) {
+            const int sq = 32 * b + lane;
+#pragma unroll
+            for (int gt = 0; gt < 4; ++gt)
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int r = gt * 32 + u0 + k;
+                pre[b][gt][k] += stg[r * NQ + ((((sq >> 2) ^ (r & 7))) << 2) + (sq & 3)];
+              }
           }
         }
-        tc_fence_before();
-        // every CTA of the cluster has finished the MMAs of step t => all copies of h_{t-1} (mine included) have been
-        // consumed: my slab and the remote buffers may be overwritten with h_t
-        if (tid == 0) mbar_wait(bar_hfree, (t - 1) & 1);
-        named_sync_epi();
+        // ---- cell (nn.LSTM gate order i | f | g | o), global writes, h_t -> fp16 hi / lo into my slab of the operand buffer
+        uint8_t* slab = gbase + K::OFF_H + g * HBUF + rank * (2 * SLAB);
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
+        for (int b = 0; b < NB; ++b) {
+          const int sq = 32 * b + lane;
+          const int q = (cgrp * NG + g) * NQ + sq;
+          float hq[4];
 #pragma unroll
-          for (int u = 0; u < 16; ++u) {
-            const int r = g * 32 + 16 * uh + u;
-            pre[g][u] += stg[r * NQ + ((((sl >> 2) ^ (r & 15))) << 2) + (sl & 3)];
+          for (int k = 0; k < 4; ++k) {
+            float i_, f_, g_, o_;
+            gates_fast(pre[b][0][k], pre[b][1][k], pre[b][2][k], pre[b][3][k], i_, f_, g_, o_);
+            const float cn = fmaf(f_, c[g][b][k], i_ * g_);
+            c[g][b][k] = cn;
+            hq[k] = o_ * tanh_fast(cn);
+            pre[b][0][k] = i_; pre[b][1][k] = f_; pre[b][2][k] = g_; pre[b][3][k] = o_;
           }
-      }
-      // ---- cell (nn.LSTM gate order i | f | g | o)
-      float hq[16];
+          float* Gs = p.G + (int64_t)s * p.bsG + (int64_t)row_g0 * p.ld + q;
+          float* Hs = p.H + (int64_t)s * p.bsH + (int64_t)row_h0 * p.ld + q;
+          float* Cc = p.Cs + (int64_t)s * p.bsH + (int64_t)row_h0 * p.ld + q;
+          if (q < p.Q) {
 #pragma unroll
-      for (int u = 0; u < 16; ++u) {
-        const float i_ = sigmoid_fast(pre[0][u]), f_ = sigmoid_fast(pre[1][u]);
-        const float g_ = tanh_fast(pre[2][u]), o_ = sigmoid_fast(pre[3][u]);
-        const float cn = valid ? fmaf(f_, c[u], i_ * g_) : 0.f;
-        c[u] = cn;
-        const float h_ = valid ? o_ * tanh_fast(cn) : 0.f;
-        hq[u] = h_;
-        pre[0][u] = valid ? i_ : 0.f; pre[1][u] = valid ? f_ : 0.f; pre[2][u] = valid ? g_ : 0.f; pre[3][u] = valid ? o_ : 0.f;
-      }
-      if (inb) {
-        float* Hs = p.H + (int64_t)s * p.bsH + (int64_t)row_h0 * p.ld + q;
-        float* Cc = p.Cs + (int64_t)s * p.bsH + (int64_t)row_h0 * p.ld + q;
+            for (int gt = 0; gt < 4; ++gt)
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
+              for (int k = 0; k < 4; ++k) __stcs(Gs + ((int64_t)gt * Hd + k) * p.ld, pre[b][gt][k]);
 #pragma unroll
-          for (int u = 0; u < 16; ++u) __stcs(Gs + ((int64_t)g * Hd + u) * p.ld, pre[g][u]);
+            for (int k = 0; k < 4; ++k) {
+              __stcs(Cc + (int64_t)k * p.ld, c[g][b][k]);
+              Hs[(int64_t)k * p.ld] = hq[k];
+            }
+          } else {
+            if (q < p.ld) {   // pad columns of the row stride: zeros (cold path, last group only)
+              for (int gt = 0; gt < 4; ++gt)
+                for (int k = 0; k < 4; ++k) Gs[((int64_t)gt * Hd + k) * p.ld] = 0.f;
+              for (int k = 0; k < 4; ++k) { Cc[(int64_t)k * p.ld] = 0.f; Hs[(int64_t)k * p.ld] = 0.f; }
+            }
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-          __stcs(Cc + (int64_t)u * p.ld, c[u]);
-          Hs[(int64_t)u * p.ld] = hq[u];
+            for (int k = 0; k < 4; ++k) { hq[k] = 0.f; c[g][b][k] = 0.f; }
+          }
+          if (t + 1 < S) {
+            uint32_t hi[2], lo[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const float a = hq[2 * j] * H_SCALE, bb = hq[2 * j + 1] * H_SCALE;
+              const __half2 h2 = __floats2half2_rn(a, bb);
+              const float2 hf = __half22float2(h2);
+              const __half2 l2 = __floats2half2_rn(a - hf.x, bb - hf.y);
+              hi[j] = *reinterpret_cast<const uint32_t*>(&h2);
+              lo[j] = *reinterpret_cast<const uint32_t*>(&l2);
+            }
+            const uint32_t off = sw64_off(sq, warp >> 1) + (warp & 1) * 8;   // units 4w .. 4w+3 = bytes [8w, 8w + 8) of the row
+            *reinterpret_cast<uint2*>(slab + off) = make_uint2(hi[0], hi[1]);
+            *reinterpret_cast<uint2*>(slab + SLAB + off) = make_uint2(lo[0], lo[1]);
+          }
         }
-      }
-      if (t + 1 < S) {
-        // ---- h_t -> fp16 hi / lo into my slab (K block `rank`) of my own operand buffer, then all-gather it
-        uint32_t hi[8], lo[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float a = hq[2 * j] * H_SCALE, b = hq[2 * j + 1] * H_SCALE;
-          const __half2 h2 = __floats2half2_rn(a, b);
-          const float2 hf = __half22float2(h2);
-          const __half2 l2 = __floats2half2_rn(a - hf.x, b - hf.y);
-          hi[j] = *reinterpret_cast<const uint32_t*>(&h2);
-          lo[j] = *reinterpret_cast<const uint32_t*>(&l2);
+        if (tid == 0) LR_STAMP(5);
+        // prefetch the next item's pre-activations while the exchange / the other group's MMAs run
+        {
+          const int gn = (g + 1) % NG, tn = t + (g + 1) / NG;
+          if (tn < S) load_pre(tn, gn);
         }
-        uint8_t* slab = gbase + OFF_H + rank * (2 * SLAB_H);
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const uint32_t off = sw64_off(sl, 2 * uh + e);
-          *reinterpret_cast<uint4*>(slab + off) = make_uint4(hi[4 * e], hi[4 * e + 1], hi[4 * e + 2], hi[4 * e + 3]);
-          *reinterpret_cast<uint4*>(slab + SLAB_H + off) = make_uint4(lo[4 * e], lo[4 * e + 1], lo[4 * e + 2], lo[4 * e + 3]);
-        }
-        fence_proxy_async();
-        named_sync_epi();
-        if (tid == 0) {
-          const uint32_t src = base + OFF_H + rank * (2 * SLAB_H);
-          if (C > 1) mbar_arrive_expect_tx(bar_hfull, (uint32_t)(C - 1) * 2 * SLAB_H);
-          else mbar_arrive(bar_hfull);
-          for (int peer = 0; peer < C; ++peer)
-            if (peer != (int)rank) bulk_copy_s2c(mapa(src, peer), src, 2 * SLAB_H, mapa(bar_hfull, peer));
+        if (t + 1 < S) {
+          fence_proxy_async();
+          named_sync_epi();
+          if (tid == 0) LR_STAMP(6);
+          if (warp == 0) {
+            const uint32_t src = base + K::OFF_H + g * HBUF + rank * (2 * SLAB);
+            if (lane == 0) {
+              if (C > 1) mbar_arrive_expect_tx(bar_hfull(g), (uint32_t)(C - 1) * 2 * SLAB);
+              else mbar_arrive(bar_hfull(g));
+            }
+            if (lane < C && lane != (int)rank) bulk_copy_s2c(mapa(src, lane), src, 2 * SLAB, mapa(bar_hfull(g), lane));
+          }
+          if (tid == 0) LR_STAMP(7);
+        } else if (NG > 1 && g + 1 < NG) {
+          named_sync_epi();          // the staging tile is shared by the groups
         }
       }
     }
@@ -259,38 +403,42 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_fwd_kernel(const FwdParam
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();            // nobody exits while a peer may still copy into / arrive on its shared memory
-  if (warp == 4) {
+  if (warp == 8) {
     tc_fence_after();
-    tmem_dealloc<64>(tmem_base);
+    tmem_dealloc<K::TCOLS>(tmem_base);
   }
 }
 
-
 // ================================================================================================ backward (BPTT)
-// Iterating the steps in the reverse of the forward order, per step t:
-//   dh_t = dH_t (from the layers above) + W_hh^T . da_{t+1}          (the second term = the recurrent gradient)
-//   cell backward -> da_t = d(pre-activations) [4 gates] (written over the saved activations in G), dc carried in registers
-// CTA `rank` owns the 128 gate rows of ITS 32 hidden units, so its share of W_hh^T . da is a K = 128 contraction with the
-// da it has just computed (no operand exchange): D[Hd hidden][64 seqs] = A[m][k] . B[seq][k], A = W_hh[rows of this CTA]^T
-// resident in shared memory (bf16 hi + lo: gradients need the fp32 exponent range, 16 mantissa bits are plenty), B = da
-// (bf16 hi + lo, written by the cell threads).  The partial dh is then reduce-scattered: TMEM lanes [32 w, 32 w + 32) of
-// M block mb are exactly the hidden units of CTA 4 mb + w, whose receive buffer gets them with coalesced
-// st.shared::cluster stores; every CTA sums the C partials for its 32 units in a fixed order (deterministic).
-constexpr int B_OFF_AHI = 0;                              // 4 K slabs x [256 rows x 64 B]
-constexpr int B_SLAB_A = 256 * 64;                        // 16384
-constexpr int B_OFF_ALO = 4 * B_SLAB_A;                   // 65536
-constexpr int B_OFF_B = 8 * B_SLAB_A;                     // 131072: 4 K slabs x [hi | lo] x [64 x 64 B]
-constexpr int B_OFF_R = B_OFF_B + 4 * 2 * SLAB_H;         // 163840: C x 8 KB partial-sum slabs
-constexpr int B_R_BYTES = 32 * NQ * 4;                    // 8192
-constexpr int B_OFF_BAR = B_OFF_R + MAXC * B_R_BYTES;     // 229376
-constexpr int B_SMEM_BYTES = B_OFF_BAR + 64 + 1024;
-constexpr uint32_t IDESC_BWD = idesc_f16(128, NQ, 1);
+// Iterating the steps in the reverse of the forward order, per step n and group g:
+//   phase B: dh = dH (from the layers above) + sum over source CTAs of the partial W_hh^T . da of the previous iteration;
+//            cell backward -> da = d(pre-activations) [4 gates] (written over the saved activations in G and, as bf16
+//            hi / lo, into the B operand buffer: row = sequence, K = gate * 32 + unit); dc carried in registers
+//   MMA    : D[Hd hidden][NQ] = A[m][k] . B[seq][k], A = W_hh[gate rows of this CTA]^T resident in TMEM, K = 128
+//   phase A: TMEM lanes [32 w', 32 w' + 32) of M block mb are the hidden units of CTA 4 mb + w': coalesced
+//            st.shared::cluster into that CTA's receive slab for this source, one fence + one remote arrive per warp.
+template <int C, int NB, int NG>
+struct BwdCfg {
+  static constexpr int NQ = 32 * NB;
+  static constexpr int MB = (32 * C + 127) / 128;        // M blocks of 128 hidden units
+  static constexpr int SLAB = NQ * 64;                   // one K block (32 gate rows) of a group's da, hi or lo
+  static constexpr int BBUF = 4 * 2 * SLAB;              // B operand of one group
+  static constexpr int RSLAB = 32 * NQ * 4;              // partial sums of one source CTA for my 32 units
+  static constexpr int RBUF = C * RSLAB;
+  static constexpr int OFF_B = 0;
+  static constexpr int OFF_R = NG * BBUF;
+  static constexpr int OFF_BAR = OFF_R + NG * RBUF;
+  static constexpr int SMEM = OFF_BAR + 128 + 1024;
+  static constexpr int COL_AHI = 0, COL_ALO = 64 * MB, COL_D = 128 * MB;   // D of (g, mb) at COL_D + (g * MB + mb) * NQ
+  static constexpr uint32_t TCOLS = pow2_cols(128 * MB + NG * MB * NQ);
+};
 
 struct BwdParams {
   float* G; const float* Cs; const float* dH;
   const float* Whh[2];
-  int S, Q, Hd, C;
+  int S, Q, Hd;
   int64_t ld, bsG, bsH;
+  long long* prof;
 };
 
 __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
@@ -301,212 +449,327 @@ __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uin
   lo = *reinterpret_cast<const uint32_t*>(&l2);
 }
 
+template <int C, int NB, int NG>
 __global__ void __launch_bounds__(THREADS, 1) lstm_rec_bwd_kernel(const BwdParams p) {
+  using K = BwdCfg<C, NB, NG>;
+  constexpr int NQ = K::NQ, SLAB = K::SLAB, MB = K::MB, Hd = 32 * C;
+  constexpr uint32_t IDESC = idesc_f16(128, NQ, 1);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int C = p.C, Hd = p.Hd, S = p.S;
-  const int MB = (Hd + 127) / 128;
   const uint32_t rank = cluster_ctarank();
   const int cid = blockIdx.x / C;
-  const int dir = cid & 1, grp = cid >> 1;
-  const int q0 = grp * NQ;
-  const uint32_t bar_bfull = base + B_OFF_BAR, bar_acc = base + B_OFF_BAR + 8, bar_rfull = base + B_OFF_BAR + 16,
-                 bar_rfree = base + B_OFF_BAR + 24;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + B_OFF_BAR + 32);
+  const int dir = cid & 1, cgrp = cid >> 1;
+  const int S = p.S;
+  auto bar_bfull = [&](int g) { return base + K::OFF_BAR + 8u * g; };
+  auto bar_acc = [&](int g) { return base + K::OFF_BAR + 16u + 8u * g; };
+  auto bar_rfull = [&](int g) { return base + K::OFF_BAR + 32u + 8u * g; };
+  auto bar_rfree = [&](int g) { return base + K::OFF_BAR + 48u + 8u * g; };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + K::OFF_BAR + 64);
 
   if (tid == 0) {
-    mbar_init(bar_bfull, 1);
-    mbar_init(bar_acc, 1);
-    mbar_init(bar_rfull, 32 * C);
-    mbar_init(bar_rfree, C);
+    for (int g = 0; g < NG; ++g) {
+      mbar_init(bar_bfull(g), 1);
+      mbar_init(bar_acc(g), 1);
+      mbar_init(bar_rfull(g), C);
+      mbar_init(bar_rfree(g), C);
+    }
     mbar_init_fence();
   }
-  if (warp == 4) tmem_alloc<128>(smem_u32(tmem_slot));
+  if (warp == 8) tmem_alloc<K::TCOLS>(smem_u32(tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
 
-  // ---- resident A = W_hh[gate rows of this CTA]^T: A[m][k], k = gate * 32 + j  <->  W_hh[gate * Hd + 32 rank + j][m];
-  //      rows m >= Hd of the last M block are zero
-  {
-    const float* W = p.Whh[dir];
-    const int Mrows = MB * 128;
-    for (int k = warp; k < ROWS; k += THREADS / 32) {
-      const float* wr = W + ((int64_t)(k >> 5) * Hd + 32 * rank + (k & 31)) * Hd;
-      const int j = k & 31;
-      uint8_t* sl_hi = gbase + B_OFF_AHI + (k >> 5) * B_SLAB_A;
-      uint8_t* sl_lo = gbase + B_OFF_ALO + (k >> 5) * B_SLAB_A;
-      for (int m = lane; m < Mrows; m += 32) {
-        const float w = m < Hd ? __ldg(wr + m) : 0.f;
-        const __nv_bfloat16 hi = __float2bfloat16_rn(w);
-        const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
-        const uint32_t off = sw64_off(m, j >> 3) + (j & 7) * 2;
-        *reinterpret_cast<__nv_bfloat16*>(sl_hi + off) = hi;
-        *reinterpret_cast<__nv_bfloat16*>(sl_lo + off) = lo;
+  // ---- resident A = W_hh[gate rows of this CTA]^T -> TMEM: lane m (hidden unit, M block warp / 4), K index
+  //      k = gate * 32 + j  <->  W_hh[gate * Hd + 32 rank + j][m]; column c holds the bf16 pair (k = 2c, 2c + 1)
+  if (warp < 4 * MB) {
+    const int mb = warp >> 2;
+    const int m = mb * 128 + (warp & 3) * 32 + lane;
+    const bool mok = m < Hd;
+    const float* W = p.Whh[dir] + (int64_t)(32 * rank) * Hd + (mok ? m : 0);
+    const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + mb * 64;
+#pragma unroll 1
+    for (int kc = 0; kc < 4; ++kc) {                      // gate kc: 32 k values -> 16 columns
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float w0 = mok ? __ldg(W + ((int64_t)kc * Hd + 2 * i) * Hd) : 0.f;
+        const float w1 = mok ? __ldg(W + ((int64_t)kc * Hd + 2 * i + 1) * Hd) : 0.f;
+        split_bf16x2(w0, w1, hi[i], lo[i]);
       }
+      tc_st16(trow + K::COL_AHI + 16 * kc, hi);
+      tc_st16(trow + K::COL_ALO + 16 * kc, lo);
     }
+    tc_st_wait();
   }
-  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ================================================= MMA issuer: one product per step except the last processed one
     if (lane == 0) {
-      for (int n = 0; n + 1 < S; ++n) {
-        mbar_wait(bar_bfull, n & 1);
-        tc_fence_after();
-        for (int mb = 0; mb < MB; ++mb) {
+      for (int t = 0; t + 1 < S; ++t) {
 #pragma unroll
-          for (int kb = 0; kb < 4; ++kb) {
+        for (int g = 0; g < NG; ++g) {
+          mbar_wait(bar_bfull(g), t & 1);
+          tc_fence_after();
+          LR_STAMP(8);
+          const uint32_t bb = base + K::OFF_B + g * K::BBUF;
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              const uint32_t a_off = kb * B_SLAB_A + mb * (128 * 64) + half * 32;
-              const uint64_t a_hi = desc_k_sw64(base + B_OFF_AHI + a_off);
-              const uint64_t a_lo = desc_k_sw64(base + B_OFF_ALO + a_off);
-              const uint64_t b_hi = desc_k_sw64(base + B_OFF_B + kb * 2 * SLAB_H + half * 32);
-              const uint64_t b_lo = desc_k_sw64(base + B_OFF_B + kb * 2 * SLAB_H + SLAB_H + half * 32);
-              const uint32_t d = tmem_base + mb * NQ;
-              tc_mma_f16(d, a_lo, b_hi, IDESC_BWD, (kb | half) ? 1u : 0u);
-              tc_mma_f16(d, a_hi, b_lo, IDESC_BWD, 1u);
-              tc_mma_f16(d, a_hi, b_hi, IDESC_BWD, 1u);
+          for (int mb = 0; mb < MB; ++mb) {
+            const uint32_t d = tmem_base + K::COL_D + (g * MB + mb) * NQ;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint64_t b_hi = desc_k_sw64(bb + (j >> 1) * 2 * SLAB + (j & 1) * 32);
+              const uint64_t b_lo = desc_k_sw64(bb + (j >> 1) * 2 * SLAB + SLAB + (j & 1) * 32);
+              const uint32_t a_hi = tmem_base + K::COL_AHI + mb * 64 + 8 * j, a_lo = tmem_base + K::COL_ALO + mb * 64 + 8 * j;
+              tc_mma_f16_ts(d, a_lo, b_hi, IDESC, j ? 1u : 0u);
+              tc_mma_f16_ts(d, a_hi, b_lo, IDESC, 1u);
+              tc_mma_f16_ts(d, a_hi, b_hi, IDESC, 1u);
             }
           }
+          tc_commit(bar_acc(g));
+          LR_STAMP(9);
         }
-        tc_commit(bar_acc);
       }
     }
     __syncwarp();
   } else {
-    const int sl = tid & 63, uh = tid >> 6;
-    const int q = q0 + sl;
-    const bool inb = q < p.ld, valid = q < p.Q;
-    const int row_g0 = dir * 4 * Hd + 32 * (int)rank + 16 * uh;
-    const int row_h0 = dir * Hd + 32 * (int)rank + 16 * uh;
-    float dc[16], c_cur[16];
+    const int u0 = 4 * warp;
+    const int row_g0 = dir * 4 * Hd + 32 * (int)rank + u0;
+    const int row_h0 = dir * Hd + 32 * (int)rank + u0;
+    float dc[NG][NB][4], c_cur[NG][NB][4];
 #pragma unroll
-    for (int u = 0; u < 16; ++u) { dc[u] = 0.f; c_cur[u] = 0.f; }
-    {   // c of the first processed step (t = S - 1)
-      const int s = dir ? 0 : S - 1;
-      const float* Cc = p.Cs + (int64_t)s * p.bsH + (int64_t)row_h0 * p.ld + q;
+    for (int g = 0; g < NG; ++g)
 #pragma unroll
-      for (int u = 0; u < 16; ++u) c_cur[u] = valid ? __ldcs(Cc + (int64_t)u * p.ld) : 0.f;
-    }
-    for (int n = 0; n < S; ++n) {
-      const int t = S - 1 - n;                                  // forward processing index of this step
-      const int s = dir ? S - 1 - t : t;
-      const int sp = dir ? S - t : t - 1;                       // time index of the step processed before t in the forward
-      float* Gs = p.G + (int64_t)s * p.bsG + (int64_t)row_g0 * p.ld + q;
-      const float* dHs = p.dH + (int64_t)s * p.bsH + (int64_t)row_h0 * p.ld + q;
-      float act[4][16], dh[16], c_prev[16];
+      for (int b = 0; b < NB; ++b) {
+        const int q = (cgrp * NG + g) * NQ + 32 * b + lane;
+        const int s = dir ? 0 : S - 1;                           // first processed step
+        const float* Cc = p.Cs + (int64_t)s * p.bsH + (int64_t)row_h0 * p.ld + q;
 #pragma unroll
-      for (int g = 0; g < 4; ++g)
-#pragma unroll
-        for (int u = 0; u < 16; ++u) act[g][u] = valid ? __ldcs(Gs + ((int64_t)g * Hd + u) * p.ld) : 0.f;
-#pragma unroll
-      for (int u = 0; u < 16; ++u) dh[u] = valid ? __ldcs(dHs + (int64_t)u * p.ld) : 0.f;
-      if (t > 0) {
-        const float* Cp = p.Cs + (int64_t)sp * p.bsH + (int64_t)row_h0 * p.ld + q;
-#pragma unroll
-        for (int u = 0; u < 16; ++u) c_prev[u] = valid ? __ldcs(Cp + (int64_t)u * p.ld) : 0.f;
-      } else {
-#pragma unroll
-        for (int u = 0; u < 16; ++u) c_prev[u] = 0.f;
+        for (int k = 0; k < 4; ++k) {
+          dc[g][b][k] = 0.f;
+          c_cur[g][b][k] = q < p.Q ? __ldcs(Cc + (int64_t)k * p.ld) : 0.f;
+        }
       }
-      if (n > 0) {
-        // ---- recurrent gradient: sum of the C partial products of round n - 1 for my 16 units
-        mbar_wait_cluster(bar_rfull, (n - 1) & 1);
-        const float* R = reinterpret_cast<const float*>(gbase + B_OFF_R);
-        const int q4 = sl >> 2;
-        for (int src = 0; src < C; ++src) {
+    for (int t = 0; t < S; ++t) {                                // t = backward iteration; tf = forward processing index
+      const int tf = S - 1 - t;
+      const int s = dir ? S - 1 - tf : tf;
+      const int sp = dir ? S - tf : tf - 1;                      // time index of the step processed before tf in the forward
+      // ------------------------------------------------------------------ phase B of every group
 #pragma unroll
-          for (int u = 0; u < 16; ++u) {
-            const int ju = 16 * uh + u;
-            dh[u] += R[src * (B_R_BYTES / 4) + q4 * 128 + ((ju ^ (q4 & 7)) << 2) + (sl & 3)];
+      for (int g = 0; g < NG; ++g) {
+        if (tid == 0) LR_STAMP(0);
+        float act[NB][4][4], dh[NB][4], c_prev[NB][4];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          const int q = (cgrp * NG + g) * NQ + 32 * b + lane;
+          const bool valid = q < p.Q;
+          const float* Gs = p.G + (int64_t)s * p.bsG + (int64_t)row_g0 * p.ld + q;
+          const float* dHs = p.dH + (int64_t)s * p.bsH + (int64_t)row_h0 * p.ld + q;
+          const float* Cp = p.Cs + (int64_t)sp * p.bsH + (int64_t)row_h0 * p.ld + q;
+#pragma unroll
+          for (int gt = 0; gt < 4; ++gt)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) act[b][gt][k] = valid ? __ldcs(Gs + ((int64_t)gt * Hd + k) * p.ld) : 0.f;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            dh[b][k] = valid ? __ldcs(dHs + (int64_t)k * p.ld) : 0.f;
+            c_prev[b][k] = (valid && tf > 0) ? __ldcs(Cp + (int64_t)k * p.ld) : 0.f;
           }
         }
-      }
-      // ---- cell backward
-      float da[4][16];
+        if (t > 0) {
+          // ---- recurrent gradient: sum of the C partial products of round t - 1 for my 4 units
+          mbar_wait_cluster(bar_rfull(g), (t - 1) & 1);
+          if (tid == 0) LR_STAMP(1);
+          const float* R = reinterpret_cast<const float*>(gbase + K::OFF_R + g * K::RBUF);
 #pragma unroll
-      for (int u = 0; u < 16; ++u) {
-        const float i_ = act[0][u], f_ = act[1][u], g_ = act[2][u], o_ = act[3][u];
-        const float tc = tanh_fast(c_cur[u]);
-        const float dhu = dh[u];
-        const float dcu = fmaf(dhu * o_, 1.f - tc * tc, dc[u]);
-        da[0][u] = dcu * g_ * i_ * (1.f - i_);
-        da[1][u] = dcu * c_prev[u] * f_ * (1.f - f_);
-        da[2][u] = dcu * i_ * (1.f - g_ * g_);
-        da[3][u] = dhu * tc * o_ * (1.f - o_);
-        dc[u] = dcu * f_;
-        c_cur[u] = c_prev[u];
-      }
-      if (inb) {
+          for (int b = 0; b < NB; ++b) {
+            const int q4 = 8 * b + (lane >> 2);
+#pragma unroll 2
+            for (int src = 0; src < C; ++src) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
-#pragma unroll
-          for (int u = 0; u < 16; ++u) Gs[((int64_t)g * Hd + u) * p.ld] = valid ? da[g][u] : 0.f;
-      }
-      if (n + 1 < S) {
-        // ---- da -> bf16 hi / lo B operand: row = sequence, K index = gate * 32 + unit
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint32_t hi[8], lo[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) split_bf16x2(da[g][2 * j], da[g][2 * j + 1], hi[j], lo[j]);
-          uint8_t* slab = gbase + B_OFF_B + g * (2 * SLAB_H);
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const uint32_t off = sw64_off(sl, 2 * uh + e);
-            *reinterpret_cast<uint4*>(slab + off) = make_uint4(hi[4 * e], hi[4 * e + 1], hi[4 * e + 2], hi[4 * e + 3]);
-            *reinterpret_cast<uint4*>(slab + SLAB_H + off) = make_uint4(lo[4 * e], lo[4 * e + 1], lo[4 * e + 2], lo[4 * e + 3]);
-          }
-        }
-        fence_proxy_async();
-        named_sync_epi();
-        if (tid == 0) {
-          mbar_arrive(bar_bfull);
-          if (n > 0)                                   // round n - 1 has been read by all my threads: its senders may reuse R
-            for (int peer = 0; peer < C; ++peer) mbar_arrive_remote_release(mapa(bar_rfree, peer));
-        }
-        // ---- phase A: my partial W^T da -> the CTAs that own those hidden units
-        mbar_wait(bar_acc, n & 1);
-        tc_fence_after();
-        if (n > 0) mbar_wait_cluster(bar_rfree, (n - 1) & 1);
-        for (int mb = 0; mb < MB; ++mb) {
-          const int m0 = mb * 128 + warp * 32;         // hidden units of this warp's TMEM lanes (warp-uniform)
-          if (m0 < Hd) {
-            uint32_t acc[64];
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + mb * NQ;
-            tc_ld32_nowait(taddr, acc);
-            tc_ld32_nowait(taddr + 32, acc + 32);
-            tc_ld_wait();
-            const uint32_t dst = (uint32_t)(m0 >> 5);
-            const uint32_t rbase = mapa(base + B_OFF_R + rank * B_R_BYTES, dst);
-#pragma unroll
-            for (int q4 = 0; q4 < 16; ++q4) {
-              float4 v;
-              v.x = __uint_as_float(acc[4 * q4 + 0]); v.y = __uint_as_float(acc[4 * q4 + 1]);
-              v.z = __uint_as_float(acc[4 * q4 + 2]); v.w = __uint_as_float(acc[4 * q4 + 3]);
-              st_cluster_v4(rbase + q4 * 512 + ((lane ^ (q4 & 7)) << 4), v);
+              for (int k = 0; k < 4; ++k)
+                dh[b][k] += R[src * (K::RSLAB / 4) + q4 * 128 + (((u0 + k) ^ (q4 & 7)) << 2) + (lane & 3)];
             }
-            mbar_arrive_remote_release(mapa(bar_rfull, dst));
           }
         }
-        tc_fence_before();
+        if (tid == 0) LR_STAMP(2);
+        // ---- cell backward, da -> global (over the activations) and -> bf16 hi / lo B operand
+        uint8_t* bbuf = gbase + K::OFF_B + g * K::BBUF;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          const int sq = 32 * b + lane;
+          const int q = (cgrp * NG + g) * NQ + sq;
+          float da[4][4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float i_ = act[b][0][k], f_ = act[b][1][k], g_ = act[b][2][k], o_ = act[b][3][k];
+            const float tc = tanh_fast(c_cur[g][b][k]);
+            const float dhu = dh[b][k];
+            const float dcu = fmaf(dhu * o_, 1.f - tc * tc, dc[g][b][k]);
+            da[0][k] = dcu * g_ * i_ * (1.f - i_);
+            da[1][k] = dcu * c_prev[b][k] * f_ * (1.f - f_);
+            da[2][k] = dcu * i_ * (1.f - g_ * g_);
+            da[3][k] = dhu * tc * o_ * (1.f - o_);
+            dc[g][b][k] = dcu * f_;
+            c_cur[g][b][k] = c_prev[b][k];
+          }
+          if (q < p.ld) {      // invalid (pad) columns carry zeros (act = dh = 0 there)
+            float* Gs = p.G + (int64_t)s * p.bsG + (int64_t)row_g0 * p.ld + q;
+#pragma unroll
+            for (int gt = 0; gt < 4; ++gt)
+#pragma unroll
+              for (int k = 0; k < 4; ++k) Gs[((int64_t)gt * Hd + k) * p.ld] = da[gt][k];
+          }
+          if (t + 1 < S) {
+            const uint32_t off = sw64_off(sq, warp >> 1) + (warp & 1) * 8;
+#pragma unroll
+            for (int gt = 0; gt < 4; ++gt) {
+              uint32_t h0, l0, h1, l1;
+              split_bf16x2(da[gt][0], da[gt][1], h0, l0);
+              split_bf16x2(da[gt][2], da[gt][3], h1, l1);
+              *reinterpret_cast<uint2*>(bbuf + gt * 2 * SLAB + off) = make_uint2(h0, h1);
+              *reinterpret_cast<uint2*>(bbuf + gt * 2 * SLAB + SLAB + off) = make_uint2(l0, l1);
+            }
+          }
+        }
+        if (tid == 0) LR_STAMP(3);
+        if (t + 1 < S) {
+          fence_proxy_async();
+          named_sync_epi();
+          if (warp == 0) {
+            if (lane == 0) mbar_arrive(bar_bfull(g));
+            // round t - 1 has been read by all my threads: its senders may reuse my receive slabs
+            if (t > 0 && lane < C) mbar_arrive_remote(mapa(bar_rfree(g), lane));
+          }
+        }
+        if (tid == 0) LR_STAMP(4);
+      }
+      // ------------------------------------------------------------------ phase A of every group
+      if (t + 1 < S) {
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          mbar_wait(bar_acc(g), t & 1);
+          tc_fence_after();
+          if (tid == 0) LR_STAMP(5);
+          if (t > 0) mbar_wait_cluster(bar_rfree(g), (t - 1) & 1);
+          if (tid == 0) LR_STAMP(6);
+          const int mb = warp >> 2;
+          const int m0 = mb * 128 + (warp & 3) * 32;            // hidden units of this warp's TMEM lanes (warp-uniform)
+          if (mb < MB && m0 < Hd) {
+            const uint32_t dst = (uint32_t)(m0 >> 5);
+            const uint32_t rbase = mapa(base + K::OFF_R + g * K::RBUF + rank * K::RSLAB, dst);
+            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + K::COL_D + (g * MB + mb) * NQ;
+#pragma unroll
+            for (int cb = 0; cb < NB; ++cb) {
+              uint32_t acc[32];
+              tc_ld32_nowait(taddr + 32 * cb, acc);
+              tc_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int q4 = 8 * cb + i;
+                float4 v;
+                v.x = __uint_as_float(acc[4 * i + 0]); v.y = __uint_as_float(acc[4 * i + 1]);
+                v.z = __uint_as_float(acc[4 * i + 2]); v.w = __uint_as_float(acc[4 * i + 3]);
+                st_cluster_v4(rbase + q4 * 512 + ((lane ^ (q4 & 7)) << 4), v);
+              }
+            }
+            __syncwarp();
+            if (lane == 0) {
+              fence_cluster();
+              mbar_arrive_remote(mapa(bar_rfull(g), dst));
+            }
+          }
+          tc_fence_before();
+          if (tid == 0) LR_STAMP(7);
+        }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
-  if (warp == 4) {
+  if (warp == 8) {
     tc_fence_after();
-    tmem_dealloc<128>(tmem_base);
+    tmem_dealloc<K::TCOLS>(tmem_base);
   }
+}
+
+// ================================================================================================ host side
+template <typename Params, typename Kern>
+static int launch_cluster(Kern kern, int smem, int C, int clusters, const Params& p, cudaStream_t st) {
+  WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(clusters * C));
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  WB_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+  return 0;
+}
+
+template <typename Kern>
+static int max_clusters_of(Kern kern, int smem, int C) {
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(C * 64));
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return -1; }
+  return n;
+}
+
+// Sequences per cluster (capacity) -> (NB, NG): 32 -> (1, 1), 64 -> (2, 1), 128 -> (2, 2).  Pick the smallest capacity whose
+// cluster count fits in one wave (co-resident clusters, cached per hidden size); larger problems take 128.
+static int pick_capacity(int Q, int maxc, int force) {
+  if (force == 32 || force == 64 || force == 128) return force;
+  for (int cap : {32, 64, 128})
+    if (2 * cdiv(Q, cap) <= maxc) return cap;
+  return 128;
+}
+
+template <int C>
+static int max_clusters_c(bool bwd) {
+  static int cached[2] = {0, 0};
+  if (!cached[bwd]) {
+    int n = bwd ? max_clusters_of(lstm_rec_bwd_kernel<C, 2, 2>, BwdCfg<C, 2, 2>::SMEM, C)
+                : max_clusters_of(lstm_rec_fwd_kernel<C, 2, 2>, FwdCfg<C, 2, 2>::SMEM, C);
+    cached[bwd] = n > 0 ? n : 1;
+  }
+  return cached[bwd];
+}
+
+template <int C>
+static int run_fwd(const FwdParams& p, int force, cudaStream_t st) {
+  const int cap = pick_capacity(p.Q, max_clusters_c<C>(false), force);
+  const int clusters = 2 * cdiv(p.Q, cap);
+  if (cap == 32) return launch_cluster(lstm_rec_fwd_kernel<C, 1, 1>, FwdCfg<C, 1, 1>::SMEM, C, clusters, p, st);
+  if (cap == 64) return launch_cluster(lstm_rec_fwd_kernel<C, 2, 1>, FwdCfg<C, 2, 1>::SMEM, C, clusters, p, st);
+  return launch_cluster(lstm_rec_fwd_kernel<C, 2, 2>, FwdCfg<C, 2, 2>::SMEM, C, clusters, p, st);
+}
+template <int C>
+static int run_bwd(const BwdParams& p, int force, cudaStream_t st) {
+  const int cap = pick_capacity(p.Q, max_clusters_c<C>(true), force);
+  const int clusters = 2 * cdiv(p.Q, cap);
+  if (cap == 32) return launch_cluster(lstm_rec_bwd_kernel<C, 1, 1>, BwdCfg<C, 1, 1>::SMEM, C, clusters, p, st);
+  if (cap == 64) return launch_cluster(lstm_rec_bwd_kernel<C, 2, 1>, BwdCfg<C, 2, 1>::SMEM, C, clusters, p, st);
+  return launch_cluster(lstm_rec_bwd_kernel<C, 2, 2>, BwdCfg<C, 2, 2>::SMEM, C, clusters, p, st);
 }
 
 }  // namespace lr
@@ -514,37 +777,51 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_bwd_kernel(const BwdParam
 
 using namespace wb;
 
+extern "C" int wesep_b200_lstm_rec_supported(int Hd) {
+  return (Hd == 32 || Hd == 64 || Hd == 128 || Hd == 192 || Hd == 256) ? 1 : 0;
+}
+
 static int check_rec(const WesepLstmRecArgs* a, bool bwd) {
   if (a->S <= 0 || a->Q <= 0 || a->Hd <= 0) return fail(-1, "lstm_rec: empty shape");
-  if (a->Hd % 32 || a->Hd / 32 > lr::MAXC) return fail(-2, "lstm_rec: hidden size must be 32 * (1..8)");
+  if (!wesep_b200_lstm_rec_supported(a->Hd)) return fail(-2, "lstm_rec: hidden size must be 32, 64, 128, 192 or 256");
   if ((a->ld & 3) || a->ld < a->Q) return fail(-1, "lstm_rec: ld must be a multiple of 4 and >= Q");
   if (!a->G || !a->H || !a->C || !a->Whh_f || !a->Whh_r) return fail(-1, "lstm_rec: null pointer");
+  if (!aligned16(a->Whh_f) || !aligned16(a->Whh_r)) return fail(-1, "lstm_rec: W_hh must be 16-byte aligned");
   if (a->bsG < 8 * (int64_t)a->Hd * a->ld || a->bsH < 2 * (int64_t)a->Hd * a->ld) return fail(-1, "lstm_rec: step strides");
   if (bwd && !a->dH) return fail(-1, "lstm_rec_bwd: dH missing");
   return 0;
 }
 
-extern "C" int wesep_b200_lstm_rec_supported(int Hd) { return (Hd > 0 && Hd % 32 == 0 && Hd / 32 <= lr::MAXC) ? 1 : 0; }
+// How many clusters of the (largest configuration of the) kernel can be resident at once on the current device.
+extern "C" int wesep_b200_lstm_rec_max_clusters(int Hd, int bwd) {
+  switch (Hd / 32) {
+    case 1: return lr::max_clusters_c<1>(bwd != 0);
+    case 2: return lr::max_clusters_c<2>(bwd != 0);
+    case 4: return lr::max_clusters_c<4>(bwd != 0);
+    case 6: return lr::max_clusters_c<6>(bwd != 0);
+    case 8: return lr::max_clusters_c<8>(bwd != 0);
+  }
+  return 0;
+}
 
 extern "C" int wesep_b200_lstm_rec_fwd(const WesepLstmRecArgs* a, void* stream) {
   if (int rc = check_rec(a, false)) return rc;
   lr::FwdParams p{};
   p.G = a->G; p.H = a->H; p.Cs = a->C;
   p.Whh[0] = a->Whh_f; p.Whh[1] = a->Whh_r;
-  p.S = a->S; p.Q = a->Q; p.Hd = a->Hd; p.C = a->Hd / 32;
+  p.S = a->S; p.Q = a->Q; p.Hd = a->Hd;
   p.ld = a->ld; p.bsG = a->bsG; p.bsH = a->bsH;
-  const int groups = cdiv(a->Q, lr::NQ);
-  WB_CUDA(cudaFuncSetAttribute(lr::lstm_rec_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lr::SMEM_BYTES));
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(2 * groups * p.C));
-  cfg.blockDim = dim3(lr::THREADS);
-  cfg.dynamicSmemBytes = lr::SMEM_BYTES;
-  cfg.stream = (cudaStream_t)stream;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = (unsigned)p.C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
-  WB_CUDA(cudaLaunchKernelEx(&cfg, lr::lstm_rec_fwd_kernel, p));
+  p.prof = (long long*)a->prof;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = -2;
+  switch (a->Hd / 32) {
+    case 1: rc = lr::run_fwd<1>(p, a->seqs_per_cluster, st); break;
+    case 2: rc = lr::run_fwd<2>(p, a->seqs_per_cluster, st); break;
+    case 4: rc = lr::run_fwd<4>(p, a->seqs_per_cluster, st); break;
+    case 6: rc = lr::run_fwd<6>(p, a->seqs_per_cluster, st); break;
+    case 8: rc = lr::run_fwd<8>(p, a->seqs_per_cluster, st); break;
+  }
+  if (rc) return rc;
   WB_LAUNCH_CHECK("lstm_rec_fwd");
   return 0;
 }
@@ -554,20 +831,19 @@ extern "C" int wesep_b200_lstm_rec_bwd(const WesepLstmRecArgs* a, void* stream) 
   lr::BwdParams p{};
   p.G = a->G; p.Cs = a->C; p.dH = a->dH;
   p.Whh[0] = a->Whh_f; p.Whh[1] = a->Whh_r;
-  p.S = a->S; p.Q = a->Q; p.Hd = a->Hd; p.C = a->Hd / 32;
+  p.S = a->S; p.Q = a->Q; p.Hd = a->Hd;
   p.ld = a->ld; p.bsG = a->bsG; p.bsH = a->bsH;
-  const int groups = cdiv(a->Q, lr::NQ);
-  WB_CUDA(cudaFuncSetAttribute(lr::lstm_rec_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lr::B_SMEM_BYTES));
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(2 * groups * p.C));
-  cfg.blockDim = dim3(lr::THREADS);
-  cfg.dynamicSmemBytes = lr::B_SMEM_BYTES;
-  cfg.stream = (cudaStream_t)stream;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = (unsigned)p.C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
-  WB_CUDA(cudaLaunchKernelEx(&cfg, lr::lstm_rec_bwd_kernel, p));
+  p.prof = (long long*)a->prof;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = -2;
+  switch (a->Hd / 32) {
+    case 1: rc = lr::run_bwd<1>(p, a->seqs_per_cluster, st); break;
+    case 2: rc = lr::run_bwd<2>(p, a->seqs_per_cluster, st); break;
+    case 4: rc = lr::run_bwd<4>(p, a->seqs_per_cluster, st); break;
+    case 6: rc = lr::run_bwd<6>(p, a->seqs_per_cluster, st); break;
+    case 8: rc = lr::run_bwd<8>(p, a->seqs_per_cluster, st); break;
+  }
+  if (rc) return rc;
   WB_LAUNCH_CHECK("lstm_rec_bwd");
   return 0;
 }

@@ -873,7 +873,7 @@ class LstmTmFn(torch.autograd.Function):
         if rec:
             _lib.call("wesep_b200_lstm_rec_fwd",
                       _args("WesepLstmRecArgs", S=S, Q=Q, Hd=Hd, ld=G.stride(1), bsG=G.stride(0), bsH=H.stride(0), G=G, H=H,
-                            C=Cs, Whh_f=whh[0], Whh_r=whh[1]), st)
+                            C=Cs, Whh_f=whh[0], Whh_r=whh[1], seqs_per_cluster=_rec_force()), st)
         for d in range(0 if rec else 2):
             prev = None
             for s in (range(S) if d == 0 else range(S - 1, -1, -1)):
@@ -905,7 +905,7 @@ class LstmTmFn(torch.autograd.Function):
             gH = as_act(gH)
             _lib.call("wesep_b200_lstm_rec_bwd",
                       _args("WesepLstmRecArgs", S=S, Q=Q, Hd=Hd, ld=G.stride(1), bsG=G.stride(0), bsH=H.stride(0), G=G, H=H,
-                            C=Cs, Whh_f=whh[0], Whh_r=whh[1], dH=gH), st)
+                            C=Cs, Whh_f=whh[0], Whh_r=whh[1], dH=gH, seqs_per_cluster=_rec_force()), st)
         else:
             dH = new_act(S, 2 * Hd, Q, dev)
             dH.copy_(gH)                               # accumulated in place below: never touch autograd's tensor
@@ -936,6 +936,11 @@ class LstmTmFn(torch.autograd.Function):
             conv1x1_dw_raw(G[:-1, 4 * Hd:], H[1:, Hd:], dWhh[1])
         dxn = conv1x1_raw(G, Wih, True, C)
         return (dxn, dWih[:4 * Hd], dWhh[0], db[:4 * Hd], db[:4 * Hd], dWih[4 * Hd:], dWhh[1], db[4 * Hd:], db[4 * Hd:])
+
+
+def _rec_force():
+    """WESEP_LSTM_REC_SEQS = 32 / 64 / 128 forces the sequences-per-cluster grouping of the recurrence kernels (tests)."""
+    return int(os.environ.get("WESEP_LSTM_REC_SEQS", "0") or 0)
 
 
 def lstm_rec_supported(Hd):
