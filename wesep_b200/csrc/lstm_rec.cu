@@ -34,8 +34,10 @@ namespace lr {
 using namespace tcx;
 
 constexpr int MAXC = 8;                // cluster size = Hd / 32
-constexpr int THREADS = 288;           // warps 0-7: TMEM drain / cell, warp 8: MMA issuer + TMEM owner
-constexpr int EPI_THREADS = 256;
+constexpr int NW = 16;                 // cell warps: warp w owns hidden units [2w, 2w + 2) of the CTA (lane = sequence)
+constexpr int UPW = 32 / NW;           // units per cell warp
+constexpr int THREADS = 32 * NW + 32;  // warps 0-15: TMEM drain / cell (4 per scheduler: the cell is latency-bound), warp 16: MMA issuer + TMEM owner
+constexpr int MMA_WARP = NW;
 constexpr float H_SCALE = 4096.f;      // h in (-1, 1) -> fp16 hi + lo of 4096 h
 constexpr float LOG2E = 1.4426950408889634f;
 
@@ -102,7 +104,14 @@ __device__ __forceinline__ void gates_fast(float ai, float af, float ag, float a
   g_ = fmaf(-2.f * rp, dO, 1.f);
 }
 
-__device__ __forceinline__ void named_sync_epi() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
+__device__ __forceinline__ void named_sync_epi() { asm volatile("bar.sync 1, 512;\n" ::: "memory"); }
+static_assert(NW == 16, "named_sync_epi / column split assume 16 cell warps");
+
+__device__ __forceinline__ void tc_ld8_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
 
 __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t* r) {
   asm volatile(
@@ -163,7 +172,7 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_fwd_kernel(const FwdParam
     }
     mbar_init_fence();
   }
-  if (warp == 8) tmem_alloc<K::TCOLS>(smem_u32(tmem_slot));
+  if (warp == MMA_WARP) tmem_alloc<K::TCOLS>(smem_u32(tmem_slot));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -210,9 +219,9 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_fwd_kernel(const FwdParam
   cluster_sync_all();            // every CTA's barriers are initialised before any remote traffic
   tc_fence_after();
 
-  if (warp == 8) {
+  if (warp == MMA_WARP) {
     // ================================================= MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       const uint16_t mask = (uint16_t)((1u << C) - 1u);
       for (int t = 1; t < S; ++t) {
 #pragma unroll
@@ -239,20 +248,20 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_fwd_kernel(const FwdParam
     }
     __syncwarp();
   } else {
-    // ================================================= TMEM drain + cell warps: warp w owns hidden units [4w, 4w + 4) of the
+    // ================================================= TMEM drain + cell warps: warp w owns hidden units [2w, 2w + 2) of the
     // CTA, lane = sequence within a 32-sequence block
-    const int u0 = 4 * warp;
+    const int u0 = UPW * warp;
     const int row_g0 = dir * 4 * Hd + 32 * (int)rank + u0;     // G row of (gate 0, unit 0 of this thread)
     const int row_h0 = dir * Hd + 32 * (int)rank + u0;
-    float c[NG][NB][4];
+    float c[NG][NB][UPW];
 #pragma unroll
     for (int g = 0; g < NG; ++g)
 #pragma unroll
       for (int b = 0; b < NB; ++b)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) c[g][b][k] = 0.f;
+        for (int k = 0; k < UPW; ++k) c[g][b][k] = 0.f;
     const float* stg = reinterpret_cast<const float*>(gbase + K::OFF_STG);
-    float nxt[NB][4][4];
+    float nxt[NB][4][UPW];
     auto load_pre = [&](int t, int g) {
       const int s = dir ? S - 1 - t : t;
 #pragma unroll
@@ -262,7 +271,7 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_fwd_kernel(const FwdParam
 #pragma unroll
         for (int gt = 0; gt < 4; ++gt)
 #pragma unroll
-          for (int k = 0; k < 4; ++k) nxt[b][gt][k] = q < p.Q ? __ldcs(Gs + ((int64_t)gt * Hd + k) * p.ld) : 0.f;
+          for (int k = 0; k < UPW; ++k) nxt[b][gt][k] = q < p.Q ? __ldcs(Gs + ((int64_t)gt * Hd + k) * p.ld) : 0.f;
       }
     };
     load_pre(0, 0);
@@ -270,25 +279,25 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_fwd_kernel(const FwdParam
       const int s = dir ? S - 1 - t : t;
 #pragma unroll
       for (int g = 0; g < NG; ++g) {
-        float pre[NB][4][4];
+        float pre[NB][4][UPW];
 #pragma unroll
         for (int b = 0; b < NB; ++b)
 #pragma unroll
           for (int gt = 0; gt < 4; ++gt)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) pre[b][gt][k] = nxt[b][gt][k];
+            for (int k = 0; k < UPW; ++k) pre[b][gt][k] = nxt[b][gt][k];
         if (tid == 0) LR_STAMP(0);
         if (t > 0) {
           mbar_wait(bar_acc(g), (t - 1) & 1);
           tc_fence_after();
           if (tid == 0) LR_STAMP(1);
           {   // phase 1: lane = gate row; TMEM -> registers -> descale -> staging (so that phase 2 can read by sequence)
-            constexpr int NCOL = NQ / 2;               // warps w and w + 4 share a lane quarter and split the columns
+            constexpr int NCOL = NQ / 4;               // warps w, w + 4, w + 8, w + 12 share a lane quarter and split the columns
             const int r = (warp & 3) * 32 + lane, c0 = (warp >> 2) * NCOL;
             uint32_t acc[NCOL];
             const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + K::COL_D + g * NQ + c0;
-            if constexpr (NCOL == 32) tc_ld32_nowait(taddr, acc);
-            else tc_ld16_nowait(taddr, acc);
+            if constexpr (NCOL == 16) tc_ld16_nowait(taddr, acc);
+            else tc_ld8_nowait(taddr, acc);
             tc_ld_wait();
             const float sc = rs[r];
             uint8_t* row = gbase + K::OFF_STG + r * (NQ * 4);
@@ -315,7 +324,7 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_fwd_kernel(const FwdParam
 #pragma unroll
             for (int gt = 0; gt < 4; ++gt)
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
+              for (int k = 0; k < UPW; ++k) {
                 const int r = gt * 32 + u0 + k;
                 pre[b][gt][k] += stg[r * NQ + ((((sq >> 2) ^ (r & 7))) << 2) + (sq & 3)];
               }
@@ -327,9 +336,9 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_fwd_kernel(const FwdParam
         for (int b = 0; b < NB; ++b) {
           const int sq = 32 * b + lane;
           const int q = (cgrp * NG + g) * NQ + sq;
-          float hq[4];
+          float hq[UPW];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
+          for (int k = 0; k < UPW; ++k) {
             float i_, f_, g_, o_;
             gates_fast(pre[b][0][k], pre[b][1][k], pre[b][2][k], pre[b][3][k], i_, f_, g_, o_);
             const float cn = fmaf(f_, c[g][b][k], i_ * g_);
@@ -344,35 +353,30 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_fwd_kernel(const FwdParam
 #pragma unroll
             for (int gt = 0; gt < 4; ++gt)
 #pragma unroll
-              for (int k = 0; k < 4; ++k) __stcs(Gs + ((int64_t)gt * Hd + k) * p.ld, pre[b][gt][k]);
+              for (int k = 0; k < UPW; ++k) __stcs(Gs + ((int64_t)gt * Hd + k) * p.ld, pre[b][gt][k]);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < UPW; ++k) {
               __stcs(Cc + (int64_t)k * p.ld, c[g][b][k]);
               Hs[(int64_t)k * p.ld] = hq[k];
             }
           } else {
             if (q < p.ld) {   // pad columns of the row stride: zeros (cold path, last group only)
               for (int gt = 0; gt < 4; ++gt)
-                for (int k = 0; k < 4; ++k) Gs[((int64_t)gt * Hd + k) * p.ld] = 0.f;
-              for (int k = 0; k < 4; ++k) { Cc[(int64_t)k * p.ld] = 0.f; Hs[(int64_t)k * p.ld] = 0.f; }
+                for (int k = 0; k < UPW; ++k) Gs[((int64_t)gt * Hd + k) * p.ld] = 0.f;
+              for (int k = 0; k < UPW; ++k) { Cc[(int64_t)k * p.ld] = 0.f; Hs[(int64_t)k * p.ld] = 0.f; }
             }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { hq[k] = 0.f; c[g][b][k] = 0.f; }
+            for (int k = 0; k < UPW; ++k) { hq[k] = 0.f; c[g][b][k] = 0.f; }
           }
           if (t + 1 < S) {
-            uint32_t hi[2], lo[2];
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const float a = hq[2 * j] * H_SCALE, bb = hq[2 * j + 1] * H_SCALE;
-              const __half2 h2 = __floats2half2_rn(a, bb);
-              const float2 hf = __half22float2(h2);
-              const __half2 l2 = __floats2half2_rn(a - hf.x, bb - hf.y);
-              hi[j] = *reinterpret_cast<const uint32_t*>(&h2);
-              lo[j] = *reinterpret_cast<const uint32_t*>(&l2);
-            }
-            const uint32_t off = sw64_off(sq, warp >> 1) + (warp & 1) * 8;   // units 4w .. 4w+3 = bytes [8w, 8w + 8) of the row
-            *reinterpret_cast<uint2*>(slab + off) = make_uint2(hi[0], hi[1]);
-            *reinterpret_cast<uint2*>(slab + SLAB + off) = make_uint2(lo[0], lo[1]);
+            static_assert(UPW == 2, "slab write packs one fp16 pair per thread");
+            const float a = hq[0] * H_SCALE, bb = hq[1] * H_SCALE;
+            const __half2 h2 = __floats2half2_rn(a, bb);
+            const float2 hf = __half22float2(h2);
+            const __half2 l2 = __floats2half2_rn(a - hf.x, bb - hf.y);
+            const uint32_t off = sw64_off(sq, warp >> 2) + (warp & 3) * 4;   // units 2w, 2w + 1 = bytes [4w, 4w + 4) of the row
+            *reinterpret_cast<uint32_t*>(slab + off) = *reinterpret_cast<const uint32_t*>(&h2);
+            *reinterpret_cast<uint32_t*>(slab + SLAB + off) = *reinterpret_cast<const uint32_t*>(&l2);
           }
         }
         if (tid == 0) LR_STAMP(5);
@@ -403,7 +407,7 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_fwd_kernel(const FwdParam
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();            // nobody exits while a peer may still copy into / arrive on its shared memory
-  if (warp == 8) {
+  if (warp == MMA_WARP) {
     tc_fence_after();
     tmem_dealloc<K::TCOLS>(tmem_base);
   }
@@ -473,12 +477,12 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_bwd_kernel(const BwdParam
     for (int g = 0; g < NG; ++g) {
       mbar_init(bar_bfull(g), 1);
       mbar_init(bar_acc(g), 1);
-      mbar_init(bar_rfull(g), C);
+      mbar_init(bar_rfull(g), 2 * C);            // two sender warps (column halves) per source CTA
       mbar_init(bar_rfree(g), C);
     }
     mbar_init_fence();
   }
-  if (warp == 8) tmem_alloc<K::TCOLS>(smem_u32(tmem_slot));
+  if (warp == MMA_WARP) tmem_alloc<K::TCOLS>(smem_u32(tmem_slot));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -511,9 +515,9 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_bwd_kernel(const BwdParam
   cluster_sync_all();
   tc_fence_after();
 
-  if (warp == 8) {
+  if (warp == MMA_WARP) {
     // ================================================= MMA issuer: one product per step except the last processed one
-    if (lane == 0) {
+    if (elect_one()) {
       for (int t = 0; t + 1 < S; ++t) {
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
@@ -541,10 +545,10 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_bwd_kernel(const BwdParam
     }
     __syncwarp();
   } else {
-    const int u0 = 4 * warp;
+    const int u0 = UPW * warp;
     const int row_g0 = dir * 4 * Hd + 32 * (int)rank + u0;
     const int row_h0 = dir * Hd + 32 * (int)rank + u0;
-    float dc[NG][NB][4], c_cur[NG][NB][4];
+    float dc[NG][NB][UPW], c_cur[NG][NB][UPW];
 #pragma unroll
     for (int g = 0; g < NG; ++g)
 #pragma unroll
@@ -553,7 +557,7 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_bwd_kernel(const BwdParam
         const int s = dir ? 0 : S - 1;                           // first processed step
         const float* Cc = p.Cs + (int64_t)s * p.bsH + (int64_t)row_h0 * p.ld + q;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < UPW; ++k) {
           dc[g][b][k] = 0.f;
           c_cur[g][b][k] = q < p.Q ? __ldcs(Cc + (int64_t)k * p.ld) : 0.f;
         }
@@ -566,7 +570,7 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_bwd_kernel(const BwdParam
 #pragma unroll
       for (int g = 0; g < NG; ++g) {
         if (tid == 0) LR_STAMP(0);
-        float act[NB][4][4], dh[NB][4], c_prev[NB][4];
+        float act[NB][4][UPW], dh[NB][UPW], c_prev[NB][UPW];
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
           const int q = (cgrp * NG + g) * NQ + 32 * b + lane;
@@ -577,9 +581,9 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_bwd_kernel(const BwdParam
 #pragma unroll
           for (int gt = 0; gt < 4; ++gt)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) act[b][gt][k] = valid ? __ldcs(Gs + ((int64_t)gt * Hd + k) * p.ld) : 0.f;
+            for (int k = 0; k < UPW; ++k) act[b][gt][k] = valid ? __ldcs(Gs + ((int64_t)gt * Hd + k) * p.ld) : 0.f;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
+          for (int k = 0; k < UPW; ++k) {
             dh[b][k] = valid ? __ldcs(dHs + (int64_t)k * p.ld) : 0.f;
             c_prev[b][k] = (valid && tf > 0) ? __ldcs(Cp + (int64_t)k * p.ld) : 0.f;
           }
@@ -592,10 +596,10 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_bwd_kernel(const BwdParam
 #pragma unroll
           for (int b = 0; b < NB; ++b) {
             const int q4 = 8 * b + (lane >> 2);
-#pragma unroll 2
+#pragma unroll
             for (int src = 0; src < C; ++src) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
+              for (int k = 0; k < UPW; ++k)
                 dh[b][k] += R[src * (K::RSLAB / 4) + q4 * 128 + (((u0 + k) ^ (q4 & 7)) << 2) + (lane & 3)];
             }
           }
@@ -607,9 +611,9 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_bwd_kernel(const BwdParam
         for (int b = 0; b < NB; ++b) {
           const int sq = 32 * b + lane;
           const int q = (cgrp * NG + g) * NQ + sq;
-          float da[4][4];
+          float da[4][UPW];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
+          for (int k = 0; k < UPW; ++k) {
             const float i_ = act[b][0][k], f_ = act[b][1][k], g_ = act[b][2][k], o_ = act[b][3][k];
             const float tc = tanh_fast(c_cur[g][b][k]);
             const float dhu = dh[b][k];
@@ -626,17 +630,16 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_bwd_kernel(const BwdParam
 #pragma unroll
             for (int gt = 0; gt < 4; ++gt)
 #pragma unroll
-              for (int k = 0; k < 4; ++k) Gs[((int64_t)gt * Hd + k) * p.ld] = da[gt][k];
+              for (int k = 0; k < UPW; ++k) Gs[((int64_t)gt * Hd + k) * p.ld] = da[gt][k];
           }
           if (t + 1 < S) {
-            const uint32_t off = sw64_off(sq, warp >> 1) + (warp & 1) * 8;
+            const uint32_t off = sw64_off(sq, warp >> 2) + (warp & 3) * 4;
 #pragma unroll
             for (int gt = 0; gt < 4; ++gt) {
-              uint32_t h0, l0, h1, l1;
+              uint32_t h0, l0;
               split_bf16x2(da[gt][0], da[gt][1], h0, l0);
-              split_bf16x2(da[gt][2], da[gt][3], h1, l1);
-              *reinterpret_cast<uint2*>(bbuf + gt * 2 * SLAB + off) = make_uint2(h0, h1);
-              *reinterpret_cast<uint2*>(bbuf + gt * 2 * SLAB + SLAB + off) = make_uint2(l0, l1);
+              *reinterpret_cast<uint32_t*>(bbuf + gt * 2 * SLAB + off) = h0;
+              *reinterpret_cast<uint32_t*>(bbuf + gt * 2 * SLAB + SLAB + off) = l0;
             }
           }
         }
@@ -661,25 +664,24 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_bwd_kernel(const BwdParam
           if (tid == 0) LR_STAMP(5);
           if (t > 0) mbar_wait_cluster(bar_rfree(g), (t - 1) & 1);
           if (tid == 0) LR_STAMP(6);
-          const int mb = warp >> 2;
+          const int mb = (warp >> 2) & 1, ch = warp >> 3;      // M block, column half
           const int m0 = mb * 128 + (warp & 3) * 32;            // hidden units of this warp's TMEM lanes (warp-uniform)
           if (mb < MB && m0 < Hd) {
+            constexpr int NCOL = NQ / 2;
             const uint32_t dst = (uint32_t)(m0 >> 5);
             const uint32_t rbase = mapa(base + K::OFF_R + g * K::RBUF + rank * K::RSLAB, dst);
-            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + K::COL_D + (g * MB + mb) * NQ;
+            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + K::COL_D + (g * MB + mb) * NQ + ch * NCOL;
+            uint32_t acc[NCOL];
+            if constexpr (NCOL == 32) tc_ld32_nowait(taddr, acc);
+            else tc_ld16_nowait(taddr, acc);
+            tc_ld_wait();
 #pragma unroll
-            for (int cb = 0; cb < NB; ++cb) {
-              uint32_t acc[32];
-              tc_ld32_nowait(taddr + 32 * cb, acc);
-              tc_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int q4 = 8 * cb + i;
-                float4 v;
-                v.x = __uint_as_float(acc[4 * i + 0]); v.y = __uint_as_float(acc[4 * i + 1]);
-                v.z = __uint_as_float(acc[4 * i + 2]); v.w = __uint_as_float(acc[4 * i + 3]);
-                st_cluster_v4(rbase + q4 * 512 + ((lane ^ (q4 & 7)) << 4), v);
-              }
+            for (int i = 0; i < NCOL / 4; ++i) {
+              const int q4 = ch * (NCOL / 4) + i;
+              float4 v;
+              v.x = __uint_as_float(acc[4 * i + 0]); v.y = __uint_as_float(acc[4 * i + 1]);
+              v.z = __uint_as_float(acc[4 * i + 2]); v.w = __uint_as_float(acc[4 * i + 3]);
+              st_cluster_v4(rbase + q4 * 512 + ((lane ^ (q4 & 7)) << 4), v);
             }
             __syncwarp();
             if (lane == 0) {
@@ -696,7 +698,7 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_bwd_kernel(const BwdParam
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
-  if (warp == 8) {
+  if (warp == MMA_WARP) {
     tc_fence_after();
     tmem_dealloc<K::TCOLS>(tmem_base);
   }
