@@ -409,7 +409,7 @@ typedef struct {
   float* G; float* H; float* C;
   const float* Whh_f; const float* Whh_r;   /* [4*Hd][Hd] each, nn.LSTM weight_hh_l0 / weight_hh_l0_reverse */
   const float* dH;          /* bwd only */
-  int seqs_per_cluster;     /* 0 = automatic; 32 / 64 / 128 force the grouping (tests, tuning) */
+  int seqs_per_cluster;     /* 0 = automatic; 64 / 128 force the grouping (tests, tuning) */
   void* prof;               /* optional (NULL = off): int64 [16][16] SM-clock stamps of cluster 0 for 16 steps (tools/time_lstm_rec.py) */
 } WesepLstmRecArgs;
 int wesep_b200_lstm_rec_supported(int Hd);

@@ -75,7 +75,7 @@ if __name__ == "__main__":
     profile(64, 512, 256, 128)
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 16
     t0 = time.time()
-    for seqs in (32, 64, 128):
+    for seqs in (64, 128):
         run(501, 32 * n, 256, seqs=seqs)
     for seqs in (64, 128):
         run(32, 501 * n, 256, seqs=seqs)

@@ -2,7 +2,7 @@
 //
 // The recurrence a_t = P_t + W_hh . h_{t-1} (P = input projection + biases, one big GEMM done beforehand) is serial in t
 // but independent across sequences, so ONE launch runs all S steps of both directions:
-//   * a cluster of C = Hd / 32 CTAs owns NG groups of NQ = 32 NB sequences of one direction for the whole sequence;
+//   * a cluster of C = Hd / 32 CTAs owns NG groups of NQ = 64 sequences of one direction for the whole sequence;
 //   * CTA `rank` owns hidden units [32 rank, 32 rank + 32) = 128 gate rows (i | f | g | o blocks of 32).  ITS [128 x Hd]
 //     slice of W_hh stays resident in TENSOR MEMORY for all steps as the A operand of the step product (fp16 hi + lo with a
 //     per-row power-of-two scale: 22 mantissa bits, undone exactly in the epilogue) — shared memory then only holds the
@@ -34,8 +34,7 @@ namespace lr {
 using namespace tcx;
 
 constexpr int MAXC = 8;                // cluster size = Hd / 32
-constexpr int NW = 16;                 // cell warps: warp w owns hidden units [2w, 2w + 2) of the CTA (lane = sequence)
-constexpr int UPW = 32 / NW;           // units per cell warp
+constexpr int NW = 16;                 // cell warps: 512 threads = 32 hidden units x 16 sequence quads
 constexpr int THREADS = 32 * NW + 32;  // warps 0-15: TMEM drain / cell (4 per scheduler: the cell is latency-bound), warp 16: MMA issuer + TMEM owner
 constexpr int MMA_WARP = NW;
 constexpr float H_SCALE = 4096.f;      // h in (-1, 1) -> fp16 hi + lo of 4096 h
@@ -45,14 +44,17 @@ __host__ __device__ constexpr uint32_t pow2_cols(int need) {
   return need <= 32 ? 32u : need <= 64 ? 64u : need <= 128 ? 128u : need <= 256 ? 256u : 512u;
 }
 
-template <int C, int NB, int NG>
+constexpr int NQ = 64;                 // sequences per group (N of the step product)
+constexpr int SLAB = 32 * 128;         // one K block (32 K rows x 64 sequences x 2 B) of a B operand, hi or lo (MN-major, SW128)
+
+template <int C, int NG>
 struct FwdCfg {
-  static constexpr int NQ = 32 * NB;                 // sequences per group
-  static constexpr int SLAB = NQ * 64;               // one K block (32 hidden units) of a group's h, hi or lo
   static constexpr int HBUF = C * 2 * SLAB;          // operand buffer of one group: C x [hi slab | lo slab]
   static constexpr int OFF_H = 0;
-  static constexpr int OFF_STG = NG * HBUF;          // [128 rows][NQ] fp32, 16-byte chunks XOR-swizzled by row
-  static constexpr int OFF_RS = OFF_STG + 128 * NQ * 4;
+  static constexpr int OFF_OUT = NG * HBUF;          // outgoing copy of my slab, double-buffered per group: [NG][2][hi | lo]
+  static constexpr int OFF_STG = OFF_OUT + NG * 2 * 2 * SLAB;   // 2 x [128 rows][NQ] fp32, 16-byte chunks XOR-swizzled by row
+  static constexpr int STG_BYTES = 128 * NQ * 4;
+  static constexpr int OFF_RS = OFF_STG + 2 * STG_BYTES;
   static constexpr int OFF_BAR = OFF_RS + 512;
   static constexpr int SMEM = OFF_BAR + 128 + 1024;  // + alignment slack
   static constexpr int COL_WHI = 0, COL_WLO = 16 * C, COL_D = 32 * C;   // TMEM columns
@@ -105,6 +107,12 @@ __device__ __forceinline__ void gates_fast(float ai, float af, float ag, float a
 }
 
 __device__ __forceinline__ void named_sync_epi() { asm volatile("bar.sync 1, 512;\n" ::: "memory"); }
+// barrier 2: the cell warps only ARRIVE (they go on to the next item), warp 0 waits for all of them before it publishes
+// the slab / signals the MMA thread
+// (one barrier id per group: consecutive publications of DIFFERENT groups are not separated by a full barrier, and an
+// early second arrival on the same id would corrupt its phase)
+__device__ __forceinline__ void named_arrive_pub(int g) { asm volatile("bar.arrive %0, 512;\n" ::"r"(2 + g) : "memory"); }
+__device__ __forceinline__ void named_sync_pub(int g) { asm volatile("bar.sync %0, 512;\n" ::"r"(2 + g) : "memory"); }
 static_assert(NW == 16, "named_sync_epi / column split assume 16 cell warps");
 
 __device__ __forceinline__ void tc_ld8_nowait(uint32_t taddr, uint32_t* r) {
@@ -144,11 +152,11 @@ __device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, 
 __device__ __forceinline__ void fence_cluster() { asm volatile("fence.acq_rel.cluster;\n" ::: "memory"); }
 
 // ================================================================================================ forward
-template <int C, int NB, int NG>
+template <int C, int NG>
 __global__ void __launch_bounds__(THREADS, 1) lstm_rec_fwd_kernel(const FwdParams p) {
-  using K = FwdCfg<C, NB, NG>;
-  constexpr int NQ = K::NQ, SLAB = K::SLAB, HBUF = K::HBUF, Hd = 32 * C;
-  constexpr uint32_t IDESC = idesc_f16(128, NQ, 0);
+  using K = FwdCfg<C, NG>;
+  constexpr int HBUF = K::HBUF, Hd = 32 * C;
+  constexpr uint32_t IDESC = idesc_f16(128, NQ, 0, 1);          // fp16 operands, B MN-major
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -232,9 +240,9 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_fwd_kernel(const FwdParam
           const uint32_t d = tmem_base + K::COL_D + g * NQ;
           const uint32_t hb = base + K::OFF_H + g * HBUF;
 #pragma unroll
-          for (int j = 0; j < 2 * C; ++j) {       // K step of 16: K block j / 2, half j % 2
-            const uint64_t b_hi = desc_k_sw64(hb + (j >> 1) * 2 * SLAB + (j & 1) * 32);
-            const uint64_t b_lo = desc_k_sw64(hb + (j >> 1) * 2 * SLAB + SLAB + (j & 1) * 32);
+          for (int j = 0; j < 2 * C; ++j) {       // K step of 16 = two 8-row atoms: K block j / 2, half j % 2
+            const uint64_t b_hi = desc_mn_sw128(hb + (j >> 1) * 2 * SLAB + (j & 1) * 2048);
+            const uint64_t b_lo = desc_mn_sw128(hb + (j >> 1) * 2 * SLAB + SLAB + (j & 1) * 2048);
             const uint32_t a_hi = tmem_base + K::COL_WHI + 8 * j, a_lo = tmem_base + K::COL_WLO + 8 * j;
             tc_mma_f16_ts(d, a_lo, b_hi, IDESC, j ? 1u : 0u);
             tc_mma_f16_ts(d, a_hi, b_lo, IDESC, 1u);
@@ -248,59 +256,49 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_fwd_kernel(const FwdParam
     }
     __syncwarp();
   } else {
-    // ================================================= TMEM drain + cell warps: warp w owns hidden units [2w, 2w + 2) of the
-    // CTA, lane = sequence within a 32-sequence block
-    const int u0 = UPW * warp;
-    const int row_g0 = dir * 4 * Hd + 32 * (int)rank + u0;     // G row of (gate 0, unit 0 of this thread)
-    const int row_h0 = dir * Hd + 32 * (int)rank + u0;
-    float c[NG][NB][UPW];
+    // ================================================= TMEM drain + cell warps.  Cell phase: thread = (hidden unit u of the CTA,
+    // quad of 4 consecutive sequences) so that every global / shared access is a 16-byte vector (the cell is bound by the
+    // number of LSU instructions, not by bytes)
+    const int u = tid >> 4, qd = tid & 15;
+    const int64_t row_g = (int64_t)(dir * 4 * Hd + 32 * (int)rank + u) * p.ld;   // gate 0 row of this unit
+    const int64_t row_h = (int64_t)(dir * Hd + 32 * (int)rank + u) * p.ld;
+    const int64_t gstride = (int64_t)Hd * p.ld;
+    float c[NG][4];
 #pragma unroll
     for (int g = 0; g < NG; ++g)
 #pragma unroll
-      for (int b = 0; b < NB; ++b)
-#pragma unroll
-        for (int k = 0; k < UPW; ++k) c[g][b][k] = 0.f;
-    const float* stg = reinterpret_cast<const float*>(gbase + K::OFF_STG);
-    float nxt[NB][4][UPW];
+      for (int k = 0; k < 4; ++k) c[g][k] = 0.f;
+    float4 nxt[NG][4];                                        // pre-activations of each group's NEXT step (a whole item ahead)
     auto load_pre = [&](int t, int g) {
       const int s = dir ? S - 1 - t : t;
+      const int q = (cgrp * NG + g) * NQ + 4 * qd;
+      const float* Gs = p.G + (int64_t)s * p.bsG + row_g + q;
 #pragma unroll
-      for (int b = 0; b < NB; ++b) {
-        const int q = (cgrp * NG + g) * NQ + 32 * b + lane;
-        const float* Gs = p.G + (int64_t)s * p.bsG + (int64_t)row_g0 * p.ld + q;
-#pragma unroll
-        for (int gt = 0; gt < 4; ++gt)
-#pragma unroll
-          for (int k = 0; k < UPW; ++k) nxt[b][gt][k] = q < p.Q ? __ldcs(Gs + ((int64_t)gt * Hd + k) * p.ld) : 0.f;
-      }
+      for (int gt = 0; gt < 4; ++gt)
+        nxt[g][gt] = q < p.Q ? __ldcs(reinterpret_cast<const float4*>(Gs + gt * gstride)) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
-    load_pre(0, 0);
+#pragma unroll
+    for (int g = 0; g < NG; ++g) load_pre(0, g);
+    uint32_t item = 0;                                        // staging tile parity
     for (int t = 0; t < S; ++t) {
       const int s = dir ? S - 1 - t : t;
 #pragma unroll
-      for (int g = 0; g < NG; ++g) {
-        float pre[NB][4][UPW];
-#pragma unroll
-        for (int b = 0; b < NB; ++b)
-#pragma unroll
-          for (int gt = 0; gt < 4; ++gt)
-#pragma unroll
-            for (int k = 0; k < UPW; ++k) pre[b][gt][k] = nxt[b][gt][k];
+      for (int g = 0; g < NG; ++g, ++item) {
+        float pre[4][4];
+        uint8_t* stg = gbase + K::OFF_STG + (item & 1) * K::STG_BYTES;
         if (tid == 0) LR_STAMP(0);
         if (t > 0) {
           mbar_wait(bar_acc(g), (t - 1) & 1);
           tc_fence_after();
           if (tid == 0) LR_STAMP(1);
-          {   // phase 1: lane = gate row; TMEM -> registers -> descale -> staging (so that phase 2 can read by sequence)
+          {   // phase 1: lane = gate row; TMEM -> registers -> descale -> staging (so that the cell can read by sequence)
             constexpr int NCOL = NQ / 4;               // warps w, w + 4, w + 8, w + 12 share a lane quarter and split the columns
             const int r = (warp & 3) * 32 + lane, c0 = (warp >> 2) * NCOL;
             uint32_t acc[NCOL];
-            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + K::COL_D + g * NQ + c0;
-            if constexpr (NCOL == 16) tc_ld16_nowait(taddr, acc);
-            else tc_ld8_nowait(taddr, acc);
+            tc_ld16_nowait(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + K::COL_D + g * NQ + c0, acc);
             tc_ld_wait();
             const float sc = rs[r];
-            uint8_t* row = gbase + K::OFF_STG + r * (NQ * 4);
+            uint8_t* row = stg + r * (NQ * 4);
 #pragma unroll
             for (int ch = 0; ch < NCOL / 4; ++ch) {
               float4 v;
@@ -313,93 +311,91 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_fwd_kernel(const FwdParam
           }
           tc_fence_before();
           if (tid == 0) LR_STAMP(2);
-          // every CTA of the cluster has finished the MMAs of (t, g) => all copies of h_{t-1} (mine included) have been
-          // consumed: my slab and the remote buffers of this group may be overwritten with h_t
-          if (tid == 0) mbar_wait(bar_hfree(g), (t - 1) & 1);
           named_sync_epi();
           if (tid == 0) LR_STAMP(3);
 #pragma unroll
-          for (int b = 0; b < NB; ++b) {
-            const int sq = 32 * b + lane;
+          for (int gt = 0; gt < 4; ++gt) {
+            const int r = gt * 32 + u;
+            const float4 v = *reinterpret_cast<const float4*>(stg + r * (NQ * 4) + ((qd ^ (r & 7)) << 4));
+            const float4 n4 = nxt[g][gt];
+            pre[gt][0] = n4.x + v.x; pre[gt][1] = n4.y + v.y; pre[gt][2] = n4.z + v.z; pre[gt][3] = n4.w + v.w;
+          }
+        } else {
 #pragma unroll
-            for (int gt = 0; gt < 4; ++gt)
-#pragma unroll
-              for (int k = 0; k < UPW; ++k) {
-                const int r = gt * 32 + u0 + k;
-                pre[b][gt][k] += stg[r * NQ + ((((sq >> 2) ^ (r & 7))) << 2) + (sq & 3)];
-              }
+          for (int gt = 0; gt < 4; ++gt) {
+            const float4 n4 = nxt[g][gt];
+            pre[gt][0] = n4.x; pre[gt][1] = n4.y; pre[gt][2] = n4.z; pre[gt][3] = n4.w;
           }
         }
         // ---- cell (nn.LSTM gate order i | f | g | o), global writes, h_t -> fp16 hi / lo into my slab of the operand buffer
-        uint8_t* slab = gbase + K::OFF_H + g * HBUF + rank * (2 * SLAB);
+        const int q = (cgrp * NG + g) * NQ + 4 * qd;
+        const int nv = p.Q - q;                                  // valid sequences of this quad (<= 0: none)
+        float hq[4];
 #pragma unroll
-        for (int b = 0; b < NB; ++b) {
-          const int sq = 32 * b + lane;
-          const int q = (cgrp * NG + g) * NQ + sq;
-          float hq[UPW];
+        for (int k = 0; k < 4; ++k) {
+          float i_, f_, g_, o_;
+          gates_fast(pre[0][k], pre[1][k], pre[2][k], pre[3][k], i_, f_, g_, o_);
+          const float cn = fmaf(f_, c[g][k], i_ * g_);
+          const float hn = o_ * tanh_fast(cn);
+          const bool ok = k < nv;                                // pad columns carry zeros
+          c[g][k] = ok ? cn : 0.f;
+          hq[k] = ok ? hn : 0.f;
+          pre[0][k] = ok ? i_ : 0.f; pre[1][k] = ok ? f_ : 0.f; pre[2][k] = ok ? g_ : 0.f; pre[3][k] = ok ? o_ : 0.f;
+        }
+        if (q < p.ld) {
+          float* Gs = p.G + (int64_t)s * p.bsG + row_g + q;
 #pragma unroll
-          for (int k = 0; k < UPW; ++k) {
-            float i_, f_, g_, o_;
-            gates_fast(pre[b][0][k], pre[b][1][k], pre[b][2][k], pre[b][3][k], i_, f_, g_, o_);
-            const float cn = fmaf(f_, c[g][b][k], i_ * g_);
-            c[g][b][k] = cn;
-            hq[k] = o_ * tanh_fast(cn);
-            pre[b][0][k] = i_; pre[b][1][k] = f_; pre[b][2][k] = g_; pre[b][3][k] = o_;
-          }
-          float* Gs = p.G + (int64_t)s * p.bsG + (int64_t)row_g0 * p.ld + q;
-          float* Hs = p.H + (int64_t)s * p.bsH + (int64_t)row_h0 * p.ld + q;
-          float* Cc = p.Cs + (int64_t)s * p.bsH + (int64_t)row_h0 * p.ld + q;
-          if (q < p.Q) {
+          for (int gt = 0; gt < 4; ++gt)
+            __stcs(reinterpret_cast<float4*>(Gs + gt * gstride), make_float4(pre[gt][0], pre[gt][1], pre[gt][2], pre[gt][3]));
+          __stcs(reinterpret_cast<float4*>(p.Cs + (int64_t)s * p.bsH + row_h + q), make_float4(c[g][0], c[g][1], c[g][2], c[g][3]));
+          *reinterpret_cast<float4*>(p.H + (int64_t)s * p.bsH + row_h + q) = make_float4(hq[0], hq[1], hq[2], hq[3]);
+        }
+        if (t + 1 < S) {
+          // B operand of the next step, MN-major: K row = my unit, 4 consecutive sequences = 8 bytes
+          uint32_t hi[2], lo[2];
 #pragma unroll
-            for (int gt = 0; gt < 4; ++gt)
-#pragma unroll
-              for (int k = 0; k < UPW; ++k) __stcs(Gs + ((int64_t)gt * Hd + k) * p.ld, pre[b][gt][k]);
-#pragma unroll
-            for (int k = 0; k < UPW; ++k) {
-              __stcs(Cc + (int64_t)k * p.ld, c[g][b][k]);
-              Hs[(int64_t)k * p.ld] = hq[k];
-            }
-          } else {
-            if (q < p.ld) {   // pad columns of the row stride: zeros (cold path, last group only)
-              for (int gt = 0; gt < 4; ++gt)
-                for (int k = 0; k < UPW; ++k) Gs[((int64_t)gt * Hd + k) * p.ld] = 0.f;
-              for (int k = 0; k < UPW; ++k) { Cc[(int64_t)k * p.ld] = 0.f; Hs[(int64_t)k * p.ld] = 0.f; }
-            }
-#pragma unroll
-            for (int k = 0; k < UPW; ++k) { hq[k] = 0.f; c[g][b][k] = 0.f; }
-          }
-          if (t + 1 < S) {
-            static_assert(UPW == 2, "slab write packs one fp16 pair per thread");
-            const float a = hq[0] * H_SCALE, bb = hq[1] * H_SCALE;
+          for (int j = 0; j < 2; ++j) {
+            const float a = hq[2 * j] * H_SCALE, bb = hq[2 * j + 1] * H_SCALE;
             const __half2 h2 = __floats2half2_rn(a, bb);
             const float2 hf = __half22float2(h2);
             const __half2 l2 = __floats2half2_rn(a - hf.x, bb - hf.y);
-            const uint32_t off = sw64_off(sq, warp >> 2) + (warp & 3) * 4;   // units 2w, 2w + 1 = bytes [4w, 4w + 4) of the row
-            *reinterpret_cast<uint32_t*>(slab + off) = *reinterpret_cast<const uint32_t*>(&h2);
-            *reinterpret_cast<uint32_t*>(slab + SLAB + off) = *reinterpret_cast<const uint32_t*>(&l2);
+            hi[j] = *reinterpret_cast<const uint32_t*>(&h2);
+            lo[j] = *reinterpret_cast<const uint32_t*>(&l2);
+          }
+          // my own operand buffer (my MMAs of (t, g) are done: bar_acc) and the outgoing copy (buffer t & 1: the copies of
+          // step t - 2 out of it completed before the hfree wait of step t - 1)
+          uint8_t* slab = gbase + K::OFF_H + g * HBUF + rank * (2 * SLAB);
+          uint8_t* outb = gbase + K::OFF_OUT + (g * 2 + (t & 1)) * (2 * SLAB);
+          const uint32_t off = sw128_off(u, qd >> 1) + (qd & 1) * 8;
+          *reinterpret_cast<uint2*>(slab + off) = make_uint2(hi[0], hi[1]);
+          *reinterpret_cast<uint2*>(slab + SLAB + off) = make_uint2(lo[0], lo[1]);
+          if (C > 1) {
+            *reinterpret_cast<uint2*>(outb + off) = make_uint2(hi[0], hi[1]);
+            *reinterpret_cast<uint2*>(outb + SLAB + off) = make_uint2(lo[0], lo[1]);
           }
         }
         if (tid == 0) LR_STAMP(5);
-        // prefetch the next item's pre-activations while the exchange / the other group's MMAs run
-        {
-          const int gn = (g + 1) % NG, tn = t + (g + 1) / NG;
-          if (tn < S) load_pre(tn, gn);
-        }
+        // prefetch this group's next pre-activations: a whole item (the other group's) of latency to hide behind
+        if (t + 1 < S) load_pre(t + 1, g);
         if (t + 1 < S) {
           fence_proxy_async();
-          named_sync_epi();
-          if (tid == 0) LR_STAMP(6);
-          if (warp == 0) {
-            const uint32_t src = base + K::OFF_H + g * HBUF + rank * (2 * SLAB);
+          if (warp != 0) {
+            named_arrive_pub(g);
+          } else {
+            named_sync_pub(g);            // every cell thread has written its part of the slab
+            if (tid == 0) LR_STAMP(6);
+            // every CTA of the cluster has finished the MMAs of (t, g) => all copies of h_{t-1} have been consumed and the
+            // remote operand buffers of this group may be overwritten with h_t
+            if (t > 0) mbar_wait(bar_hfree(g), (t - 1) & 1);
+            const uint32_t src = base + K::OFF_OUT + (g * 2 + (t & 1)) * (2 * SLAB);
+            const uint32_t dst = base + K::OFF_H + g * HBUF + rank * (2 * SLAB);
             if (lane == 0) {
               if (C > 1) mbar_arrive_expect_tx(bar_hfull(g), (uint32_t)(C - 1) * 2 * SLAB);
               else mbar_arrive(bar_hfull(g));
             }
-            if (lane < C && lane != (int)rank) bulk_copy_s2c(mapa(src, lane), src, 2 * SLAB, mapa(bar_hfull(g), lane));
+            if (lane < C && lane != (int)rank) bulk_copy_s2c(mapa(dst, lane), src, 2 * SLAB, mapa(bar_hfull(g), lane));
+            if (tid == 0) LR_STAMP(7);
           }
-          if (tid == 0) LR_STAMP(7);
-        } else if (NG > 1 && g + 1 < NG) {
-          named_sync_epi();          // the staging tile is shared by the groups
         }
       }
     }
@@ -421,12 +417,10 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_fwd_kernel(const FwdParam
 //   MMA    : D[Hd hidden][NQ] = A[m][k] . B[seq][k], A = W_hh[gate rows of this CTA]^T resident in TMEM, K = 128
 //   phase A: TMEM lanes [32 w', 32 w' + 32) of M block mb are the hidden units of CTA 4 mb + w': coalesced
 //            st.shared::cluster into that CTA's receive slab for this source, one fence + one remote arrive per warp.
-template <int C, int NB, int NG>
+template <int C, int NG>
 struct BwdCfg {
-  static constexpr int NQ = 32 * NB;
   static constexpr int MB = (32 * C + 127) / 128;        // M blocks of 128 hidden units
-  static constexpr int SLAB = NQ * 64;                   // one K block (32 gate rows) of a group's da, hi or lo
-  static constexpr int BBUF = 4 * 2 * SLAB;              // B operand of one group
+  static constexpr int BBUF = 4 * 2 * SLAB;              // B operand of one group: 4 K blocks (gates) x [hi | lo]
   static constexpr int RSLAB = 32 * NQ * 4;              // partial sums of one source CTA for my 32 units
   static constexpr int RBUF = C * RSLAB;
   static constexpr int OFF_B = 0;
@@ -453,11 +447,11 @@ __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uin
   lo = *reinterpret_cast<const uint32_t*>(&l2);
 }
 
-template <int C, int NB, int NG>
+template <int C, int NG>
 __global__ void __launch_bounds__(THREADS, 1) lstm_rec_bwd_kernel(const BwdParams p) {
-  using K = BwdCfg<C, NB, NG>;
-  constexpr int NQ = K::NQ, SLAB = K::SLAB, MB = K::MB, Hd = 32 * C;
-  constexpr uint32_t IDESC = idesc_f16(128, NQ, 1);
+  using K = BwdCfg<C, NG>;
+  constexpr int MB = K::MB, Hd = 32 * C;
+  constexpr uint32_t IDESC = idesc_f16(128, NQ, 1, 1);          // bf16 operands, B MN-major
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -530,8 +524,8 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_bwd_kernel(const BwdParam
             const uint32_t d = tmem_base + K::COL_D + (g * MB + mb) * NQ;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const uint64_t b_hi = desc_k_sw64(bb + (j >> 1) * 2 * SLAB + (j & 1) * 32);
-              const uint64_t b_lo = desc_k_sw64(bb + (j >> 1) * 2 * SLAB + SLAB + (j & 1) * 32);
+              const uint64_t b_hi = desc_mn_sw128(bb + (j >> 1) * 2 * SLAB + (j & 1) * 2048);
+              const uint64_t b_lo = desc_mn_sw128(bb + (j >> 1) * 2 * SLAB + SLAB + (j & 1) * 2048);
               const uint32_t a_hi = tmem_base + K::COL_AHI + mb * 64 + 8 * j, a_lo = tmem_base + K::COL_ALO + mb * 64 + 8 * j;
               tc_mma_f16_ts(d, a_lo, b_hi, IDESC, j ? 1u : 0u);
               tc_mma_f16_ts(d, a_hi, b_lo, IDESC, 1u);
@@ -545,23 +539,22 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_bwd_kernel(const BwdParam
     }
     __syncwarp();
   } else {
-    const int u0 = UPW * warp;
-    const int row_g0 = dir * 4 * Hd + 32 * (int)rank + u0;
-    const int row_h0 = dir * Hd + 32 * (int)rank + u0;
-    float dc[NG][NB][UPW], c_cur[NG][NB][UPW];
+    // cell threads: (hidden unit u of the CTA, quad of 4 consecutive sequences), 16-byte accesses everywhere
+    const int u = tid >> 4, qd = tid & 15;
+    const int64_t row_g = (int64_t)(dir * 4 * Hd + 32 * (int)rank + u) * p.ld;
+    const int64_t row_h = (int64_t)(dir * Hd + 32 * (int)rank + u) * p.ld;
+    const int64_t gstride = (int64_t)Hd * p.ld;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float dc[NG][4], c_cur[NG][4];
 #pragma unroll
-    for (int g = 0; g < NG; ++g)
+    for (int g = 0; g < NG; ++g) {
+      const int q = (cgrp * NG + g) * NQ + 4 * qd;
+      const int s = dir ? 0 : S - 1;                           // first processed step
+      const float4 v = q < p.Q ? __ldcs(reinterpret_cast<const float4*>(p.Cs + (int64_t)s * p.bsH + row_h + q)) : zero4;
+      c_cur[g][0] = v.x; c_cur[g][1] = v.y; c_cur[g][2] = v.z; c_cur[g][3] = v.w;
 #pragma unroll
-      for (int b = 0; b < NB; ++b) {
-        const int q = (cgrp * NG + g) * NQ + 32 * b + lane;
-        const int s = dir ? 0 : S - 1;                           // first processed step
-        const float* Cc = p.Cs + (int64_t)s * p.bsH + (int64_t)row_h0 * p.ld + q;
-#pragma unroll
-        for (int k = 0; k < UPW; ++k) {
-          dc[g][b][k] = 0.f;
-          c_cur[g][b][k] = q < p.Q ? __ldcs(Cc + (int64_t)k * p.ld) : 0.f;
-        }
-      }
+      for (int k = 0; k < 4; ++k) dc[g][k] = 0.f;
+    }
     for (int t = 0; t < S; ++t) {                                // t = backward iteration; tf = forward processing index
       const int tf = S - 1 - t;
       const int s = dir ? S - 1 - tf : tf;
@@ -570,84 +563,71 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_bwd_kernel(const BwdParam
 #pragma unroll
       for (int g = 0; g < NG; ++g) {
         if (tid == 0) LR_STAMP(0);
-        float act[NB][4][UPW], dh[NB][UPW], c_prev[NB][UPW];
+        const int q = (cgrp * NG + g) * NQ + 4 * qd;
+        const int nv = p.Q - q;
+        const bool any = q < p.Q;
+        float* Gs = p.G + (int64_t)s * p.bsG + row_g + q;
+        float4 a4[4];
 #pragma unroll
-        for (int b = 0; b < NB; ++b) {
-          const int q = (cgrp * NG + g) * NQ + 32 * b + lane;
-          const bool valid = q < p.Q;
-          const float* Gs = p.G + (int64_t)s * p.bsG + (int64_t)row_g0 * p.ld + q;
-          const float* dHs = p.dH + (int64_t)s * p.bsH + (int64_t)row_h0 * p.ld + q;
-          const float* Cp = p.Cs + (int64_t)sp * p.bsH + (int64_t)row_h0 * p.ld + q;
-#pragma unroll
-          for (int gt = 0; gt < 4; ++gt)
-#pragma unroll
-            for (int k = 0; k < UPW; ++k) act[b][gt][k] = valid ? __ldcs(Gs + ((int64_t)gt * Hd + k) * p.ld) : 0.f;
-#pragma unroll
-          for (int k = 0; k < UPW; ++k) {
-            dh[b][k] = valid ? __ldcs(dHs + (int64_t)k * p.ld) : 0.f;
-            c_prev[b][k] = (valid && tf > 0) ? __ldcs(Cp + (int64_t)k * p.ld) : 0.f;
-          }
-        }
+        for (int gt = 0; gt < 4; ++gt) a4[gt] = any ? __ldcs(reinterpret_cast<const float4*>(Gs + gt * gstride)) : zero4;
+        const float4 dh4 = any ? __ldcs(reinterpret_cast<const float4*>(p.dH + (int64_t)s * p.bsH + row_h + q)) : zero4;
+        const float4 cp4 = (any && tf > 0) ? __ldcs(reinterpret_cast<const float4*>(p.Cs + (int64_t)sp * p.bsH + row_h + q)) : zero4;
+        float dh[4] = {dh4.x, dh4.y, dh4.z, dh4.w};
+        const float c_prev[4] = {cp4.x, cp4.y, cp4.z, cp4.w};
         if (t > 0) {
-          // ---- recurrent gradient: sum of the C partial products of round t - 1 for my 4 units
+          // ---- recurrent gradient: sum of the C partial products of round t - 1 for my unit
           mbar_wait_cluster(bar_rfull(g), (t - 1) & 1);
           if (tid == 0) LR_STAMP(1);
-          const float* R = reinterpret_cast<const float*>(gbase + K::OFF_R + g * K::RBUF);
+          const uint8_t* R = gbase + K::OFF_R + g * K::RBUF + qd * 512 + ((u ^ (qd & 7)) << 4);
 #pragma unroll
-          for (int b = 0; b < NB; ++b) {
-            const int q4 = 8 * b + (lane >> 2);
-#pragma unroll
-            for (int src = 0; src < C; ++src) {
-#pragma unroll
-              for (int k = 0; k < UPW; ++k)
-                dh[b][k] += R[src * (K::RSLAB / 4) + q4 * 128 + (((u0 + k) ^ (q4 & 7)) << 2) + (lane & 3)];
-            }
+          for (int src = 0; src < C; ++src) {
+            const float4 v = *reinterpret_cast<const float4*>(R + src * K::RSLAB);
+            dh[0] += v.x; dh[1] += v.y; dh[2] += v.z; dh[3] += v.w;
           }
         }
         if (tid == 0) LR_STAMP(2);
-        // ---- cell backward, da -> global (over the activations) and -> bf16 hi / lo B operand
-        uint8_t* bbuf = gbase + K::OFF_B + g * K::BBUF;
+        // ---- cell backward, da -> global (over the activations) and -> bf16 hi / lo B operand (MN-major: K row = gate * 32 + u)
+        const float ai[4] = {a4[0].x, a4[0].y, a4[0].z, a4[0].w}, af[4] = {a4[1].x, a4[1].y, a4[1].z, a4[1].w};
+        const float ag[4] = {a4[2].x, a4[2].y, a4[2].z, a4[2].w}, ao[4] = {a4[3].x, a4[3].y, a4[3].z, a4[3].w};
+        float da[4][4];
 #pragma unroll
-        for (int b = 0; b < NB; ++b) {
-          const int sq = 32 * b + lane;
-          const int q = (cgrp * NG + g) * NQ + sq;
-          float da[4][UPW];
+        for (int k = 0; k < 4; ++k) {
+          const bool ok = k < nv;                               // pad columns: zeros
+          const float i_ = ai[k], f_ = af[k], g_ = ag[k], o_ = ao[k];
+          const float tc = tanh_fast(c_cur[g][k]);
+          const float dhu = ok ? dh[k] : 0.f;
+          const float dcu = ok ? fmaf(dhu * o_, 1.f - tc * tc, dc[g][k]) : 0.f;
+          da[0][k] = dcu * g_ * i_ * (1.f - i_);
+          da[1][k] = dcu * c_prev[k] * f_ * (1.f - f_);
+          da[2][k] = dcu * i_ * (1.f - g_ * g_);
+          da[3][k] = dhu * tc * o_ * (1.f - o_);
+          dc[g][k] = dcu * f_;
+          c_cur[g][k] = c_prev[k];
+        }
+        if (q < p.ld) {
 #pragma unroll
-          for (int k = 0; k < UPW; ++k) {
-            const float i_ = act[b][0][k], f_ = act[b][1][k], g_ = act[b][2][k], o_ = act[b][3][k];
-            const float tc = tanh_fast(c_cur[g][b][k]);
-            const float dhu = dh[b][k];
-            const float dcu = fmaf(dhu * o_, 1.f - tc * tc, dc[g][b][k]);
-            da[0][k] = dcu * g_ * i_ * (1.f - i_);
-            da[1][k] = dcu * c_prev[b][k] * f_ * (1.f - f_);
-            da[2][k] = dcu * i_ * (1.f - g_ * g_);
-            da[3][k] = dhu * tc * o_ * (1.f - o_);
-            dc[g][b][k] = dcu * f_;
-            c_cur[g][b][k] = c_prev[b][k];
-          }
-          if (q < p.ld) {      // invalid (pad) columns carry zeros (act = dh = 0 there)
-            float* Gs = p.G + (int64_t)s * p.bsG + (int64_t)row_g0 * p.ld + q;
+          for (int gt = 0; gt < 4; ++gt)
+            *reinterpret_cast<float4*>(Gs + gt * gstride) = make_float4(da[gt][0], da[gt][1], da[gt][2], da[gt][3]);
+        }
+        if (t + 1 < S) {
+          uint8_t* bbuf = gbase + K::OFF_B + g * K::BBUF;
+          const uint32_t off = sw128_off(u, qd >> 1) + (qd & 1) * 8;
 #pragma unroll
-            for (int gt = 0; gt < 4; ++gt)
-#pragma unroll
-              for (int k = 0; k < UPW; ++k) Gs[((int64_t)gt * Hd + k) * p.ld] = da[gt][k];
-          }
-          if (t + 1 < S) {
-            const uint32_t off = sw64_off(sq, warp >> 2) + (warp & 3) * 4;
-#pragma unroll
-            for (int gt = 0; gt < 4; ++gt) {
-              uint32_t h0, l0;
-              split_bf16x2(da[gt][0], da[gt][1], h0, l0);
-              *reinterpret_cast<uint32_t*>(bbuf + gt * 2 * SLAB + off) = h0;
-              *reinterpret_cast<uint32_t*>(bbuf + gt * 2 * SLAB + SLAB + off) = l0;
-            }
+          for (int gt = 0; gt < 4; ++gt) {
+            uint32_t h0, l0, h1, l1;
+            split_bf16x2(da[gt][0], da[gt][1], h0, l0);
+            split_bf16x2(da[gt][2], da[gt][3], h1, l1);
+            *reinterpret_cast<uint2*>(bbuf + gt * 2 * SLAB + off) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2*>(bbuf + gt * 2 * SLAB + SLAB + off) = make_uint2(l0, l1);
           }
         }
         if (tid == 0) LR_STAMP(3);
         if (t + 1 < S) {
           fence_proxy_async();
-          named_sync_epi();
-          if (warp == 0) {
+          if (warp != 0) {
+            named_arrive_pub(g);
+          } else {
+            named_sync_pub(g);
             if (lane == 0) mbar_arrive(bar_bfull(g));
             // round t - 1 has been read by all my threads: its senders may reuse my receive slabs
             if (t > 0 && lane < C) mbar_arrive_remote(mapa(bar_rfree(g), lane));
@@ -670,10 +650,8 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_bwd_kernel(const BwdParam
             constexpr int NCOL = NQ / 2;
             const uint32_t dst = (uint32_t)(m0 >> 5);
             const uint32_t rbase = mapa(base + K::OFF_R + g * K::RBUF + rank * K::RSLAB, dst);
-            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + K::COL_D + (g * MB + mb) * NQ + ch * NCOL;
             uint32_t acc[NCOL];
-            if constexpr (NCOL == 32) tc_ld32_nowait(taddr, acc);
-            else tc_ld16_nowait(taddr, acc);
+            tc_ld32_nowait(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + K::COL_D + (g * MB + mb) * NQ + ch * NCOL, acc);
             tc_ld_wait();
 #pragma unroll
             for (int i = 0; i < NCOL / 4; ++i) {
@@ -737,21 +715,19 @@ static int max_clusters_of(Kern kern, int smem, int C) {
   return n;
 }
 
-// Sequences per cluster (capacity) -> (NB, NG): 32 -> (1, 1), 64 -> (2, 1), 128 -> (2, 2).  Pick the smallest capacity whose
-// cluster count fits in one wave (co-resident clusters, cached per hidden size); larger problems take 128.
+// Sequences per cluster (capacity) = 64 NG.  Pick the smaller one if its cluster count fits in one wave (co-resident
+// clusters, cached per hidden size); larger problems take 128 (two interleaved groups).
 static int pick_capacity(int Q, int maxc, int force) {
-  if (force == 32 || force == 64 || force == 128) return force;
-  for (int cap : {32, 64, 128})
-    if (2 * cdiv(Q, cap) <= maxc) return cap;
-  return 128;
+  if (force == 64 || force == 128) return force;
+  return 2 * cdiv(Q, 64) <= maxc ? 64 : 128;
 }
 
 template <int C>
 static int max_clusters_c(bool bwd) {
   static int cached[2] = {0, 0};
   if (!cached[bwd]) {
-    int n = bwd ? max_clusters_of(lstm_rec_bwd_kernel<C, 2, 2>, BwdCfg<C, 2, 2>::SMEM, C)
-                : max_clusters_of(lstm_rec_fwd_kernel<C, 2, 2>, FwdCfg<C, 2, 2>::SMEM, C);
+    int n = bwd ? max_clusters_of(lstm_rec_bwd_kernel<C, 2>, BwdCfg<C, 2>::SMEM, C)
+                : max_clusters_of(lstm_rec_fwd_kernel<C, 2>, FwdCfg<C, 2>::SMEM, C);
     cached[bwd] = n > 0 ? n : 1;
   }
   return cached[bwd];
@@ -761,17 +737,15 @@ template <int C>
 static int run_fwd(const FwdParams& p, int force, cudaStream_t st) {
   const int cap = pick_capacity(p.Q, max_clusters_c<C>(false), force);
   const int clusters = 2 * cdiv(p.Q, cap);
-  if (cap == 32) return launch_cluster(lstm_rec_fwd_kernel<C, 1, 1>, FwdCfg<C, 1, 1>::SMEM, C, clusters, p, st);
-  if (cap == 64) return launch_cluster(lstm_rec_fwd_kernel<C, 2, 1>, FwdCfg<C, 2, 1>::SMEM, C, clusters, p, st);
-  return launch_cluster(lstm_rec_fwd_kernel<C, 2, 2>, FwdCfg<C, 2, 2>::SMEM, C, clusters, p, st);
+  if (cap == 64) return launch_cluster(lstm_rec_fwd_kernel<C, 1>, FwdCfg<C, 1>::SMEM, C, clusters, p, st);
+  return launch_cluster(lstm_rec_fwd_kernel<C, 2>, FwdCfg<C, 2>::SMEM, C, clusters, p, st);
 }
 template <int C>
 static int run_bwd(const BwdParams& p, int force, cudaStream_t st) {
   const int cap = pick_capacity(p.Q, max_clusters_c<C>(true), force);
   const int clusters = 2 * cdiv(p.Q, cap);
-  if (cap == 32) return launch_cluster(lstm_rec_bwd_kernel<C, 1, 1>, BwdCfg<C, 1, 1>::SMEM, C, clusters, p, st);
-  if (cap == 64) return launch_cluster(lstm_rec_bwd_kernel<C, 2, 1>, BwdCfg<C, 2, 1>::SMEM, C, clusters, p, st);
-  return launch_cluster(lstm_rec_bwd_kernel<C, 2, 2>, BwdCfg<C, 2, 2>::SMEM, C, clusters, p, st);
+  if (cap == 64) return launch_cluster(lstm_rec_bwd_kernel<C, 1>, BwdCfg<C, 1>::SMEM, C, clusters, p, st);
+  return launch_cluster(lstm_rec_bwd_kernel<C, 2>, BwdCfg<C, 2>::SMEM, C, clusters, p, st);
 }
 
 }  // namespace lr

@@ -157,10 +157,25 @@ __device__ __forceinline__ uint64_t desc_k_sw64(uint32_t saddr) {
 // byte offset of element (row, 16-byte chunk c in [0,4)) inside a [rows x 64 B] K-major SWIZZLE_64B slab
 __device__ __forceinline__ uint32_t sw64_off(uint32_t row, uint32_t chunk) { return row * 64u + ((chunk ^ ((row >> 1) & 3u)) << 4); }
 
+// MN-major 16-bit operand with the 128-byte swizzle (layout_type 2): rows = K index, 64 MN elements (128 B) contiguous per
+// row, atoms of 8 K rows (1024 B) -> SBO = 1024 B between the two K atoms of one K = 16 instruction; LBO (stride between
+// MN atoms) is unused while the MN extent is <= 64.  Within an atom the 16-byte chunk index is XORed with (K row & 7).
+__device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t saddr) {
+  uint64_t d = (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// byte offset of (K row, 16-byte chunk c in [0,8)) inside a [K rows x 128 B] MN-major SWIZZLE_128B slab (1024-byte aligned)
+__device__ __forceinline__ uint32_t sw128_off(uint32_t krow, uint32_t chunk) { return krow * 128u + ((chunk ^ (krow & 7u)) << 4); }
+
 // Instruction descriptor (cute::UMMA::InstrDescriptor): c_format[4,6)=1 (f32), a_format[7,10), b_format[10,13)
 // (kind::f16: 0 = f16, 1 = bf16), a_major[15], b_major[16] (0 = K-major), n_dim[17,23) = N >> 3, m_dim[24,29) = M >> 4.
-__host__ __device__ constexpr uint32_t idesc_f16(int M, int N, int fmt /* 0 = f16, 1 = bf16 */) {
-  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N, int fmt /* 0 = f16, 1 = bf16 */, int b_mn_major = 0) {
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
 }
 
 }  // namespace tcx

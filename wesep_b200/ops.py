@@ -939,7 +939,7 @@ class LstmTmFn(torch.autograd.Function):
 
 
 def _rec_force():
-    """WESEP_LSTM_REC_SEQS = 32 / 64 / 128 forces the sequences-per-cluster grouping of the recurrence kernels (tests)."""
+    """WESEP_LSTM_REC_SEQS = 64 / 128 forces the sequences-per-cluster grouping of the recurrence kernels (tests)."""
     return int(os.environ.get("WESEP_LSTM_REC_SEQS", "0") or 0)
 
 
