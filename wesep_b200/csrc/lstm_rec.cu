@@ -35,8 +35,8 @@ using namespace tcx;
 
 constexpr int MAXC = 8;                // cluster size = Hd / 32
 constexpr int NW = 16;                 // cell warps: 512 threads = 32 hidden units x 16 sequence quads
-constexpr int THREADS = 32 * NW + 32;  // warps 0-15: TMEM drain / cell (4 per scheduler: the cell is latency-bound), warp 16: MMA issuer + TMEM owner
-constexpr int MMA_WARP = NW;
+constexpr int THREADS = 32 * NW + 64;  // warps 0-15: TMEM drain / cell, warp 16: MMA issuer + TMEM owner, warp 17: publisher
+constexpr int MMA_WARP = NW, PUB_WARP = NW + 1;   // (576 threads cost the same registers as 544: allocation is per 4 warps)
 constexpr float H_SCALE = 4096.f;      // h in (-1, 1) -> fp16 hi + lo of 4096 h
 constexpr float LOG2E = 1.4426950408889634f;
 
@@ -73,8 +73,7 @@ struct FwdParams {
 constexpr int PROF_T0 = 8, PROF_N = 16;
 #define LR_STAMP(slot)                                                                                            \
   do {                                                                                                            \
-    if (p.prof && blockIdx.x == 0 && g == 0 && t >= PROF_T0 && t < PROF_T0 + PROF_N)                              \
-      p.prof[(t - PROF_T0) * 16 + (slot)] = clock64();                                                            \
+    if (do_prof && g == 0 && (unsigned)(t - PROF_T0) < (unsigned)PROF_N) p.prof[(t - PROF_T0) * 16 + (slot)] = clock64(); \
   } while (0)
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -92,11 +91,14 @@ __device__ __forceinline__ float tanh_fast(float x) { return 1.f - 2.f * rcpf(1.
 // The four gate activations with ONE reciprocal: 1 / (1 + e_k) = (prod of the other three denominators) / (prod of all four).
 // Inputs are clamped to +-20 (sigma(-20) = 2e-9, tanh(10) = 1 - 4e-9: below fp32 resolution of the results) so that the
 // product of four denominators (<= (1 + e^20)^4 = 5.5e34) cannot overflow.  5 MUFU ops instead of 8.
-__device__ __forceinline__ void gates_fast(float ai, float af, float ag, float ao, float& i_, float& f_, float& g_, float& o_) {
-  const float di = 1.f + ex2f(fminf(fmaxf(-ai, -20.f), 20.f) * LOG2E);
-  const float df = 1.f + ex2f(fminf(fmaxf(-af, -20.f), 20.f) * LOG2E);
-  const float dO = 1.f + ex2f(fminf(fmaxf(-ao, -20.f), 20.f) * LOG2E);
-  const float dg = 1.f + ex2f(fminf(fmaxf(2.f * ag, -20.f), 20.f) * LOG2E);
+// The arguments arrive PRE-SCALED for ex2: xi = -log2(e) a_i (same for f, o), xg = 2 log2(e) a_g (the scale is folded into
+// the descale of the accumulator and one FFMA on the input projection); only the upper clamp is needed (ex2 -> 0 is fine).
+constexpr float EX2_CLAMP = 20.f * LOG2E;
+__device__ __forceinline__ void gates_fast(float xi, float xf, float xg, float xo, float& i_, float& f_, float& g_, float& o_) {
+  const float di = 1.f + ex2f(fminf(xi, EX2_CLAMP));
+  const float df = 1.f + ex2f(fminf(xf, EX2_CLAMP));
+  const float dO = 1.f + ex2f(fminf(xo, EX2_CLAMP));
+  const float dg = 1.f + ex2f(fminf(xg, EX2_CLAMP));
   const float pif = di * df, pog = dO * dg;
   const float r = rcpf(pif * pog);
   const float rp = r * pif, rq = r * pog;
@@ -111,8 +113,10 @@ __device__ __forceinline__ void named_sync_epi() { asm volatile("bar.sync 1, 512
 // the slab / signals the MMA thread
 // (one barrier id per group: consecutive publications of DIFFERENT groups are not separated by a full barrier, and an
 // early second arrival on the same id would corrupt its phase)
-__device__ __forceinline__ void named_arrive_pub(int g) { asm volatile("bar.arrive %0, 512;\n" ::"r"(2 + g) : "memory"); }
-__device__ __forceinline__ void named_sync_pub(int g) { asm volatile("bar.sync %0, 512;\n" ::"r"(2 + g) : "memory"); }
+// All 16 cell warps arrive and go on; the publisher warp (no cell work of its own, so no cell warp becomes the critical
+// path) waits for them and then publishes.
+__device__ __forceinline__ void named_arrive_pub(int g) { asm volatile("bar.arrive %0, 544;\n" ::"r"(2 + g) : "memory"); }
+__device__ __forceinline__ void named_sync_pub(int g) { asm volatile("bar.sync %0, 544;\n" ::"r"(2 + g) : "memory"); }
 static_assert(NW == 16, "named_sync_epi / column split assume 16 cell warps");
 
 __device__ __forceinline__ void tc_ld8_nowait(uint32_t taddr, uint32_t* r) {
@@ -166,6 +170,7 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_fwd_kernel(const FwdParam
   const int cid = blockIdx.x / C;
   const int dir = cid & 1, cgrp = cid >> 1;
   const int S = p.S;
+  const bool do_prof = p.prof != nullptr && blockIdx.x == 0 && (tid == 0 || warp == MMA_WARP);
   auto bar_hfull = [&](int g) { return base + K::OFF_BAR + 8u * g; };
   auto bar_hfree = [&](int g) { return base + K::OFF_BAR + 16u + 8u * g; };
   auto bar_acc = [&](int g) { return base + K::OFF_BAR + 32u + 8u * g; };
@@ -200,7 +205,7 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_fwd_kernel(const FwdParam
     if (mx > 0.f) frexpf(mx, &e);
     e = max(e, -100);
     const float s = ldexpf(1.f, 14 - e);
-    rs[r] = ldexpf(1.f, e - 14 - 12);                       // 1 / (s * H_SCALE)
+    rs[r] = ldexpf(1.f, e - 14 - 12) * (warp == 2 ? 2.f * LOG2E : -LOG2E);   // 1 / (s * H_SCALE) x the gate's ex2 scale
     const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
     for (int kc = 0; kc < C; ++kc) {                         // 32 k values -> 16 columns
@@ -230,7 +235,6 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_fwd_kernel(const FwdParam
   if (warp == MMA_WARP) {
     // ================================================= MMA issuer
     if (elect_one()) {
-      const uint16_t mask = (uint16_t)((1u << C) - 1u);
       for (int t = 1; t < S; ++t) {
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
@@ -249,13 +253,12 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_fwd_kernel(const FwdParam
             tc_mma_f16_ts(d, a_hi, b_hi, IDESC, 1u);
           }
           tc_commit(bar_acc(g));                  // accumulator ready for the cell warps
-          tc_commit_mc(bar_hfree(g), mask);       // and this CTA has finished reading its h buffer: tell the whole cluster
           LR_STAMP(9);
         }
       }
     }
     __syncwarp();
-  } else {
+  } else if (warp < NW) {
     // ================================================= TMEM drain + cell warps.  Cell phase: thread = (hidden unit u of the CTA,
     // quad of 4 consecutive sequences) so that every global / shared access is a 16-byte vector (the cell is bound by the
     // number of LSU instructions, not by bytes)
@@ -268,17 +271,26 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_fwd_kernel(const FwdParam
     for (int g = 0; g < NG; ++g)
 #pragma unroll
       for (int k = 0; k < 4; ++k) c[g][k] = 0.f;
-    float4 nxt[NG][4];                                        // pre-activations of each group's NEXT step (a whole item ahead)
+    // (544 threads cap the kernel at 96 registers: the pre-activations of an item are loaded at its start - the latency
+    // hides behind the accumulator wait, the TMEM drain and the barrier - after an L2 prefetch issued one item earlier)
+    float4 nxt[4];
     auto load_pre = [&](int t, int g) {
       const int s = dir ? S - 1 - t : t;
       const int q = (cgrp * NG + g) * NQ + 4 * qd;
       const float* Gs = p.G + (int64_t)s * p.bsG + row_g + q;
 #pragma unroll
       for (int gt = 0; gt < 4; ++gt)
-        nxt[g][gt] = q < p.Q ? __ldcs(reinterpret_cast<const float4*>(Gs + gt * gstride)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        nxt[gt] = q < p.Q ? __ldcs(reinterpret_cast<const float4*>(Gs + gt * gstride)) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
+    auto prefetch_pre = [&](int t, int g) {
+      const int s = dir ? S - 1 - t : t;
+      const int q = (cgrp * NG + g) * NQ + 4 * qd;
+      const float* Gs = p.G + (int64_t)s * p.bsG + row_g + q;
+      if ((qd & 7) == 0 && q < p.Q) {                         // one request per 128-byte line
 #pragma unroll
-    for (int g = 0; g < NG; ++g) load_pre(0, g);
+        for (int gt = 0; gt < 4; ++gt) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(Gs + gt * gstride));
+      }
+    };
     uint32_t item = 0;                                        // staging tile parity
     for (int t = 0; t < S; ++t) {
       const int s = dir ? S - 1 - t : t;
@@ -286,11 +298,15 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_fwd_kernel(const FwdParam
       for (int g = 0; g < NG; ++g, ++item) {
         float pre[4][4];
         uint8_t* stg = gbase + K::OFF_STG + (item & 1) * K::STG_BYTES;
-        if (tid == 0) LR_STAMP(0);
+        load_pre(t, g);
+        LR_STAMP(0);
         if (t > 0) {
           mbar_wait(bar_acc(g), (t - 1) & 1);
           tc_fence_after();
-          if (tid == 0) LR_STAMP(1);
+          LR_STAMP(1);
+          // my MMAs of (t, g) are done, i.e. this CTA has finished reading its copy of h_{t-1}: tell every CTA of the
+          // cluster (plain remote arrives: a multicast tcgen05.commit was measured to land > 1000 cycles later)
+          if (warp == 1 && lane < C) mbar_arrive_remote(mapa(bar_hfree(g), lane));
           {   // phase 1: lane = gate row; TMEM -> registers -> descale -> staging (so that the cell can read by sequence)
             constexpr int NCOL = NQ / 4;               // warps w, w + 4, w + 8, w + 12 share a lane quarter and split the columns
             const int r = (warp & 3) * 32 + lane, c0 = (warp >> 2) * NCOL;
@@ -310,21 +326,24 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_fwd_kernel(const FwdParam
             }
           }
           tc_fence_before();
-          if (tid == 0) LR_STAMP(2);
+          LR_STAMP(2);
           named_sync_epi();
-          if (tid == 0) LR_STAMP(3);
+          LR_STAMP(3);
 #pragma unroll
           for (int gt = 0; gt < 4; ++gt) {
             const int r = gt * 32 + u;
             const float4 v = *reinterpret_cast<const float4*>(stg + r * (NQ * 4) + ((qd ^ (r & 7)) << 4));
-            const float4 n4 = nxt[g][gt];
-            pre[gt][0] = n4.x + v.x; pre[gt][1] = n4.y + v.y; pre[gt][2] = n4.z + v.z; pre[gt][3] = n4.w + v.w;
+            const float4 n4 = nxt[gt];
+            const float kg = gt == 2 ? 2.f * LOG2E : -LOG2E;
+            pre[gt][0] = fmaf(n4.x, kg, v.x); pre[gt][1] = fmaf(n4.y, kg, v.y);
+            pre[gt][2] = fmaf(n4.z, kg, v.z); pre[gt][3] = fmaf(n4.w, kg, v.w);
           }
         } else {
 #pragma unroll
           for (int gt = 0; gt < 4; ++gt) {
-            const float4 n4 = nxt[g][gt];
-            pre[gt][0] = n4.x; pre[gt][1] = n4.y; pre[gt][2] = n4.z; pre[gt][3] = n4.w;
+            const float4 n4 = nxt[gt];
+            const float kg = gt == 2 ? 2.f * LOG2E : -LOG2E;
+            pre[gt][0] = n4.x * kg; pre[gt][1] = n4.y * kg; pre[gt][2] = n4.z * kg; pre[gt][3] = n4.w * kg;
           }
         }
         // ---- cell (nn.LSTM gate order i | f | g | o), global writes, h_t -> fp16 hi / lo into my slab of the operand buffer
@@ -336,11 +355,14 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_fwd_kernel(const FwdParam
           float i_, f_, g_, o_;
           gates_fast(pre[0][k], pre[1][k], pre[2][k], pre[3][k], i_, f_, g_, o_);
           const float cn = fmaf(f_, c[g][k], i_ * g_);
-          const float hn = o_ * tanh_fast(cn);
-          const bool ok = k < nv;                                // pad columns carry zeros
-          c[g][k] = ok ? cn : 0.f;
-          hq[k] = ok ? hn : 0.f;
-          pre[0][k] = ok ? i_ : 0.f; pre[1][k] = ok ? f_ : 0.f; pre[2][k] = ok ? g_ : 0.f; pre[3][k] = ok ? o_ : 0.f;
+          c[g][k] = cn;
+          hq[k] = o_ * tanh_fast(cn);
+          pre[0][k] = i_; pre[1][k] = f_; pre[2][k] = g_; pre[3][k] = o_;
+        }
+        if (nv < 4) {                                            // pad columns carry zeros (cold path: last quad of the batch)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (k >= nv) { c[g][k] = 0.f; hq[k] = 0.f; pre[0][k] = 0.f; pre[1][k] = 0.f; pre[2][k] = 0.f; pre[3][k] = 0.f; }
         }
         if (q < p.ld) {
           float* Gs = p.G + (int64_t)s * p.bsG + row_g + q;
@@ -374,29 +396,34 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_fwd_kernel(const FwdParam
             *reinterpret_cast<uint2*>(outb + SLAB + off) = make_uint2(lo[0], lo[1]);
           }
         }
-        if (tid == 0) LR_STAMP(5);
-        // prefetch this group's next pre-activations: a whole item (the other group's) of latency to hide behind
-        if (t + 1 < S) load_pre(t + 1, g);
+        LR_STAMP(5);
         if (t + 1 < S) {
-          fence_proxy_async();
-          if (warp != 0) {
-            named_arrive_pub(g);
-          } else {
-            named_sync_pub(g);            // every cell thread has written its part of the slab
-            if (tid == 0) LR_STAMP(6);
-            // every CTA of the cluster has finished the MMAs of (t, g) => all copies of h_{t-1} have been consumed and the
-            // remote operand buffers of this group may be overwritten with h_t
-            if (t > 0) mbar_wait(bar_hfree(g), (t - 1) & 1);
-            const uint32_t src = base + K::OFF_OUT + (g * 2 + (t & 1)) * (2 * SLAB);
-            const uint32_t dst = base + K::OFF_H + g * HBUF + rank * (2 * SLAB);
-            if (lane == 0) {
-              if (C > 1) mbar_arrive_expect_tx(bar_hfull(g), (uint32_t)(C - 1) * 2 * SLAB);
-              else mbar_arrive(bar_hfull(g));
-            }
-            if (lane < C && lane != (int)rank) bulk_copy_s2c(mapa(dst, lane), src, 2 * SLAB, mapa(bar_hfull(g), lane));
-            if (tid == 0) LR_STAMP(7);
-          }
+          fence_proxy_async();             // (a membar: keep the prefetch below it, or it waits for it)
+          named_arrive_pub(g);
+          LR_STAMP(6);
+          prefetch_pre(t + 1, g);          // this group's next pre-activations -> L2
         }
+      }
+    }
+  }
+  if (warp == PUB_WARP) {
+    // ================================================= publisher: h_t of (t, g) is complete in shared memory -> all-gather it
+    for (int t = 0; t + 1 < S; ++t) {
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        named_sync_pub(g);              // every cell thread has written its part of the slab (and fenced it for the async proxy)
+        // every CTA of the cluster has finished the MMAs of (t, g) => all copies of h_{t-1} have been consumed and the
+        // remote operand buffers of this group may be overwritten with h_t
+        if (t > 0) mbar_wait(bar_hfree(g), (t - 1) & 1);
+        const uint32_t src = base + K::OFF_OUT + (g * 2 + (t & 1)) * (2 * SLAB);
+        const uint32_t dst = base + K::OFF_H + g * HBUF + rank * (2 * SLAB);
+        if (lane == 0) {
+          if (C > 1) mbar_arrive_expect_tx(bar_hfull(g), (uint32_t)(C - 1) * 2 * SLAB);
+          else mbar_arrive(bar_hfull(g));
+        }
+        if (lane < C && lane != (int)rank) bulk_copy_s2c(mapa(dst, lane), src, 2 * SLAB, mapa(bar_hfull(g), lane));
+        if (lane == 0 && p.prof && blockIdx.x == 0 && g == 0 && (unsigned)(t - PROF_T0) < (unsigned)PROF_N)
+          p.prof[(t - PROF_T0) * 16 + 7] = clock64();
       }
     }
   }
@@ -461,6 +488,7 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_bwd_kernel(const BwdParam
   const int cid = blockIdx.x / C;
   const int dir = cid & 1, cgrp = cid >> 1;
   const int S = p.S;
+  const bool do_prof = p.prof != nullptr && blockIdx.x == 0 && (tid == 0 || warp == MMA_WARP);
   auto bar_bfull = [&](int g) { return base + K::OFF_BAR + 8u * g; };
   auto bar_acc = [&](int g) { return base + K::OFF_BAR + 16u + 8u * g; };
   auto bar_rfull = [&](int g) { return base + K::OFF_BAR + 32u + 8u * g; };
@@ -538,6 +566,17 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_bwd_kernel(const BwdParam
       }
     }
     __syncwarp();
+  } else if (warp == PUB_WARP) {
+    // ================================================= publisher: da of (t, g) is complete -> start its product; the receive
+    // slabs of round t - 1 have been read by all my cell threads -> their senders may reuse them
+    for (int t = 0; t + 1 < S; ++t) {
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        named_sync_pub(g);
+        if (lane == 0) mbar_arrive(bar_bfull(g));
+        if (t > 0 && lane < C) mbar_arrive_remote(mapa(bar_rfree(g), lane));
+      }
+    }
   } else {
     // cell threads: (hidden unit u of the CTA, quad of 4 consecutive sequences), 16-byte accesses everywhere
     const int u = tid >> 4, qd = tid & 15;
@@ -562,7 +601,7 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_bwd_kernel(const BwdParam
       // ------------------------------------------------------------------ phase B of every group
 #pragma unroll
       for (int g = 0; g < NG; ++g) {
-        if (tid == 0) LR_STAMP(0);
+        LR_STAMP(0);
         const int q = (cgrp * NG + g) * NQ + 4 * qd;
         const int nv = p.Q - q;
         const bool any = q < p.Q;
@@ -577,7 +616,7 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_bwd_kernel(const BwdParam
         if (t > 0) {
           // ---- recurrent gradient: sum of the C partial products of round t - 1 for my unit
           mbar_wait_cluster(bar_rfull(g), (t - 1) & 1);
-          if (tid == 0) LR_STAMP(1);
+          LR_STAMP(1);
           const uint8_t* R = gbase + K::OFF_R + g * K::RBUF + qd * 512 + ((u ^ (qd & 7)) << 4);
 #pragma unroll
           for (int src = 0; src < C; ++src) {
@@ -585,7 +624,7 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_bwd_kernel(const BwdParam
             dh[0] += v.x; dh[1] += v.y; dh[2] += v.z; dh[3] += v.w;
           }
         }
-        if (tid == 0) LR_STAMP(2);
+        LR_STAMP(2);
         // ---- cell backward, da -> global (over the activations) and -> bf16 hi / lo B operand (MN-major: K row = gate * 32 + u)
         const float ai[4] = {a4[0].x, a4[0].y, a4[0].z, a4[0].w}, af[4] = {a4[1].x, a4[1].y, a4[1].z, a4[1].w};
         const float ag[4] = {a4[2].x, a4[2].y, a4[2].z, a4[2].w}, ao[4] = {a4[3].x, a4[3].y, a4[3].z, a4[3].w};
@@ -621,19 +660,12 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_bwd_kernel(const BwdParam
             *reinterpret_cast<uint2*>(bbuf + gt * 2 * SLAB + SLAB + off) = make_uint2(l0, l1);
           }
         }
-        if (tid == 0) LR_STAMP(3);
+        LR_STAMP(3);
         if (t + 1 < S) {
           fence_proxy_async();
-          if (warp != 0) {
-            named_arrive_pub(g);
-          } else {
-            named_sync_pub(g);
-            if (lane == 0) mbar_arrive(bar_bfull(g));
-            // round t - 1 has been read by all my threads: its senders may reuse my receive slabs
-            if (t > 0 && lane < C) mbar_arrive_remote(mapa(bar_rfree(g), lane));
-          }
+          named_arrive_pub(g);
         }
-        if (tid == 0) LR_STAMP(4);
+        LR_STAMP(4);
       }
       // ------------------------------------------------------------------ phase A of every group
       if (t + 1 < S) {
@@ -641,9 +673,9 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_bwd_kernel(const BwdParam
         for (int g = 0; g < NG; ++g) {
           mbar_wait(bar_acc(g), t & 1);
           tc_fence_after();
-          if (tid == 0) LR_STAMP(5);
+          LR_STAMP(5);
           if (t > 0) mbar_wait_cluster(bar_rfree(g), (t - 1) & 1);
-          if (tid == 0) LR_STAMP(6);
+          LR_STAMP(6);
           const int mb = (warp >> 2) & 1, ch = warp >> 3;      // M block, column half
           const int m0 = mb * 128 + (warp & 3) * 32;            // hidden units of this warp's TMEM lanes (warp-uniform)
           if (mb < MB && m0 < Hd) {
@@ -668,7 +700,7 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_bwd_kernel(const BwdParam
             }
           }
           tc_fence_before();
-          if (tid == 0) LR_STAMP(7);
+          LR_STAMP(7);
         }
       }
     }
