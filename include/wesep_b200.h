@@ -394,6 +394,20 @@ typedef struct {
 int wesep_b200_lstm_cell_fwd(const WesepLstmCellArgs* a, void* stream);
 int wesep_b200_lstm_cell_bwd(const WesepLstmCellArgs* a, void* stream);
 
+/* nn.GroupNorm(1, C, eps) over (C, T) of every row of [n][C][ld] (the norm in front of every ResRNN, band split and mask
+ * head: wesep/models/bsrnn.py:23,39,204,274), one CTA per row.  fwd writes stats [n][2] = (sum, sum of squares) for the
+ * backward.  bwd: dx, and dgamma / dbeta [C] ACCUMULATED (+=) into the caller's (zero-initialised or running) buffers.
+ * x / y / gy / dx may be channel slices of larger tensors (batch strides bs*). */
+typedef struct {
+  int n, C, T;
+  int64_t ldx, bsx, ldy, bsy, ldg, bsg, lddx, bsdx;   /* row and batch strides (floats), multiples of 4 */
+  const float* x; const float* gamma; const float* beta; float eps;
+  float* y; double* stats;
+  const float* gy; float* dx; float* dgamma; float* dbeta;
+} WesepGroupNorm1Args;
+int wesep_b200_groupnorm1_fwd(const WesepGroupNorm1Args* a, void* stream);
+int wesep_b200_groupnorm1_bwd(const WesepGroupNorm1Args* a, void* stream);
+
 /* The LSTM recurrence of a bidirectional layer as ONE persistent cluster kernel per pass (time-major tensors, see above):
  * replaces the recurrent half of nn.LSTM inside ResRNN (wesep/models/bsrnn.py:25-31,41-44); the input projection
  * W_ih x + b_ih + b_hh of both directions is a GEMM done beforehand into G.  A cluster of Hd / 32 CTAs keeps W_hh (split

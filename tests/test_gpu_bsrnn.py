@@ -201,3 +201,29 @@ def test_lstm_second_backward_raises():
     h.sum().backward(retain_graph=True)
     with pytest.raises(RuntimeError):
         h.sum().backward()
+
+
+@pytest.mark.parametrize("n,C,T,sliced", [(5, 6, 501, False), (70, 16, 32, False), (3, 128, 501, True), (9, 32, 37, True)])
+def test_group_norm1(n, C, T, sliced):
+    """GroupNorm(1, C) one-CTA-per-row kernels vs torch.nn.functional.group_norm in fp64 (forward, dx, dgamma, dbeta);
+    `sliced`: the input is a channel slice of a larger act tensor (batch stride > C * ld)."""
+    import torch.nn.functional as F
+    from wesep_b200 import ops
+    Cbig = C + 8 if sliced else C
+    xb = ops.new_act(n, Cbig, T, DEV)
+    xb.copy_(rnd(n, Cbig, T, seed=1) * 3.0 + 0.5)
+    x0 = xb[:, 4:4 + C] if sliced else xb
+    w0, b0 = 1 + 0.2 * rnd(C, seed=2), 0.3 * rnd(C, seed=3)
+    x = x0.detach().requires_grad_(True)
+    w, b = w0.clone().requires_grad_(True), b0.clone().requires_grad_(True)
+    y = ops.group_norm1(x, w, b)
+    x64 = x0.detach().double().contiguous().requires_grad_(True)
+    w64, b64 = w0.double().requires_grad_(True), b0.double().requires_grad_(True)
+    ref = F.group_norm(x64, 1, w64, b64, ops.GN_EPS)
+    check("y", y, ref, 2e-6)
+    g = rnd(n, C, T, seed=4)
+    y.backward(g)
+    ref.backward(g.double())
+    check("dx", x.grad, x64.grad, 2e-5)
+    check("dgamma", w.grad, w64.grad, 2e-5)
+    check("dbeta", b.grad, b64.grad, 2e-5)

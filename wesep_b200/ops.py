@@ -934,7 +934,10 @@ class LstmTmFn(torch.autograd.Function):
         if S > 1:
             conv1x1_dw_raw(G[1:, :4 * Hd], H[:-1, :Hd], dWhh[0])
             conv1x1_dw_raw(G[:-1, 4 * Hd:], H[1:, Hd:], dWhh[1])
-        dxn = conv1x1_raw(G, Wih, True, C)
+        # W_ih^T . dG: 8 Hd = 2048 input channels exceed what one tcgen05 launch covers (1024), so one launch per direction,
+        # the second accumulating onto the first
+        dxn = conv1x1_raw(G[:, :4 * Hd], Wih[:4 * Hd], True, C)
+        conv1x1_raw(G[:, 4 * Hd:], Wih[4 * Hd:], True, C, epi=2, R=dxn, Y=dxn)
         return (dxn, dWih[:4 * Hd], dWhh[0], db[:4 * Hd], db[:4 * Hd], dWih[4 * Hd:], dWhh[1], db[4 * Hd:], db[4 * Hd:])
 
 
@@ -964,9 +967,42 @@ def _one(device):
 GN_EPS = float(torch.finfo(torch.float32).eps)
 
 
+class GroupNorm1Fn(torch.autograd.Function):
+    """nn.GroupNorm(1, C, eps) of an act tensor / channel slice [n, C, T] (per row over (C, T)), one CTA per row
+    (`wesep_b200_groupnorm1_fwd / _bwd`)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        if not is_act_slice(x):
+            x = as_act(x)
+        n, C, T = x.shape
+        y = new_act(n, C, T, x.device)
+        stats = torch.empty((n, 2), dtype=torch.float64, device=x.device)
+        w, b = _vec(weight), _vec(bias)
+        _lib.call("wesep_b200_groupnorm1_fwd",
+                  _args("WesepGroupNorm1Args", n=n, C=C, T=T, ldx=x.stride(1), bsx=x.stride(0), ldy=y.stride(1), bsy=y.stride(0),
+                        x=x, gamma=w, beta=b, eps=float(eps), y=y, stats=stats), _stream())
+        ctx.eps = float(eps)
+        ctx.save_for_backward(x, w, b, stats)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w, b, stats = ctx.saved_tensors
+        n, C, T = x.shape
+        gy = gy if is_act_slice(gy) else as_act(gy)
+        dx = new_act(n, C, T, x.device)
+        acc = torch.zeros(2 * C, dtype=torch.float32, device=x.device)
+        _lib.call("wesep_b200_groupnorm1_bwd",
+                  _args("WesepGroupNorm1Args", n=n, C=C, T=T, ldx=x.stride(1), bsx=x.stride(0), ldg=gy.stride(1), bsg=gy.stride(0),
+                        lddx=dx.stride(1), bsdx=dx.stride(0), x=x, gamma=w, beta=b, eps=ctx.eps, stats=stats, gy=gy, dx=dx,
+                        dgamma=acc[:C], dbeta=acc[C:]), _stream())
+        return dx, acc[:C], acc[C:], None
+
+
 def group_norm1(x, weight, bias, eps=GN_EPS):
-    """nn.GroupNorm(1, C, eps) of an act tensor [n, C, T] (per row over (C, T)): the gLN kernels with a unit PReLU slope."""
-    return FusePreluGlnFn.apply(x, None, None, _one(x.device), weight, bias, eps)
+    """nn.GroupNorm(1, C, eps) of an act tensor [n, C, T] (per row over (C, T))."""
+    return GroupNorm1Fn.apply(x, weight, bias, eps)
 
 
 def res_rnn(x, norm_w, norm_b, lstm, proj_w, proj_b):
