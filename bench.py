@@ -1,13 +1,17 @@
 #!/usr/bin/env python
-"""bench.py — Spex+ train-step throughput (utterances/sec) on synthetic 4 s @ 16 kHz two-speaker
-mixtures, batch = 32 model rows per GPU (BASELINE.json configs[1]; configs[3] for N > 1).
+"""bench.py — train-step throughput (utterances/sec) on synthetic 4 s @ 16 kHz two-speaker mixtures.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--rows 32]
+Headline (BASELINE.json `metric`, configs[1]; configs[3] for N > 1): Spex+, 32 model rows per GPU.
+Second block `pbsrnn` (the other model the metric's target names; configs[2]): pBSRNN, bsrnn.yaml network, 16 rows per GPU.
 
-A "step" = forward + 0.8/0.1/0.1 SI-SDR + 0.5 CE loss + backward + gradient all-reduce (N > 1) +
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--rows 32] [--bsrnn-rows 16]
+
+A "step" = forward + loss (Spex+: 0.8/0.1/0.1 SI-SDR + 0.5 CE; pBSRNN: SI-SDR) + backward + gradient all-reduce (N > 1) +
 per-tensor clip + Adam, the loop body of the reference Executor.train (wesep/utils/executor.py:70-134).
 Prints ONE JSON line on rank 0.  `value`: inputs already resident in HBM; `e2e`: same step through
 the public API from pinned host buffers (H2D every step, D2H of the loss every step).
+`roofline` describes the kernel with the LARGEST share of the timed step (shares from one CUPTI pass of a step inside this
+run), `roofline.step` the whole step against the HBM roofline SURVEY.md 8d says binds it.
 """
 import argparse
 import json
@@ -28,8 +32,11 @@ SPEX_ARGS = dict(B=256, H=512, L=20, N=256, P=3, R=4, X=8, spk_emb_dim=256, acti
                  encoder_type="Multi", decoder_type="Multi", joint_training=True, multi_task=True, spksInTrain=251)
 T_SAMPLES = 64000
 METRIC = "utterances/sec Spex+ train step (4s@16kHz)"
-# dram__bytes_read.sum + dram__bytes_write.sum of the K2 GEMM at n=32 (ncu --set full, profiles/r01_ncu_full_tcn_block_n32.md)
-K2_DRAM_BYTES_PER_LAUNCH = 579.5e6
+BSRNN_ARGS = dict(spk_emb_dim=256, sr=16000, win=512, stride=128, feature_dim=128, num_repeat=6, use_spk_transform=False,
+                  spk_fuse_type="multiply", multi_fuse=False, joint_training=False)   # bsrnn.yaml:48-55 (+ embeddings in)
+SPEX_BYTES_PER_ROW = 6.4e9      # algorithmic HBM bytes per row per train step (32 x 190 MB + 0.35 GB)
+SPEX_FLOPS_PER_ROW = 396e9      # algorithmic flops per row per train step (132 GFLOP forward x 3)
+BSRNN_FLOPS_PER_ROW = 1.02e12   # (340 GFLOP forward x 3)
 
 
 def peaks():
@@ -119,14 +126,29 @@ def cpu_train_rows_per_s(rows, steps, warmup, threads):
     return rows / med, med, float(loss)
 
 
+def cpu_model_name():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def run_reference(args, rank):
+    """Reference arm: the reference's algorithm (oracle port of the Spex+ train step; the reference itself is a Python package
+    that cannot be imported on the GPU box) on the host cores.  Every number printed is what actually ran."""
     if rank != 0:
         return
     threads = cpu_threads()
-    rows = args.ref_rows
-    val, med, loss = cpu_train_rows_per_s(rows, min(args.steps, 5), min(args.warmup, 1), threads)
-    sample = f"{rows} rows x {T_SAMPLES} samples per step, {args.steps} timed steps (median), oracle port on host CPU"
-    line = dict(metric=METRIC, value=val, unit="utterances/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+    rows = max(2, args.ref_rows)                    # >= 2 rows so the BatchNorm of the speaker encoder sees a batch
+    steps, warm = max(1, min(args.steps, 3)), max(0, min(args.warmup, 1))
+    val, med, loss = cpu_train_rows_per_s(rows, steps, warm, threads)
+    sample = (f"{rows} rows x {T_SAMPLES} samples per step; ran {warm} warm-up + {steps} timed steps (median {med:.2f} s); "
+              f"oracle port (plain torch fp32) on {threads} threads of {os.cpu_count()} host cores ({cpu_model_name()})")
+    line = dict(metric=METRIC, value=val, unit="utterances/s", n_gpus=args.gpus, steps=steps, warmup=warm,
+                steps_requested=args.steps, warmup_requested=args.warmup,
                 ms_per_step=med * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                 data="synthetic", impl="reference",
                 config=dict(workload="Spex+ train step, 4s@16kHz, CPU sample of %d rows" % rows, rows_per_step=rows),
@@ -137,53 +159,215 @@ def run_reference(args, rank):
 
 
 # ----------------------------------------------------------------------------- our arm
-def kernel_rooflines(n, dev, pk):
-    """Time the TCN-block kernels alone at the workload shape (CUDA events on the launching stream;
-    operands >> L2 so every launch streams from HBM).  Algorithmic bytes: DESIGN.md §kernels."""
-    from wesep_b200 import ops, synth
-    from wesep_b200.modules.tasnet.convs import Conv1DBlock
-    B, H, K = 256, 512, 6399
-    blk = Conv1DBlock(B, H, 3, 8, "gLN", False, False)
-    synth.fill_state_dict_(blk.state_dict(), seed=1)
-    blk = blk.to(dev)
-    x = ops.new_act(n, B, K, dev)
-    x.normal_()
-    x.requires_grad_(True)
-    gy = ops.new_act(n, B, K, dev)
-    gy.normal_()
-
-    def timed(fn, reps):
-        fn()
+def kernel_shares(step_fn):
+    """One CUPTI pass (torch.profiler) over one step: {kernel name: (count, total us)} and the total kernel time."""
+    import collections
+    from torch.profiler import ProfilerActivity, profile
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        step_fn()
         torch.cuda.synchronize()
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        for _ in range(reps):
-            fn()
-        e.record()
-        torch.cuda.synchronize()
-        return s.elapsed_time(e) / reps * 1e-3
+    for ev in prof.events():
+        if ev.device_type.name != "CUDA":
+            continue
+        name = ev.name
+        if name.startswith("Memcpy") or name.startswith("Memset"):
+            name = name.split(" ")[0]
+        a = agg[name]
+        a[0] += 1
+        a[1] += ev.time_range.end - ev.time_range.start
+    tot = sum(v[1] for v in agg.values())
+    return agg, tot
 
+
+# Per-launch algorithmic work of the Spex+ TCN-block kernels at n rows (B=256, H=512, K=6399; DESIGN.md 5) keyed by a
+# substring of the kernel name: (bytes per row, flops per row, bound).  GEMMs execute 3x the algorithmic flops (3xTF32).
+SPEX_KERNELS = {
+    "gemm_dw_tc2_kernel<0, false>": (19.7e6, 1.677e9, "tensor"),      # dW1 += du . x^T
+    "gemm_dw_tc2_kernel<1, true>": (19.7e6, 1.677e9, "tensor"),       # Gn = sum_t g . prelu(d)^T
+    "gemm_wx_tc2_kernel<0, 10, 4>": (32.8e6, 1.677e9, "tensor"),      # B2
+    "gemm_wx_tc2_kernel<2, 2, 4>": (26.2e6, 1.677e9, "tensor"),       # K4
+    "gemm_wx_tc2_kernel<0, 2, 4>": (26.2e6, 1.677e9, "tensor"),       # B4
+    "gemm_wx_tc2_kernel<0, 0, 6>": (19.7e6, 1.677e9, "tensor"),       # K2
+    "tcn_dw_fwd": (26.2e6, 0.04e9, "hbm"),                            # K3
+    "tcn_dw_bwd": (39.3e6, 0.1e9, "hbm"),                             # B3
+}
+
+
+def pick_roofline(agg, tot, table, rows, pk, passes, note):
+    """The table kernel with the largest share of the step; achieved from its AVERAGE duration inside the step."""
+    best = None
+    for name, (cnt, us) in agg.items():
+        for key, (byts, flops, bound) in table.items():
+            if key in name and (best is None or us > best[2]):
+                best = (name, key, us, cnt, byts, flops, bound)
+    if best is None:
+        return None
+    name, key, us, cnt, byts, flops, bound = best
+    sec = us / cnt * 1e-6
+    if bound == "tensor":
+        ach = passes * flops * rows / sec / 1e12
+        peak, unit = pk["tf_sus"], "TFLOP/s"
+    else:
+        ach = byts * rows / sec / 1e9
+        peak, unit = pk["hbm"], "GB/s"
+    return dict(kernel=name[:90], share_of_step_kernel_time=us / tot, launches_per_step=cnt, avg_us=us / cnt, bound=bound,
+                achieved=ach, peak=peak, unit=unit, frac=ach / peak, traffic=None,
+                algorithmic_gbs=byts * rows / sec / 1e9, algorithmic_tflops=flops * rows / sec / 1e12, note=note)
+
+
+def gpu_eager_baseline(n, dev):
+    """The same-box incumbent: the reference's algorithm (oracle port = the reference's module graph) run by
+    PyTorch eager on this B200 (cuDNN / cuBLAS, cudnn.benchmark as wesep/utils/utils.py:112), fp32 with TF32 off and on."""
+    from oracle import losses as olosses
+    from oracle import optim as ooptim
+    from oracle import spexplus as ospex
+    from wesep_b200 import synth
     out = {}
-    # K2-shaped GEMM (256 -> 512, bias, gLN statistics in the epilogue)
-    W = blk.conv1x1.weight.detach().reshape(H, B)
-    stats = torch.zeros((n, 2), dtype=torch.float64, device=dev)
-    u = ops.new_act(n, H, K, dev)
-    xd = x.detach()
-    t = timed(lambda: ops.conv1x1_raw(xd, W, False, H, bias=blk.conv1x1.bias.detach(), Y=u, out_stats=stats,
-                                      out_alpha=blk.PReLU_1.weight.detach()), 10)
-    flops = 2.0 * H * B * K * n
-    bytes_ = 4.0 * (B + H) * K * n
-    out["gemm_wx_k2"] = dict(seconds=t, alg_tflops=flops / t / 1e12, exec_tflops=3 * flops / t / 1e12,
-                             alg_gbs=bytes_ / t / 1e9)
-    # whole block forward / backward
-    tf = timed(lambda: blk(xd), 5)
-    y = blk(x)
-    tb = timed(lambda: torch.autograd.grad(y, [x] + list(blk.parameters()), gy, retain_graph=True), 5)
-    bf = (2 * B + 4 * H) * K * 4.0 * n
-    bb = (3 * B + 8 * H) * K * 4.0 * n
-    out["tcn_block_fwd"] = dict(seconds=tf, alg_gbs=bf / tf / 1e9, frac_hbm=bf / tf / 1e9 / pk["hbm"])
-    out["tcn_block_bwd"] = dict(seconds=tb, alg_gbs=bb / tb / 1e9, frac_hbm=bb / tb / 1e9 / pk["hbm"])
+    torch.backends.cudnn.benchmark = True
+    for tf32 in (False, True):
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.allow_tf32 = tf32
+        rows = n
+        while rows >= 2:
+            try:
+                cfg = dict(ospex.DEFAULT_CFG)
+                sd = ospex.make_state_dict(cfg)
+                synth.fill_state_dict_(sd, seed=0)
+                sd = {k: v.to(dev) for k, v in sd.items()}
+                names = [k for k, v in sd.items() if v.is_floating_point() and "running_" not in k]
+                P = [sd[k].requires_grad_(True) for k in names]
+                m = [torch.zeros_like(p) for p in P]
+                v = [torch.zeros_like(p) for p in P]
+                b = {k: x.to(dev) for k, x in synth.make_batch(rows, T=T_SAMPLES, Te=T_SAMPLES, seed=1234).items()}
+
+                def step(it):
+                    bufs = {}
+                    o = ospex.convtasnet_forward(sd, cfg, b["wav_mix"], b["spk_embeds"], training=True, buffers_out=bufs)
+                    loss, _ = olosses.train_loss(o, b["wav_targets"], b["spk_label"])
+                    grads = list(torch.autograd.grad(loss, P))
+                    ooptim.clip_gradients(grads, 5.0)
+                    with torch.no_grad():
+                        ooptim.adam_step(P, grads, m, v, it + 1, 1e-3)
+                        sd.update(bufs)
+                for it in range(2):
+                    step(it)
+                torch.cuda.synchronize()
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                for it in range(3):
+                    step(2 + it)
+                e.record()
+                torch.cuda.synchronize()
+                ms = s.elapsed_time(e) / 3
+                out["allow_tf32_%s" % str(tf32).lower()] = dict(value=rows / ms * 1e3, unit="utterances/s", rows=rows, ms_per_step=ms)
+                break
+            except torch.OutOfMemoryError:
+                rows //= 2
+            finally:
+                P = m = v = sd = b = None
+                torch.cuda.empty_cache()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = True
+    out["what"] = ("oracle port (the reference's op graph in plain torch) run eagerly on this GPU: 2 warm-up + 3 timed steps, "
+                   "cudnn.benchmark=True; the reference's own GPU path uses PyTorch defaults (cudnn TF32 on, matmul TF32 off)")
     return out
+
+
+def time_steps(one, warmup, steps, barrier, world, dev):
+    from wesep_b200 import _lib
+    import torch.distributed as dist
+    for _ in range(warmup):
+        one()
+    barrier()
+    l0 = _lib.launch_count()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    last = None
+    for _ in range(steps):
+        last = one()
+    e.record()
+    barrier()
+    ms = s.elapsed_time(e)
+    launches = _lib.launch_count() - l0
+    if world > 1:
+        tt = torch.tensor([ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt)
+    return ms, launches, float(last)
+
+
+def run_pbsrnn(args, rank, world, dev, pk, barrier):
+    """BASELINE config 3: pBSRNN train step, 4 s @ 16 kHz, 16 rows per GPU, bsrnn.yaml network (speaker embeddings as input)."""
+    import numpy as np
+    from wesep_b200 import _lib, ops, synth
+    from wesep_b200.distributed import GradAllReducer, broadcast_params
+    from wesep_b200.models import get_model
+    from wesep_b200.utils.optim import FusedClipAdam
+    n = args.bsrnn_rows
+    torch.manual_seed(42 + rank)
+    model = get_model("BSRNN")(**BSRNN_ARGS).to(dev).train()
+    opt = FusedClipAdam(model.parameters(), lr=1e-3, weight_decay=1e-4, clip=5.0)
+    broadcast_params(opt.arena.flat_p)
+    reducer = GradAllReducer(opt.arena.flat_g, n_buckets=1) if world > 1 else None
+    host = synth.make_batch(n, T=T_SAMPLES, Te=8, seed=4321 + rank, pin=True)
+    emb_h = torch.from_numpy(np.random.default_rng(5 + rank).standard_normal((n, 256)).astype(np.float32)).pin_memory()
+    host = dict(wav_mix=host["wav_mix"], wav_targets=host["wav_targets"], emb=emb_h)
+    resident = {k: v.to(dev) for k, v in host.items()}
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+
+    def step(batch, read_loss):
+        mix = batch["wav_mix"].to(dev, non_blocking=True)
+        tgt = batch["wav_targets"].to(dev, non_blocking=True)
+        emb = batch["emb"].to(dev, non_blocking=True)
+        opt.zero_grad()
+        est, _ = model(mix, emb)
+        losses, _ = ops.sisdr_losses([est], tgt)
+        losses[0].backward()
+        if reducer is not None:
+            reducer.all_reduce()
+            opt.grad_scale = reducer.grad_scale
+        opt.step()
+        return losses[0].item() if read_loss else losses[0]
+
+    ms_res, launches, loss_res = time_steps(lambda: step(resident, False), args.warmup, args.steps, barrier, world, dev)
+    ms_e2e, _, loss_e2e = time_steps(lambda: step(host, True), 1, args.steps, barrier, world, dev)
+    if rank != 0:
+        return None
+    agg, tot = kernel_shares(lambda: step(resident, False))
+    rec = {k: v for k, v in agg.items() if "lstm_rec" in k}
+    rec_us = sum(v[1] for v in rec.values())
+    rec_n = sum(v[0] for v in rec.values())
+    # one launch of either recurrence kernel: 2 directions x (4 Hd x Hd) x (sequences x steps) MACs; Q S is the same for
+    # band_rnn (32 n x 501) and band_comm (501 n x 32)
+    Hd, QS = 256, 32 * n * 501
+    alg = 2.0 * 2 * 4 * Hd * Hd * QS
+    sec = rec_us / max(rec_n, 1) * 1e-6
+    top = sorted(agg.items(), key=lambda kv: -kv[1][1])[:6]
+    step_tf = 3 * BSRNN_FLOPS_PER_ROW * n * args.steps / (ms_res * 1e-3) / 1e12
+    roof = dict(kernel="lstm_rec_fwd_kernel / lstm_rec_bwd_kernel (persistent cluster BLSTM recurrence, tcgen05 kind::f16)",
+                share_of_step_kernel_time=rec_us / tot, launches_per_step=rec_n, avg_us=rec_us / max(rec_n, 1), bound="tensor",
+                achieved=3 * alg / sec / 1e12, peak=pk["tf_sus"], unit="TFLOP/s", frac=3 * alg / sec / 1e12 / pk["tf_sus"],
+                traffic=None, algorithmic_tflops=alg / sec / 1e12,
+                serial_floor_us_per_step=1.65,
+                note="executed = 3 x algorithmic flops (fp16 / bf16 hi+lo split products, fp32-grade); avg over the 24 launches of a "
+                     "step (6 layers x (band_rnn 501 steps + band_comm 32 steps) x (fwd + bwd)); peak = measured sustained bf16 (%s); "
+                     "serial floor per time step of one cluster = one group's step product on the tensor pipe (48 MMAs x 32 clk) + "
+                     "one DSMEM all-gather hop + the cell's dependent MUFU chain ~ 3100 clk (DESIGN.md)" % pk["src"],
+                step=dict(bound="tensor", achieved=step_tf, peak=pk["tf_sus"], unit="TFLOP/s", frac=step_tf / pk["tf_sus"],
+                          note="whole step, per GPU: 3 x 1.02 TFLOP per row (SURVEY 8d, fp32-grade split products) x rows / step time "
+                               "/ sustained bf16 peak"))
+    return dict(metric="utterances/sec pBSRNN train step (4s@16kHz)", value=n * world * args.steps / (ms_res * 1e-3),
+                unit="utterances/s", ms_per_step=ms_res / args.steps, rows_per_gpu=n, global_rows=n * world,
+                config=dict(workload="pBSRNN (BSRNN, examples/librimix/tse/v2/confs/bsrnn.yaml network: 32 bands, feature 128, "
+                                     "hidden 256, 6 BSNet repeats, multiply fusion) full train step, 4s@16kHz, %d rows per GPU; "
+                                     "speaker embeddings [n, 256] as input (joint_training=False)" % n,
+                            loss="SI-SDR", optimizer="per-tensor clip 5.0 + Adam(wd 1e-4)",
+                            gemm_mode="3xTF32 GEMMs; recurrence fp16 hi/lo (fwd) / bf16 hi/lo (bwd) split products"),
+                e2e=dict(value=n * world * args.steps / (ms_e2e * 1e-3), unit="utterances/s", h2d_bytes_per_step=h2d,
+                         d2h_bytes_per_step=4, ms_per_step=ms_e2e / args.steps),
+                gpu_launches=launches, loss=loss_res, loss_e2e=loss_e2e, roofline=roof,
+                top_kernels=[dict(kernel=k[:70], share=v[1] / tot, count=v[0]) for k, v in top])
 
 
 def run_ours(args, rank, world, local):
@@ -191,8 +375,8 @@ def run_ours(args, rank, world, local):
     from wesep_b200.distributed import GradAllReducer, broadcast_params
     from wesep_b200.models import get_model
     from wesep_b200.utils.executor import train_step
+    from wesep_b200.utils.lr import exponential_decrease_lr, set_lr
     from wesep_b200.utils.optim import FusedClipAdam
-    from wesep_b200.utils.schedulers import ExponentialDecrease
     import torch.distributed as dist
 
     dev = torch.device("cuda", local)
@@ -204,7 +388,6 @@ def run_ours(args, rank, world, local):
     opt = FusedClipAdam(model.parameters(), lr=1e-3, weight_decay=1e-4, clip=5.0)
     broadcast_params(opt.arena.flat_p)
     reducer = GradAllReducer(opt.arena.flat_g, n_buckets=3) if world > 1 else None
-    sched = ExponentialDecrease(opt, num_epochs=150, epoch_iter=1000, initial_lr=1e-3, final_lr=2.5e-5, warm_up_epoch=0)
     host = synth.make_batch(n, T=T_SAMPLES, Te=T_SAMPLES, seed=1234 + rank, pin=True)
     resident = {k: v.to(dev) for k, v in host.items()}
     h2d = sum(v.numel() * v.element_size() for v in host.values())
@@ -222,56 +405,59 @@ def run_ours(args, rank, world, local):
         from wesep_b200.utils.executor import GraphedTrainStep
         graphed = GraphedTrainStep(model, opt, resident, warmup=3)   # 3 eager steps, then ONE capture of the whole step
 
-    def timed_region(batch, read_loss):
-        it = [0]
+    it = [0]
 
-        def one():
-            sched.step(it[0])
-            it[0] += 1
-            loss = graphed(batch) if graphed is not None else train_step(model, batch, opt, reducer)
-            if read_loss:
-                return loss.item()                              # D2H of the step's result
-            return loss
-        for _ in range(args.warmup):
-            one()
-        barrier()
-        l0 = _lib.launch_count()
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        last = None
-        for _ in range(args.steps):
-            last = one()
-        e.record()
-        barrier()
-        ms = s.elapsed_time(e)
-        launches = _lib.launch_count() - l0
-        if graphed is not None:                                 # replays do not pass through the host-side counter
-            launches = graphed.launches_per_step * args.steps
-        if world > 1:
-            tt = torch.tensor([ms], device=dev)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            ms = float(tt)
-        return ms, launches, float(last)
+    def one(batch, read_loss):
+        set_lr(opt, exponential_decrease_lr(it[0], 150 * 1000, 1e-3, 2.5e-5))
+        it[0] += 1
+        loss = graphed(batch) if graphed is not None else train_step(model, batch, opt, reducer)
+        return loss.item() if read_loss else loss               # .item() = D2H of the step's result
 
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    ms_res, launches, loss_res = timed_region(resident, read_loss=False)
-    ms_e2e, _, loss_e2e = timed_region(host, read_loss=True)
-    clocks = sampler.summary() if sampler else None
+    ms_res, launches, loss_res = time_steps(lambda: one(resident, False), args.warmup, args.steps, barrier, world, dev)
+    if graphed is not None:                                     # replays do not pass through the host-side counter
+        launches = graphed.launches_per_step * args.steps
+    ms_e2e, _, loss_e2e = time_steps(lambda: one(host, True), args.warmup, args.steps, barrier, world, dev)
+    clocks_spex = sampler.summary() if sampler else None
     value = n * world * args.steps / (ms_res * 1e-3)
     e2e = n * world * args.steps / (ms_e2e * 1e-3)
+    roof = None
+    if rank == 0:
+        agg, tot = kernel_shares(lambda: one(resident, False))
+        roof = pick_roofline(agg, tot, SPEX_KERNELS, n, pk, 3,
+                             "kernel with the largest share of one timed step (CUPTI pass inside this run); achieved = executed "
+                             "tensor flops (3 x algorithmic: 3xTF32 split, fp32-grade) / its average duration INSIDE the step / "
+                             "measured sustained bf16 peak (%s); kind::tf32 runs at half the bf16 rate, so 0.5 is this mode's "
+                             "ceiling; traffic: see profiles/ (ncu dram bytes ~ algorithmic bytes)" % pk["src"])
+        if roof is not None:
+            step_gbs = SPEX_BYTES_PER_ROW * n * args.steps / (ms_res * 1e-3) / 1e9
+            roof["step"] = dict(bound="hbm", achieved=step_gbs, peak=pk["hbm"], unit="GB/s", frac=step_gbs / pk["hbm"],
+                                note="whole train step: 6.4 GB algorithmic bytes per row (SURVEY 8d) x rows / step time / measured HBM "
+                                     "copy bandwidth - the binding roofline of the Spex+ step")
+            roof["top_kernels"] = [dict(kernel=k[:70], share=v[1] / tot, count=v[0])
+                                   for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:6]]
+    # free the Spex+ state before the second model
+    del model, opt, reducer, resident, graphed
+    torch.cuda.empty_cache()
+    pb = None
+    if not args.no_pbsrnn:
+        pb = run_pbsrnn(args, rank, world, dev, pk, barrier)
     if rank != 0:
         return
-    roof = kernel_rooflines(n, dev, pk)
-    dom = roof["gemm_wx_k2"]
-    cpu = None
+    cpu = eager = None
     if world == 1 and not args.no_cpu_baseline:
         threads = cpu_threads()
-        v, med, _ = cpu_train_rows_per_s(args.ref_rows, 2, 1, threads)
+        rows = max(2, args.ref_rows)
+        v, med, _ = cpu_train_rows_per_s(rows, 2, 1, threads)
         cpu = dict(value=v, unit="utterances/s", cores=threads, kind="port",
-                   sample=f"{args.ref_rows} rows x {T_SAMPLES} samples, 1 warm-up + 2 timed steps (median {med:.2f} s), "
-                          "oracle port (plain torch fp32) on host CPU")
+                   sample=f"{rows} rows x {T_SAMPLES} samples, 1 warm-up + 2 timed steps (median {med:.2f} s), "
+                          f"oracle port (plain torch fp32) on {threads} threads of {os.cpu_count()} host cores ({cpu_model_name()})")
+        try:
+            eager = gpu_eager_baseline(n, dev)
+        except Exception as ex:                                 # informative block: never lose the bench line over it
+            eager = dict(error=repr(ex)[:200])
     line = dict(
         metric=METRIC, value=value, unit="utterances/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
         ms_per_step=ms_res / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
@@ -279,25 +465,14 @@ def run_ours(args, rank, world, local):
         config=dict(workload="Spex+ (ConvTasNet, examples/librimix/tse/v2/confs/spexplus.yaml) full train step, "
                              "4s@16kHz, %d model rows per GPU" % n,
                     rows_per_gpu=n, global_rows=n * world, samples=T_SAMPLES, parallelism="dp%d" % world,
-                    gemm_mode="3xTF32 split (fp32-grade); tcgen05.mma kind::tf32 cta_group::2 + TMA + TMEM GEMMs, mma.sync for odd shapes", l2="inputs and activations >> L2 (126 MB)",
+                    gemm_mode="3xTF32 split (fp32-grade); tcgen05.mma kind::tf32 cta_group::2 + TMA + TMEM GEMMs, mma.sync for odd shapes",
+                    l2="inputs and activations >> L2 (126 MB)",
                     loss="0.8/0.1/0.1 SI-SDR + 0.5 CE", optimizer="per-tensor clip 5.0 + Adam(wd 1e-4), exp-decay lr",
-                    launch="one CUDA-graph replay per step" if graphed is not None else "eager (one launch per kernel)"),
+                    launch="one CUDA-graph replay per step" if args.cuda_graph else "eager (one launch per kernel)"),
         e2e=dict(value=e2e, unit="utterances/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
                  ms_per_step=ms_e2e / args.steps),
-        gpu_launches=launches, clocks=clocks, loss=loss_res, loss_e2e=loss_e2e,
-        roofline=dict(kernel="gemm_wx_tc2_kernel<0,0,6> (tcgen05 cta_group::2; K2 shape 256->512, n=%d, K=6399)" % n,
-                      bound="tensor", achieved=dom["exec_tflops"], peak=pk["tf_burst"], unit="TFLOP/s",
-                      frac=dom["exec_tflops"] / pk["tf_burst"], frac_of_tf32_peak=dom["exec_tflops"] / (0.5 * pk["tf_burst"]),
-                      traffic=K2_DRAM_BYTES_PER_LAUNCH if n == 32 else None,
-                      note="executed = 3x algorithmic flops (3xTF32 split, fp32-grade); peak = measured bf16 burst (%s); "
-                           "kind::tf32 runs at half the bf16 rate, so frac_of_tf32_peak is the pipe utilisation; traffic = "
-                           "dram read+write of this kernel per launch from profiles/r01_ncu_full_tcn_block_n32.md" % pk["src"],
-                      algorithmic_tflops=dom["alg_tflops"], alg_gbs=dom["alg_gbs"]),
-        roofline_tcn_block=dict(bound="hbm", peak=pk["hbm"], unit="GB/s", fwd=roof["tcn_block_fwd"],
-                                bwd=roof["tcn_block_bwd"],
-                                note="algorithmic bytes per row per block: fwd (2B+4H)*K*4 = 65.5 MB, bwd (3B+8H)*K*4 = "
-                                     "124.5 MB (SURVEY 8d)"),
-        cpu_baseline=cpu)
+        gpu_launches=launches, clocks=clocks_spex, loss=loss_res, loss_e2e=loss_e2e,
+        roofline=roof, pbsrnn=pb, cpu_baseline=cpu, gpu_eager_baseline=eager)
     print(json.dumps(line), flush=True)
 
 
@@ -307,11 +482,13 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--rows", type=int, default=32, help="model rows (utterances) per GPU per step")
-    ap.add_argument("--ref-rows", type=int, default=1, help="rows per step of the bounded CPU sample")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rows", type=int, default=32, help="Spex+ model rows (utterances) per GPU per step")
+    ap.add_argument("--bsrnn-rows", type=int, default=16, help="pBSRNN model rows per GPU per step")
+    ap.add_argument("--ref-rows", type=int, default=2, help="rows per step of the bounded CPU sample (>= 2)")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU and GPU-eager baselines")
+    ap.add_argument("--no-pbsrnn", action="store_true", help="skip the pBSRNN block")
     ap.add_argument("--cuda-graph", action="store_true",
-                    help="capture the whole train step in a CUDA graph and time replays (single GPU)")
+                    help="capture the whole Spex+ train step in a CUDA graph and time replays (single GPU)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -189,22 +189,24 @@ def test_cuda_graph_train_step_matches_eager():
         m = build_model(meta["args"], meta["wseed"])
         m.train()
         opt = FusedClipAdam(m.parameters(), lr=1e-3, weight_decay=1e-4, clip=5.0)
+        p0 = opt.arena.flat_p.clone()
         losses = []
         if graph:
-            opt.param_groups[0]["lr"] = lrs[0]
-            # the constructor trains `warmup` eager steps on the example batch: mirror that in the eager run below
+            # the constructor warms up with real optimizer steps on the example batch but must RESTORE parameters, Adam
+            # state, step count and BatchNorm buffers afterwards: training starts from the state it was given
             step = GraphedTrainStep(m, opt, batches[0], warmup=2)
-            for i in range(2, 6):
+            assert opt.step_count == 0 and torch.equal(opt.arena.flat_p, p0)
+            assert float(opt.exp_avg.abs().max()) == 0.0 and float(opt.exp_avg_sq.abs().max()) == 0.0
+            for k, b in m.named_buffers():
+                if k.endswith("num_batches_tracked"):
+                    assert int(b) == 0, k
+            for i in range(6):
                 opt.param_groups[0]["lr"] = lrs[i]
                 losses.append(float(step(batches[i])))
         else:
-            opt.enable_device_scalars()
             for i in range(6):
-                opt.param_groups[0]["lr"] = lrs[0] if i < 2 else lrs[i]
-                b = batches[0] if i < 2 else batches[i]
-                loss = float(train_step(m, b, opt))
-                if i >= 2:
-                    losses.append(loss)
+                opt.param_groups[0]["lr"] = lrs[i]
+                losses.append(float(train_step(m, batches[i], opt)))
         return losses, {k: p.detach().clone() for k, p in m.named_parameters()}, opt.step_count
 
     le, pe, se = run(False)

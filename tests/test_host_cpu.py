@@ -80,16 +80,13 @@ def test_model_registry_and_state_dict_contract():
 
 
 def test_scheduler_matches_golden():
+    """Closed-form schedule vs learning rates written by the reference's own ExponentialDecrease (tests/golden/sched.npz)."""
     import numpy as np
-    from wesep_b200.utils.schedulers import ExponentialDecrease
-
-    class O:
-        param_groups = [dict(lr=0.0)]
-    s = ExponentialDecrease(O(), num_epochs=150, epoch_iter=1000, initial_lr=1e-3, final_lr=2.5e-5, warm_up_epoch=0)
+    from wesep_b200.utils.lr import exponential_decrease_lr
     z = np.load(os.path.join(ROOT, "tests", "golden", "sched.npz"))
     for it, lr in zip(z["its"], z["lrs"]):
-        s.step(int(it))
-        assert abs(s.get_lr() - lr) <= 1e-12 + 1e-9 * lr
+        got = exponential_decrease_lr(int(it), 150 * 1000, 1e-3, 2.5e-5)
+        assert abs(got - lr) <= 1e-12 + 1e-9 * lr
 
 
 def test_shard_rows():

@@ -69,8 +69,16 @@ class GraphedTrainStep:
         self.model, self.opt = model, optimizer
         self.cfg = (loss_posi, loss_weight, multi_task)
         dev = next(model.parameters()).device
-        self.static = {k: v.to(dev).clone() for k, v in example_batch.items()}
+        # only the four tensors the step consumes (a reference collate batch also carries `spk` / `key` lists), cast as
+        # train_step casts them
+        self.static = {k: example_batch[k].to(dev).float().clone() for k in ("wav_mix", "wav_targets", "spk_embeds")}
+        self.static["spk_label"] = example_batch["spk_label"].to(dev).clone()
         optimizer.enable_device_scalars()
+        # The warm-up runs real optimizer steps (the capture needs every lazily-created buffer to exist), so snapshot
+        # everything they touch and restore it afterwards: training must start from the loaded / broadcast state, with
+        # step_count, Adam moments and the BatchNorm buffers untouched.
+        snap = dict(p=optimizer.arena.flat_p.clone(), m=optimizer.exp_avg.clone(), v=optimizer.exp_avg_sq.clone(),
+                    step=optimizer.step_count, bufs={k: b.clone() for k, b in model.named_buffers()})
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):                      # warm-up off the default stream, as graph capture requires
@@ -79,11 +87,22 @@ class GraphedTrainStep:
                 self._body()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        self._restore(snap)
         self.graph = torch.cuda.CUDAGraph()
         l0 = ops._lib.launch_count()
         with torch.cuda.graph(self.graph):
             self.loss = self._body()
         self.launches_per_step = ops._lib.launch_count() - l0   # kernels of this library inside one replay
+        self._restore(snap)                                # (capture does not execute, but keep the invariant explicit)
+
+    def _restore(self, snap):
+        with torch.no_grad():
+            self.opt.arena.flat_p.copy_(snap["p"])
+            self.opt.exp_avg.copy_(snap["m"])
+            self.opt.exp_avg_sq.copy_(snap["v"])
+            self.opt.step_count = snap["step"]
+            for k, b in self.model.named_buffers():
+                b.copy_(snap["bufs"][k])
 
     def _body(self):
         loss_posi, loss_weight, multi_task = self.cfg
@@ -98,7 +117,7 @@ class GraphedTrainStep:
 
     def __call__(self, batch):
         for k, v in self.static.items():
-            v.copy_(batch[k], non_blocking=True)            # pinned host or device source
+            v.copy_(batch[k], non_blocking=True)            # pinned host or device source (dtype cast by copy_)
         self.opt.push_scalars()
         self.graph.replay()
         return self.loss
@@ -112,9 +131,14 @@ class Executor:
 
     def train(self, dataloader, models, epoch_iter, optimizers, criterion, schedulers, scaler, epoch, enable_amp,
               logger, clip_grad=5.0, log_batch_interval=100, device=torch.device("cuda"), se_loss_weight=1.0,
-              multi_task=False, reducer=None, **_unused):
+              multi_task=False, reducer=None, SSA_enroll_prob=0, fbank_args=None, sample_rate=16000, speaker_feat=True):
         if enable_amp:
             raise NotImplementedError("AMP is off in every recipe (fp32 path only)")
+        if SSA_enroll_prob and SSA_enroll_prob > 0:
+            raise NotImplementedError("SSA_enroll_prob > 0 (self-enrollment second pass, executor.py:92-104) is not built")
+        names = [type(c).__name__ for c in (criterion or [])]
+        if criterion is not None and not (names[:1] == ["SISDRLoss"] and all(n == "CrossEntropyLoss" for n in names[1:])):
+            raise NotImplementedError(f"criterion {names}: the fused loss covers SISDR (+ CE) only")
         model, optimizer, scheduler = models[0], optimizers[0], schedulers[0]
         model.train()
         optimizer.param_groups[0]["clip"] = clip_grad or 0.0

@@ -80,7 +80,12 @@ class FusedClipAdam:
         if self._dyn is None:
             dev = self.arena.flat_p.device
             self._dyn = torch.zeros(3, dtype=torch.float32, device=dev)
-            self._dyn_host = torch.zeros(3, dtype=torch.float32).pin_memory()
+            # A RING of pinned staging slots, each guarded by an event recorded after its copy: the host may run several
+            # steps ahead of the device (graph replays, no .item()), and rewriting a pinned source whose async copy has
+            # not executed yet would hand a later step's lr / bias corrections to an earlier step.
+            self._dyn_host = [torch.zeros(3, dtype=torch.float32).pin_memory() for _ in range(8)]
+            self._dyn_evt = [None] * len(self._dyn_host)
+            self._dyn_slot = 0
         return self
 
     def push_scalars(self):
@@ -88,10 +93,18 @@ class FusedClipAdam:
         g = self.param_groups[0]
         self.step_count += 1
         b1, b2 = float(g["betas"][0]), float(g["betas"][1])
-        self._dyn_host[0] = float(g["lr"])
-        self._dyn_host[1] = 1.0 - b1 ** self.step_count
-        self._dyn_host[2] = (1.0 - b2 ** self.step_count) ** 0.5
-        self._dyn.copy_(self._dyn_host, non_blocking=True)
+        i = self._dyn_slot
+        self._dyn_slot = (i + 1) % len(self._dyn_host)
+        if self._dyn_evt[i] is not None:
+            self._dyn_evt[i].synchronize()             # the copy that last read this slot has executed
+        h = self._dyn_host[i]
+        h[0] = float(g["lr"])
+        h[1] = 1.0 - b1 ** self.step_count
+        h[2] = (1.0 - b2 ** self.step_count) ** 0.5
+        self._dyn.copy_(h, non_blocking=True)
+        evt = self._dyn_evt[i] or torch.cuda.Event()
+        evt.record(torch.cuda.current_stream(self._dyn.device))
+        self._dyn_evt[i] = evt
 
     def launch(self):
         """The two kernels of a step, with no host-side state change (what a CUDA graph captures)."""
