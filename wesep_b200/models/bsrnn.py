@@ -174,13 +174,26 @@ class BSRNN(nn.Module):
                  r.bias_ih_l0_reverse, r.bias_hh_l0_reverse], m.proj.weight, m.proj.bias)
 
     def _fuse(self, layer, x, emb):
-        v = ops.LinearFn.apply(emb, layer.fc.linear.weight, layer.fc.linear.bias)        # [B, N], once per row
-        v = v.repeat(1, self.nband)                                                       # same vector for every band
+        N, nb = self.feature_dim, self.nband
+        W, b = layer.fc.linear.weight, layer.fc.linear.bias
+        if layer.fuse_type == "concat":
+            # speaker.py:95-101 (4-D branch): Linear(N + E -> N) on cat([x, embed.expand], channel) at every (band, frame)
+            # = W[:, :N] x (one pointwise conv over the N channels of every band) + (W[:, N:] embed + bias), a per-row
+            # vector computed once and shared by all bands and frames
+            B, NN, T = x.shape
+            v = ops.LinearFn.apply(emb, W[:, N:], b)                                      # [B, N]
+            rb = v.repeat_interleave(nb, 0)                                               # rows (b, band) of the band view
+            xs = ops.as_act(x)
+            ld = xs.stride(1)
+            xb = xs.as_strided((B * nb, N, T), (N * ld, ld, 1))                           # bands as rows, same memory
+            y = ops.Conv1x1RowBiasFn.apply(xb, W[:, :N], rb)
+            ld2 = y.stride(1)
+            return y.as_strided((B, NN, T), (NN * ld2, ld2, 1))
+        v = ops.LinearFn.apply(emb, W, b)                                                 # [B, N], once per row
+        v = v.repeat(1, nb)                                                               # same vector for every band
         if layer.fuse_type == "multiply":
             return ops.RowAffineFn.apply(x, v, None)
-        if layer.fuse_type == "additive":
-            return ops.RowAffineFn.apply(x, None, v)
-        raise NotImplementedError("pBSRNN fuse type 'concat' is not on the CUDA path yet")
+        return ops.RowAffineFn.apply(x, None, v)
 
     def forward(self, input, embeddings):
         if input.dim() != 2:
