@@ -408,6 +408,48 @@ typedef struct {
 int wesep_b200_groupnorm1_fwd(const WesepGroupNorm1Args* a, void* stream);
 int wesep_b200_groupnorm1_bwd(const WesepGroupNorm1Args* a, void* stream);
 
+/* ---- wespeaker ResNet speaker encoder (joint training of pBSRNN: wesep/models/bsrnn.py:217,352-356; bsrnn.yaml:56-64).
+ * Feature maps are [n][C][H*W] with W (time) contiguous.  conv3x3 (pad 1, stride 1 / 2, no bias) = im2col3x3 + conv1x1 over the
+ * 9 C gathered channels (weight [Cout][Cin*9] = the Conv2d weight viewed 2-D); the adjoint of im2col is a gather. */
+typedef struct {
+  int n, C, H, W, stride, Ho, Wo;       /* Ho = (H - 1) / stride + 1, likewise Wo */
+  int64_t ldx, ldc, bsc;                /* row strides of x / gx ([n][C][ldx]) and col / gcol (rows of ldc, batch stride bsc >= 9 C ldc;
+                                           subsample: [n][C][ldc], bsc = C ldc) */
+  const float* x; float* col;           /* fwd */
+  const float* gcol; float* gx;         /* bwd */
+} WesepIm2colArgs;
+int wesep_b200_im2col3x3_fwd(const WesepIm2colArgs* a, void* stream);
+int wesep_b200_im2col3x3_bwd(const WesepIm2colArgs* a, void* stream);
+int wesep_b200_subsample2d_fwd(const WesepIm2colArgs* a, void* stream);   /* x[.., ::s, ::s] for the 1x1 stride-s shortcut conv */
+int wesep_b200_subsample2d_bwd(const WesepIm2colArgs* a, void* stream);
+
+/* BatchNorm2d with batch statistics over (n, H, W) on [n][C][ld] (T = H*W valid columns), fused with the residual add and
+ * the ReLU of a BasicBlock.  stats / bsum: fp64 [C][2] accumulators the CALLER zeroes; the host side turns stats into
+ * scale / shift / mean / rstd ([C] vectors) and updates the running buffers.
+ *   bn2_stats : stats[c] += (sum x, sum x^2)
+ *   bn2_apply : y = act(scale[c] x + shift[c] (+ res)), act = ReLU if relu
+ *   bn2_bwd   : g' = gy * (y > 0) if relu; bsum[c] += (sum g', sum g' xhat); gx = gamma rstd (g' - bsum0/count - xhat bsum1/count);
+ *               gres = g' if not NULL (gradient of the residual branch); dgamma = bsum[c][1], dbeta = bsum[c][0] */
+typedef struct {
+  int n, C, T, relu; int64_t ld;        /* every tensor [n][C][ld] */
+  double count;                         /* n * T (bwd) */
+  const float* x; const float* res; float* y;
+  const float* scale; const float* shift; double* stats;
+  const float* gy; const float* mean; const float* rstd; const float* gamma; double* bsum; float* gx; float* gres;
+} WesepBn2Args;
+int wesep_b200_bn2_stats(const WesepBn2Args* a, void* stream);
+int wesep_b200_bn2_apply(const WesepBn2Args* a, void* stream);
+int wesep_b200_bn2_bwd(const WesepBn2Args* a, void* stream);
+
+/* TSTP pooling (wespeaker pooling_layers.TSTP): x [n][R][ld] -> out [n][2R] = (mean over time | sqrt(unbiased var + 1e-7)). */
+typedef struct {
+  int n, R, T; int64_t ld;
+  const float* x; float* out;
+  const float* gout; float* gx;
+} WesepTstpArgs;
+int wesep_b200_tstp_fwd(const WesepTstpArgs* a, void* stream);
+int wesep_b200_tstp_bwd(const WesepTstpArgs* a, void* stream);
+
 /* The LSTM recurrence of a bidirectional layer as ONE persistent cluster kernel per pass (time-major tensors, see above):
  * replaces the recurrent half of nn.LSTM inside ResRNN (wesep/models/bsrnn.py:25-31,41-44); the input projection
  * W_ih x + b_ih + b_hh of both directions is a GEMM done beforehand into G.  A cluster of Hd / 32 CTAs keeps W_hh (split

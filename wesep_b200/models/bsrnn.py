@@ -1,11 +1,12 @@
 """pBSRNN — parameter / constructor contract of the reference wesep/models/bsrnn.py:151-298 (class name, kwargs,
 attribute paths, parameter shapes and order, hence `state_dict()` keys, checkpoint and optimizer-state layout).
 
-STATUS: first correct path (`joint_training=False`, fuse types multiply / additive).  The
-forward runs on libwesep_b200: STFT / iSTFT as framing + windowed-DFT GEMMs, band split as GroupNorm + one block-diagonal
-GEMM, ResRNN in a time-major layout (input / recurrent / output projections on the conv1x1 GEMMs, one GEMM + one cell
-kernel per time step — `ops.LstmTmFn`), mask MLPs as GEMMs with tanh / gating kernels.  It is launch-bound (the
-recurrence is driven from Python); DESIGN.md §7 has the plan for the persistent-cluster recurrence.  There is no PyTorch
+STATUS: SURVEY.md §8 rows a15-a22: fuse types multiply / additive / concat, `joint_training` False (embeddings in) or True
+(fbank in, wespeaker ResNet18 / ResNet34 + TSTP trained jointly, `multi_task` head included).  The forward runs on
+libwesep_b200: STFT / iSTFT as framing + windowed-DFT GEMMs, band split as GroupNorm + one block-diagonal GEMM, ResRNN in
+a time-major layout (input / output projections on the tcgen05 conv1x1 GEMMs, the recurrence of both directions and all
+steps as ONE persistent cluster kernel per pass — `ops.LstmTmFn`, csrc/lstm_rec.cu), mask MLPs as GEMMs with tanh /
+gating kernels.  There is no PyTorch
 fallback: the nn.GroupNorm / nn.LSTM / nn.Linear / nn.Conv1d objects below are parameter containers (same initialisation
 as the reference); their own forwards are never called.  Small torch glue remains (reflect padding, weight assembly,
 concatenation of band slices, the 1 / sum(w^2) envelope).
@@ -101,9 +102,6 @@ class BSRNN(nn.Module):
         feat_type="consistent",
     ):
         super().__init__()
-        if joint_training:
-            raise NotImplementedError("pBSRNN with joint_training=True needs the wespeaker speaker encoder (SURVEY.md §8 row "
-                                      "a22, not built); construct with joint_training=False and pass embeddings")
         if use_spk_transform:
             raise NotImplementedError("use_spk_transform=True is not on the recipe path (bsrnn.yaml:54)")
         if not use_bidirectional:
@@ -114,6 +112,7 @@ class BSRNN(nn.Module):
         self.eps = torch.finfo(torch.float32).eps
         self.spk_emb_dim = spk_emb_dim
         self.joint_training, self.multi_task = joint_training, multi_task
+        self.spk_feat, self.feat_type, self.spk_model_freeze = spk_feat, feat_type, spk_model_freeze
         # band layout, bsrnn.py:228-242
         bw100 = int(np.floor(100 / (sr / 2.0) * self.enc_dim))
         bw200 = int(np.floor(200 / (sr / 2.0) * self.enc_dim))
@@ -123,6 +122,27 @@ class BSRNN(nn.Module):
         self.band_width.append(self.enc_dim - int(np.sum(self.band_width)))
         self.nband = len(self.band_width)
         self.spk_transform = nn.Identity()
+        if joint_training:                                         # bsrnn.py:216-250
+            from wesep_b200.modules.speaker.resnet import get_speaker_model
+            if not spk_feat:
+                raise NotImplementedError("spk_feat=False (fbank computed inside the model from raw enrollment audio, "
+                                          "bsrnn.py:231-241) is not built: the recipes feed fbank features (bsrnn.yaml:15,82)")
+            self.spk_model = get_speaker_model(spk_model)(**(spk_args or {}))
+            if spk_model_init:
+                pretrained = torch.load(spk_model_init, map_location="cpu")
+                state = self.spk_model.state_dict()
+                for key in state.keys():
+                    if key in pretrained.keys():
+                        state[key] = pretrained[key]
+                    else:
+                        print("not %s loaded" % key)
+                self.spk_model.load_state_dict(state)
+            if spk_model_freeze:
+                for param in self.spk_model.parameters():
+                    param.requires_grad = False
+            self.preEmphasis = nn.Identity()
+            self.spk_encoder = nn.Identity()
+            self.pred_linear = nn.Linear(spk_emb_dim, spksInTrain) if multi_task else nn.Identity()
         self.BN = nn.ModuleList([nn.Sequential(nn.GroupNorm(1, bw * 2, self.eps), nn.Conv1d(bw * 2, feature_dim, 1))
                                  for bw in self.band_width])
         self.separator = FuseSeparation(nband=self.nband, num_repeat=num_repeat, feature_dim=feature_dim,
@@ -221,7 +241,16 @@ class BSRNN(nn.Module):
             Wbig[i * N:(i + 1) * N, o:o + 2 * bw] = self.BN[i][1].weight[:, :, 0]
         bbig = torch.cat([self.BN[i][1].bias for i in range(nb)])
         x = ops.Conv1x1Fn.apply(xhat, Wbig, bbig, False, None)                            # [B, nb*N, T]
-        emb = self.spk_transform(embeddings).float()
+        predict_speaker_lable = torch.tensor(0.0, device=dev)       # dummy, bsrnn.py:340-341
+        spk_in = embeddings
+        if self.joint_training:                                    # bsrnn.py:342-357
+            tmp = self.spk_model(spk_in)
+            spk_in = tmp[-1] if isinstance(tmp, tuple) else tmp
+            if self.multi_task:
+                predict_speaker_lable = ops.LinearFn.apply(spk_in, self.pred_linear.weight, self.pred_linear.bias)
+            else:
+                predict_speaker_lable = spk_in                      # nn.Identity
+        emb = self.spk_transform(spk_in).float()
         sep = self.separator.separation
         if self.separator.multi_fuse:
             for r in range(len(sep) // 2):
@@ -253,4 +282,4 @@ class BSRNN(nn.Module):
                 e[t * hop:t * hop + win] += w2
             env = self._env_cache[(str(dev), T)] = 1.0 / e[win // 2:win // 2 + L]
         s = y[:, win // 2:win // 2 + L] * env
-        return s, torch.tensor(0.0, device=dev)
+        return s, predict_speaker_lable

@@ -296,7 +296,7 @@ class Conv1x1Fn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, W2d, bias, w_trans, act):
-        x = as_act(x)
+        x = x if is_act_slice(x) else as_act(x)            # channel slices of an act tensor are read in place
         W2d = W2d if W2d.is_contiguous() else W2d.contiguous()
         M = W2d.shape[1] if w_trans else W2d.shape[0]
         Kd = W2d.shape[0] if w_trans else W2d.shape[1]
@@ -1153,3 +1153,155 @@ class MaskApplyFn(torch.autograd.Function):
                                                      lde=ge.stride(1), bso=o.stride(0), bss=s.stride(0), bse=ge.stride(0), o=o,
                                                      s=s, ge=ge, go=go), _stream())
         return go, None
+
+
+# --------------------------------------------------------------------------- wespeaker ResNet building blocks
+def conv1x1_bigk(x, W2d, bias=None):
+    """Conv1x1Fn for any number of input channels: > 1024 channels (what one tcgen05 launch covers) are contracted in chunks,
+    the later chunks accumulating onto the first (autograd sees ordinary Conv1x1Fn nodes + adds)."""
+    Kd = x.shape[1]
+    if Kd <= 1024:
+        return Conv1x1Fn.apply(x, W2d, bias, False, None)
+    y = None
+    for k0 in range(0, Kd, 1024):
+        k1 = min(Kd, k0 + 1024)
+        part = Conv1x1Fn.apply(x[:, k0:k1], W2d[:, k0:k1], bias if k0 == 0 else None, False, None)
+        y = part if y is None else AddFn.apply(y, part)
+    return y
+
+
+class AddFn(torch.autograd.Function):
+    """a + b for two act tensors (the gradient is shared, not copied)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = as_act(a), as_act(b)
+        out = new_act(a.shape[0], a.shape[1], a.shape[2], a.device)
+        torch.add(a, b, out=out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g
+
+
+def _i2c_args(n, C, H, W, stride, ldx, ct, **kw):
+    """`ct`: the col-side tensor (its row / batch strides)."""
+    return _args("WesepIm2colArgs", n=n, C=C, H=H, W=W, stride=stride, Ho=(H - 1) // stride + 1, Wo=(W - 1) // stride + 1,
+                 ldx=ldx, ldc=ct.stride(1), bsc=ct.stride(0), **kw)
+
+
+class Im2Col3x3Fn(torch.autograd.Function):
+    """[n, C, H*W] -> [n, 9C, Ho*Wo]: the patches of a 3x3 / pad 1 / stride s convolution (rows ordered (c, kh, kw) = the
+    Conv2d weight viewed [Cout, Cin*9]); the adjoint gathers."""
+
+    @staticmethod
+    def forward(ctx, x, H, W, stride):
+        x = as_act(x)
+        n, C, HW = x.shape
+        if HW != H * W:
+            raise RuntimeError("im2col: H * W does not match the tensor")
+        Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+        Kp = (9 * C + 15) // 16 * 16                    # GEMM-friendly channel count: zero rows beyond 9 C (first conv: 9 -> 16)
+        col = new_act(n, Kp, Ho * Wo, x.device)
+        if Kp != 9 * C:
+            col[:, 9 * C:].zero_()
+        _lib.call("wesep_b200_im2col3x3_fwd", _i2c_args(n, C, H, W, stride, x.stride(1), col, x=x, col=col), _stream())
+        ctx.meta = (n, C, H, W, stride, x.stride(1))
+        return col
+
+    @staticmethod
+    def backward(ctx, gcol):
+        n, C, H, W, stride, ldx = ctx.meta
+        gcol = as_act(gcol)                             # [n, Kp, Ho*Wo]: rows >= 9 C are ignored
+        gx = new_act(n, C, H * W, gcol.device)
+        _lib.call("wesep_b200_im2col3x3_bwd", _i2c_args(n, C, H, W, stride, gx.stride(1), gcol, gcol=gcol, gx=gx), _stream())
+        return gx, None, None, None
+
+
+class Subsample2dFn(torch.autograd.Function):
+    """x[..., ::s, ::s] of a [n, C, H*W] map (input of the 1x1 stride-s shortcut convolution)."""
+
+    @staticmethod
+    def forward(ctx, x, H, W, stride):
+        x = as_act(x)
+        n, C, _ = x.shape
+        Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+        y = new_act(n, C, Ho * Wo, x.device)
+        _lib.call("wesep_b200_subsample2d_fwd", _i2c_args(n, C, H, W, stride, x.stride(1), y, x=x, col=y), _stream())
+        ctx.meta = (n, C, H, W, stride)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        n, C, H, W, stride = ctx.meta
+        gy = as_act(gy)
+        gx = new_act(n, C, H * W, gy.device)
+        _lib.call("wesep_b200_subsample2d_bwd", _i2c_args(n, C, H, W, stride, gx.stride(1), gy, gcol=gy, gx=gx), _stream())
+        return gx, None, None, None
+
+
+class BnActFn(torch.autograd.Function):
+    """y = act(BatchNorm(x) (+ res)) on [n, C, T] with batch statistics over (n, T) (nn.BatchNorm2d on a [n, C, H, W] map),
+    act = ReLU or identity; running buffers updated like nn.BatchNorm (momentum, unbiased variance)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, res, relu, training, momentum, eps):
+        x = as_act(x)
+        n, C, T = x.shape
+        dev = x.device
+        stats = torch.zeros((C, 2), dtype=torch.float64, device=dev)
+        st = _stream()
+        if training:
+            _lib.call("wesep_b200_bn2_stats", _args("WesepBn2Args", n=n, C=C, T=T, ld=x.stride(1), x=x, stats=stats), st)
+        fin = _bn_finalize(stats, n * T, weight, bias, running_mean, running_var, momentum, eps, training)
+        if res is not None:
+            res = as_act(res)
+            if res.stride() != x.stride():
+                raise RuntimeError("bn: residual layout")
+        y = new_act(n, C, T, dev)
+        _lib.call("wesep_b200_bn2_apply", _args("WesepBn2Args", n=n, C=C, T=T, relu=int(relu), ld=x.stride(1), x=x, res=res, y=y,
+                                                scale=fin[0], shift=fin[1]), st)
+        ctx.relu, ctx.has_res, ctx.training = bool(relu), res is not None, bool(training)
+        ctx.save_for_backward(x, y if relu else None, fin, _vec(weight))
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        if not ctx.training:
+            raise NotImplementedError("BatchNorm backward with running statistics (eval mode) is not built")
+        x, y, fin, w = ctx.saved_tensors
+        n, C, T = x.shape
+        gy = as_act(gy)
+        if gy.stride() != x.stride():
+            raise RuntimeError("bn backward: gradient layout")
+        gx = new_act(n, C, T, x.device)
+        gres = new_act(n, C, T, x.device) if ctx.has_res else None
+        bsum = torch.zeros((C, 2), dtype=torch.float64, device=x.device)
+        _lib.call("wesep_b200_bn2_bwd", _args("WesepBn2Args", n=n, C=C, T=T, relu=int(ctx.relu), ld=x.stride(1), count=float(n * T),
+                                              x=x, y=y, gy=gy, mean=fin[2], rstd=fin[3], gamma=w, bsum=bsum, gx=gx, gres=gres),
+                  _stream())
+        bf = bsum.float()
+        return gx, bf[:, 1].contiguous(), bf[:, 0].contiguous(), None, None, gres, None, None, None, None
+
+
+class TstpFn(torch.autograd.Function):
+    """wespeaker TSTP pooling: [n, R, T] -> [n, 2R] = (mean | sqrt(unbiased var + 1e-7)) over time."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = as_act(x)
+        n, R, T = x.shape
+        out = torch.empty((n, 2 * R), dtype=torch.float32, device=x.device)
+        _lib.call("wesep_b200_tstp_fwd", _args("WesepTstpArgs", n=n, R=R, T=T, ld=x.stride(1), x=x, out=out), _stream())
+        ctx.save_for_backward(x)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        n, R, T = x.shape
+        gx = new_act(n, R, T, x.device)
+        _lib.call("wesep_b200_tstp_bwd", _args("WesepTstpArgs", n=n, R=R, T=T, ld=x.stride(1), x=x, gout=g.contiguous().float(),
+                                               gx=gx), _stream())
+        return gx
