@@ -32,8 +32,11 @@ SPEX_ARGS = dict(B=256, H=512, L=20, N=256, P=3, R=4, X=8, spk_emb_dim=256, acti
                  encoder_type="Multi", decoder_type="Multi", joint_training=True, multi_task=True, spksInTrain=251)
 T_SAMPLES = 64000
 METRIC = "utterances/sec Spex+ train step (4s@16kHz)"
-BSRNN_ARGS = dict(spk_emb_dim=256, sr=16000, win=512, stride=128, feature_dim=128, num_repeat=6, use_spk_transform=False,
-                  spk_fuse_type="multiply", multi_fuse=False, joint_training=False)   # bsrnn.yaml:48-55 (+ embeddings in)
+BSRNN_ARGS = dict(sr=16000, win=512, stride=128, feature_dim=128, num_repeat=6, spk_fuse_type="multiply", use_spk_transform=False,
+                  multi_fuse=False, joint_training=True, spk_model="ResNet34", spk_model_init=False,
+                  spk_args=dict(feat_dim=80, embed_dim=256, pooling_func="TSTP", two_emb_layer=False), spk_emb_dim=256,
+                  spk_model_freeze=False, spk_feat=True, feat_type="consistent", multi_task=False)   # bsrnn.yaml:46-83 verbatim
+BSRNN_FBANK_FRAMES = 398        # 1 + (64000 - 400) // 160 frames of 25 ms / 10 ms fbank for a 4 s enrollment
 SPEX_BYTES_PER_ROW = 6.4e9      # algorithmic HBM bytes per row per train step (32 x 190 MB + 0.35 GB)
 SPEX_FLOPS_PER_ROW = 396e9      # algorithmic flops per row per train step (132 GFLOP forward x 3)
 BSRNN_FLOPS_PER_ROW = 1.02e12   # (340 GFLOP forward x 3)
@@ -311,7 +314,8 @@ def run_pbsrnn(args, rank, world, dev, pk, barrier):
     broadcast_params(opt.arena.flat_p)
     reducer = GradAllReducer(opt.arena.flat_g, n_buckets=1) if world > 1 else None
     host = synth.make_batch(n, T=T_SAMPLES, Te=8, seed=4321 + rank, pin=True)
-    emb_h = torch.from_numpy(np.random.default_rng(5 + rank).standard_normal((n, 256)).astype(np.float32)).pin_memory()
+    emb_h = torch.from_numpy(np.random.default_rng(5 + rank).standard_normal((n, BSRNN_FBANK_FRAMES, 80))
+                             .astype(np.float32)).pin_memory()          # enrollment fbank features (after CMN) ~ N(0, 1)
     host = dict(wav_mix=host["wav_mix"], wav_targets=host["wav_targets"], emb=emb_h)
     resident = {k: v.to(dev) for k, v in host.items()}
     h2d = sum(v.numel() * v.element_size() for v in host.values())
@@ -330,7 +334,25 @@ def run_pbsrnn(args, rank, world, dev, pk, barrier):
         opt.step()
         return losses[0].item() if read_loss else losses[0]
 
+    graphed = None
+    if world == 1 and not args.no_graph:
+        # the eager pBSRNN step is host-bound (~4000 launches incl. the per-band loops): capture it once, replay per step
+        from wesep_b200.utils.executor import GraphedStep
+
+        def body(b):
+            est, _ = model(b["wav_mix"], b["emb"])
+            losses, _ = ops.sisdr_losses([est], b["wav_targets"])
+            losses[0].backward()
+            return losses[0]
+        graphed = GraphedStep(model, opt, resident, body, warmup=2)
+
+        def step(batch, read_loss):                                # noqa: F811
+            loss = graphed(batch)                                   # copies the batch (pinned host or device) into the static inputs
+            return loss.item() if read_loss else loss
+
     ms_res, launches, loss_res = time_steps(lambda: step(resident, False), args.warmup, args.steps, barrier, world, dev)
+    if graphed is not None:
+        launches = graphed.launches_per_step * args.steps
     ms_e2e, _, loss_e2e = time_steps(lambda: step(host, True), 1, args.steps, barrier, world, dev)
     if rank != 0:
         return None
@@ -360,9 +382,10 @@ def run_pbsrnn(args, rank, world, dev, pk, barrier):
     return dict(metric="utterances/sec pBSRNN train step (4s@16kHz)", value=n * world * args.steps / (ms_res * 1e-3),
                 unit="utterances/s", ms_per_step=ms_res / args.steps, rows_per_gpu=n, global_rows=n * world,
                 config=dict(workload="pBSRNN (BSRNN, examples/librimix/tse/v2/confs/bsrnn.yaml network: 32 bands, feature 128, "
-                                     "hidden 256, 6 BSNet repeats, multiply fusion) full train step, 4s@16kHz, %d rows per GPU; "
-                                     "speaker embeddings [n, 256] as input (joint_training=False)" % n,
+                                     "hidden 256, 6 BSNet repeats, multiply fusion, jointly trained wespeaker ResNet34-TSTP speaker encoder on "
+                                     "[n, 398, 80] enrollment fbank features) full train step, 4s@16kHz, %d rows per GPU" % n,
                             loss="SI-SDR", optimizer="per-tensor clip 5.0 + Adam(wd 1e-4)",
+                            launch="one CUDA-graph replay per step" if graphed is not None else "eager (one launch per kernel)",
                             gemm_mode="3xTF32 GEMMs; recurrence fp16 hi/lo (fwd) / bf16 hi/lo (bwd) split products"),
                 e2e=dict(value=n * world * args.steps / (ms_e2e * 1e-3), unit="utterances/s", h2d_bytes_per_step=h2d,
                          d2h_bytes_per_step=4, ms_per_step=ms_e2e / args.steps),
@@ -487,6 +510,7 @@ def main():
     ap.add_argument("--ref-rows", type=int, default=2, help="rows per step of the bounded CPU sample (>= 2)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU and GPU-eager baselines")
     ap.add_argument("--no-pbsrnn", action="store_true", help="skip the pBSRNN block")
+    ap.add_argument("--no-graph", action="store_true", help="pBSRNN block: eager launches instead of a CUDA-graph replay per step")
     ap.add_argument("--cuda-graph", action="store_true",
                     help="capture the whole Spex+ train step in a CUDA graph and time replays (single GPU)")
     args = ap.parse_args()

@@ -15,13 +15,13 @@ secs = float(sys.argv[2]) if len(sys.argv) > 2 else 4.0
 out = sys.argv[3] if len(sys.argv) > 3 else None
 L = int(16000 * secs)
 dev = "cuda"
-m = get_model("BSRNN")(spk_emb_dim=256, sr=16000, win=512, stride=128, feature_dim=128, num_repeat=6, use_spk_transform=False,
-                       spk_fuse_type="multiply", multi_fuse=False, joint_training=False)
+import bench
+m = get_model("BSRNN")(**bench.BSRNN_ARGS)
 synth.fill_state_dict_(m.state_dict(), seed=1)
 m = m.to(dev).train()
 opt = FusedClipAdam(m.parameters(), lr=1e-3, weight_decay=1e-4, clip=5.0)
 b = synth.make_batch(n, T=L, Te=8, seed=3, device=dev)
-emb = torch.from_numpy(np.random.default_rng(5).standard_normal((n, 256)).astype(np.float32)).to(dev)
+emb = torch.from_numpy(np.random.default_rng(5).standard_normal((n, bench.BSRNN_FBANK_FRAMES, 80)).astype(np.float32)).to(dev)
 
 
 def step():

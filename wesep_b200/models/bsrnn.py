@@ -241,7 +241,7 @@ class BSRNN(nn.Module):
             Wbig[i * N:(i + 1) * N, o:o + 2 * bw] = self.BN[i][1].weight[:, :, 0]
         bbig = torch.cat([self.BN[i][1].bias for i in range(nb)])
         x = ops.Conv1x1Fn.apply(xhat, Wbig, bbig, False, None)                            # [B, nb*N, T]
-        predict_speaker_lable = torch.tensor(0.0, device=dev)       # dummy, bsrnn.py:340-341
+        predict_speaker_lable = torch.zeros((), device=dev)          # dummy, bsrnn.py:340-341 (a fill kernel: graph-capturable)
         spk_in = embeddings
         if self.joint_training:                                    # bsrnn.py:342-357
             tmp = self.spk_model(spk_in)

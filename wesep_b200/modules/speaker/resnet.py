@@ -123,7 +123,7 @@ class ResNet(nn.Module):
             hc = ops.as_act(h.reshape(n, C * H, W))
         stats = ops.TstpFn.apply(hc)                                 # [n, 2 * C * H]
         emb = ops.LinearFn.apply(stats, self.seg_1.weight, self.seg_1.bias)
-        return torch.tensor(0.0, device=x.device), emb
+        return torch.zeros((), device=x.device), emb
 
 
 def ResNet18(feat_dim, embed_dim, pooling_func="TSTP", two_emb_layer=True):

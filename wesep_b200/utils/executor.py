@@ -52,31 +52,25 @@ def train_step(model, batch, optimizer, reducer=None, loss_posi=((0, 1, 2), (3,)
     return loss
 
 
-class GraphedTrainStep:
-    """The whole train step (zero_grad, forward, loss, backward, clip + Adam) captured ONCE in a CUDA graph and replayed:
-    ~840 kernel launches per step become one graph launch, removing the inter-kernel launch gaps (~5 % of the step) and
-    all per-step Python / ctypes work.  Single-process only (the gradient all-reduce stays outside a graph: use the eager
-    `train_step` with a reducer for N > 1).  Shapes are frozen at capture: every batch must match the example batch.
+class GraphedStep:
+    """A whole train step (zero_grad, forward, loss, backward, clip + Adam) captured ONCE in a CUDA graph and replayed:
+    the ~10^3 kernel launches of a step become one graph launch, removing the inter-kernel gaps and all per-step Python /
+    ctypes work (the pBSRNN step is otherwise host-bound).  Single-process only (the gradient all-reduce stays outside a
+    graph: use the eager step with a reducer for N > 1).  Shapes are frozen at capture: every batch must match the example.
 
-        step = GraphedTrainStep(model, optimizer, example_batch)     # runs `warmup` eager steps on it, then captures
+        step = GraphedStep(model, optimizer, example_batch, body)    # body(static_batch) -> loss, up to and incl. backward
         loss = step(batch)                                            # device tensor (static storage): read or copy it
 
+    The constructor runs `warmup` eager steps (every lazily created buffer must exist before the capture) and then RESTORES
+    parameters, Adam moments, the step counter and all module buffers, so training starts from the state it was given.
     The learning rate may change between calls (`param_groups[0]["lr"]`): the optimizer kernels read the schedule-dependent
     scalars from device memory (`FusedClipAdam.enable_device_scalars`)."""
 
-    def __init__(self, model, optimizer, example_batch, loss_posi=((0, 1, 2), (3,)), loss_weight=((0.8, 0.1, 0.1), (0.5,)),
-                 multi_task=True, warmup=3):
-        self.model, self.opt = model, optimizer
-        self.cfg = (loss_posi, loss_weight, multi_task)
+    def __init__(self, model, optimizer, example_batch, body, warmup=3):
+        self.model, self.opt, self.body = model, optimizer, body
         dev = next(model.parameters()).device
-        # only the four tensors the step consumes (a reference collate batch also carries `spk` / `key` lists), cast as
-        # train_step casts them
-        self.static = {k: example_batch[k].to(dev).float().clone() for k in ("wav_mix", "wav_targets", "spk_embeds")}
-        self.static["spk_label"] = example_batch["spk_label"].to(dev).clone()
+        self.static = {k: v.to(dev).clone() for k, v in example_batch.items()}
         optimizer.enable_device_scalars()
-        # The warm-up runs real optimizer steps (the capture needs every lazily-created buffer to exist), so snapshot
-        # everything they touch and restore it afterwards: training must start from the loaded / broadcast state, with
-        # step_count, Adam moments and the BatchNorm buffers untouched.
         snap = dict(p=optimizer.arena.flat_p.clone(), m=optimizer.exp_avg.clone(), v=optimizer.exp_avg_sq.clone(),
                     step=optimizer.step_count, bufs={k: b.clone() for k, b in model.named_buffers()})
         side = torch.cuda.Stream(device=dev)
@@ -105,13 +99,8 @@ class GraphedTrainStep:
                 b.copy_(snap["bufs"][k])
 
     def _body(self):
-        loss_posi, loss_weight, multi_task = self.cfg
-        b = self.static
         self.opt.zero_grad()
-        outputs = self.model(b["wav_mix"], b["spk_embeds"])
-        loss, _ = compute_loss(outputs, b["wav_targets"], b["spk_label"], loss_posi, loss_weight, multi_task)
-        with ops.direct_param_grads():
-            loss.backward()
+        loss = self.body(self.static)
         self.opt.launch()
         return loss
 
@@ -121,6 +110,25 @@ class GraphedTrainStep:
         self.opt.push_scalars()
         self.graph.replay()
         return self.loss
+
+
+class GraphedTrainStep(GraphedStep):
+    """GraphedStep for the Spex+ recipe loop body (weighted SI-SDR + CE loss on the four-tensor collate batch)."""
+
+    def __init__(self, model, optimizer, example_batch, loss_posi=((0, 1, 2), (3,)), loss_weight=((0.8, 0.1, 0.1), (0.5,)),
+                 multi_task=True, warmup=3):
+        # only the four tensors the step consumes (a reference collate batch also carries `spk` / `key` lists), cast as
+        # train_step casts them
+        ex = {k: example_batch[k].float() for k in ("wav_mix", "wav_targets", "spk_embeds")}
+        ex["spk_label"] = example_batch["spk_label"]
+
+        def body(b):
+            outputs = model(b["wav_mix"], b["spk_embeds"])
+            loss, _ = compute_loss(outputs, b["wav_targets"], b["spk_label"], loss_posi, loss_weight, multi_task)
+            with ops.direct_param_grads():
+                loss.backward()
+            return loss
+        super().__init__(model, optimizer, ex, body, warmup)
 
 
 class Executor:
