@@ -164,12 +164,15 @@ def resnet4spexplus(sd, pre, x, training, buffers_out=None):
 
 
 # --------------------------------------------------------------------------- decoder
-def multi_decoder(sd, pre, e, w1, w2, w3, stride=10):
-    """MultiDecoder.forward (actLayer = ReLU) — wesep/modules/tasnet/decoder.py:92-114."""
+def multi_decoder(sd, pre, e, w1, w2, w3, stride=10, relu_on=None):
+    """MultiDecoder.forward (actLayer = ReLU) — wesep/modules/tasnet/decoder.py:92-114.
+    `relu_on` (tests only): three boolean masks that PIN the ReLU branch of every element (two fp32 implementations
+    legitimately disagree where a pre-activation is ~1e-7; a flipped branch is a discrete change of the gradient)."""
     ests = []
     xlen = None
     for i, w in enumerate((w1, w2, w3), start=1):
-        m = F.relu(F.conv1d(e, sd[f"{pre}mask{i}.weight"], sd[f"{pre}mask{i}.bias"]))
+        a = F.conv1d(e, sd[f"{pre}mask{i}.weight"], sd[f"{pre}mask{i}.bias"])
+        m = F.relu(a) if relu_on is None else a * relu_on[i - 1].to(a.dtype)
         s = w * m
         est = F.conv_transpose1d(s, sd[f"{pre}decoder_1d_{i}.weight"], sd[f"{pre}decoder_1d_{i}.bias"], stride=stride)
         est = est.squeeze(1)  # torch.squeeze of the size-1 channel dim; n==1 handled at decoder.py:109-112

@@ -21,3 +21,13 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+def pytest_sessionstart(session):
+    """WESEP_TC_FLAGS=<int>: debug / A-B switches of the tcgen05 GEMMs for a whole test session (e.g. 1024 = 2-CTA kernels in
+    3xTF32 instead of the mixed tf32 + bf16 split product)."""
+    import os
+    fl = os.environ.get("WESEP_TC_FLAGS")
+    if fl:
+        from wesep_b200 import _lib
+        _lib.lib().wesep_b200_set_tc_flags(int(fl))

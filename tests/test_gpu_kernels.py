@@ -309,14 +309,18 @@ def test_multi_decoder(n, K):
     w = ops.new_act(n, 768, K, DEV)
     w.copy_(torch.relu(rnd(n, 768, K, seed=4)))
     w.requires_grad_(True)
+    ops.DEBUG_STASH = {}
     ests = dec.forward_cat(e, w)
+    stash, ops.DEBUG_STASH = ops.DEBUG_STASH, None
+    m_on = stash["decoder_m"] > 0           # the CUDA path's ReLU branches: pinned in the oracle (PReLU / ReLU kink)
     gys = [rnd(*o.shape, seed=5 + i) for i, o in enumerate(ests)]
     params = list(dec.parameters())
     grads = torch.autograd.grad(ests, [e, w] + params, gys)
     sd64 = {k: v.detach().double().requires_grad_(True) for k, v in dec.state_dict().items()}
     e64 = e.detach().double().requires_grad_(True)
     w64 = w.detach().double().requires_grad_(True)
-    r = ospex.multi_decoder(sd64, "", e64, w64[:, :256], w64[:, 256:512], w64[:, 512:])
+    r = ospex.multi_decoder(sd64, "", e64, w64[:, :256], w64[:, 256:512], w64[:, 512:],
+                            relu_on=[m_on[:, :256], m_on[:, 256:512], m_on[:, 512:]])
     names = [k for k, _ in dec.named_parameters()]
     ref = torch.autograd.grad(r, [e64, w64] + [sd64[k] for k in names], [g.double() for g in gys])
     for i, (a, b) in enumerate(zip(ests, r)):

@@ -164,6 +164,8 @@ struct TcParams {
   int skip_hi_store;   // PRO 0 only: leave the raw fp32 tile as the "hi" operand (valid iff the MMA truncates to tf32)
   int xf_groups;       // transform warps split into this many groups (1, 2, 4); group g handles stages with it % groups == g
   int dbg;             // timing experiments only (2-CTA kernel): 1 = no epilogue loads, 2 = no epilogue stores, 4 = no transform
+  int mixed;           // 2-CTA kernel: tf32 leading term + bf16 cross terms (see tc_mma_bf16_2cta) instead of 3xTF32
+  const uint8_t* wimg; // mixed: bf16 weight images, 8 KB per (128-channel block, K block)
 };
 int g_tc_flags = 0;
 
@@ -558,7 +560,9 @@ bool gemm_wx_tc_eligible(const GemmWxP& p, int pro, int epi) {
   return true;
 }
 
-size_t gemm_wx_tc_ws_bytes(int M, int Kd) { return (size_t)2 * ((M + 31) & ~31) * Kd * sizeof(float); }
+size_t gemm_wx_tc_ws_bytes(int M, int Kd) {   // hi + lo fp32 copies, or hi + the bf16 images (K padded to 16) of the mixed mode
+  return (size_t)((M + 31) & ~31) * (Kd + ((Kd + 15) & ~15)) * sizeof(float);
+}
 
 template <int PRO, int EPI>
 static int launch_tc_t(const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& mx, const TcParams& P, cudaStream_t st) {
@@ -577,6 +581,9 @@ static int launch_tc_t(const CUtensorMap& mh, const CUtensorMap& ml, const CUten
 }
 
 bool gemm_wx_tc2_eligible(const GemmWxP& p, int pro, int epi);
+bool gemm_wx_tc2_instantiated(int pro, int epi);
+__global__ void split_w_mixed_kernel(const float* __restrict__ W, int64_t ldw, int w_trans, int M, int Kd, float* __restrict__ hi,
+                                     uint8_t* __restrict__ img);
 int launch_gemm_wx_tc2(const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& mx, TcParams P, int pro, int epi,
                        cudaStream_t st);
 
@@ -587,9 +594,18 @@ int launch_gemm_wx_tc(const GemmWxP& p, bool a_trans, int pro, int epi, void* ws
   const int M32 = (p.M + 31) & ~31;
   float* whi = reinterpret_cast<float*>(ws);
   float* wlo = whi + (size_t)M32 * p.Kd;
-  if (!p.ws_presplit) {   // loops that reuse one weight (the LSTM recurrence) split it once and set ws_presplit
-    int total = M32 * p.Kd;
-    split_w_kernel<<<cdiv(total, 256), 256, 0, st>>>(p.W, p.ldw, a_trans ? 1 : 0, p.M, p.Kd, whi, wlo);
+  // the 2-CTA kernel runs the mixed tf32 + bf16 split product (its weight operand is prepared differently)
+  const bool use2 = gemm_wx_tc2_eligible(p, pro, epi) && gemm_wx_tc2_instantiated(pro, epi);
+  const bool mixed = use2 && !(g_tc_flags & 1024);
+  if (!p.ws_presplit) {   // loops that reuse one weight split it once and set ws_presplit
+    if (mixed) {
+      const int total = (p.M >> 2) * (((p.Kd + 15) >> 4) * 16);
+      split_w_mixed_kernel<<<cdiv(total, 256), 256, 0, st>>>(p.W, p.ldw, a_trans ? 1 : 0, p.M, p.Kd, whi,
+                                                             reinterpret_cast<uint8_t*>(wlo));
+    } else {
+      const int total = M32 * p.Kd;
+      split_w_kernel<<<cdiv(total, 256), 256, 0, st>>>(p.W, p.ldw, a_trans ? 1 : 0, p.M, p.Kd, whi, wlo);
+    }
     WB_LAUNCH_CHECK("split_w");
   }
   CUtensorMap mh, ml, mx, mx2;
@@ -623,7 +639,9 @@ int launch_gemm_wx_tc(const GemmWxP& p, bool a_trans, int pro, int epi, void* ws
     P.xf_groups = sel == 1 ? 1 : sel == 3 ? 4 : 2;
     P.dbg = (g_tc_flags >> 4) & 15;
   }
-  if (gemm_wx_tc2_eligible(p, pro, epi)) {      // 2-CTA (cta_group::2) kernel for 256-channel multiples
+  P.mixed = mixed ? 1 : 0;
+  P.wimg = reinterpret_cast<const uint8_t*>(wlo);
+  if (use2) {                                   // 2-CTA (cta_group::2) kernel for 256-channel multiples
     int rc = launch_gemm_wx_tc2(mh, ml, mx2, P, pro, epi, st);
     if (rc != -100) return rc;
   }
@@ -679,6 +697,7 @@ struct DwTcParams {
   GemmDwP g;
   int n_ob, n_cb, n_tiles;
   int skip_hi_store;
+  int mixed;           // 2-CTA kernel: tf32 leading term + bf16 cross terms instead of 3xTF32
 };
 
 // Stream-K over (tile, k-block) units: the grid is one CTA per SM and CTA i owns the contiguous unit range
@@ -978,6 +997,7 @@ int launch_gemm_dw_tc(const GemmDwP& p, int pro_b, cudaStream_t st) {
   P.n_cb = cdiv(p.N, DW_BN);
   P.n_tiles = P.n_ob * P.n_cb * p.n;
   P.skip_hi_store = (g_tc_flags & 1) ? 0 : 1;
+  P.mixed = 0;
   static int n_sm = 0;
   if (!n_sm) {
     int dev = 0;
@@ -1082,6 +1102,94 @@ __device__ __forceinline__ void tc_mma_tf32_2cta(uint32_t d_tmem, uint64_t adesc
       : "memory");
 }
 
+// ---- mixed-precision split product (2-CTA kernels): x.y = xt.yt + xl.yt + xt.yl with xt = tf32(x), xl = x - xt.
+// The leading term runs as kind::tf32 on the raw fp32 tiles (the tensor core truncates its inputs to tf32); the two
+// cross terms are 2^-11 of the product, so they run as kind::f16 on bf16 operands (bf16(x) for the big factor, bf16(xl)
+// for the small one: error 2^-9 . 2^-11 = 2^-20 relative, the same order as the dropped xl.yl term) at twice the tf32
+// rate and half the operand bytes.  One K = 16 slice costs 2 tf32 + 2 bf16 instructions = 4 time units instead of the 6 of
+// 3xTF32, at the same fp32-grade accuracy (measured rel. L2 ~1e-6) and the same shared-memory footprint:
+//   3xTF32 stage: [hi fp32][lo fp32]        mixed stage: [raw fp32][bf16(x) | bf16(x - tf32(x))]
+__device__ __forceinline__ void tc_mma_bf16_2cta(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// bf16 hi / lo of four fp32 values -> two 8-byte packets
+__device__ __forceinline__ void split_bf16_quad(const float4& v, uint2& bh, uint2& bl) {
+  const float lx = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u), ly = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+  const float lz = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u), lw = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+  uint32_t h0, h1, l0, l1;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;\n" : "=r"(h0) : "f"(v.y), "f"(v.x));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;\n" : "=r"(h1) : "f"(v.w), "f"(v.z));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;\n" : "=r"(l0) : "f"(ly), "f"(lx));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;\n" : "=r"(l1) : "f"(lw), "f"(lz));
+  bh = make_uint2(h0, h1);
+  bl = make_uint2(l0, l1);
+}
+// MN-major 16-bit operand, 128-byte swizzle: [MN atom of 64 elements][K atom of 8 rows][8 rows][128 B]; LBO = stride between
+// MN atoms (2048 B), SBO = stride between the two K atoms of a K = 16 instruction (1024 B)
+__device__ __forceinline__ uint64_t make_desc_mn16_sw128(uint32_t saddr) {
+  uint64_t d = (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(2048 >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// byte offset of 4 consecutive MN elements (mn % 4 == 0) at K row k of a [128 MN x 16 K] bf16 tile in that layout
+__device__ __host__ __forceinline__ uint32_t mn16_off(uint32_t mn, uint32_t k) {
+  const uint32_t row = k & 7u;
+  return (mn >> 6) * 2048u + (k >> 3) * 1024u + row * 128u + ((((mn & 63u) >> 3) ^ row) << 4) + (mn & 4u) * 2u;
+}
+// K-major 16-bit operand with rows of 16 elements (32 B), 32-byte swizzle: 8-row atoms of 256 B (SBO), 16-byte chunk ^= (row >> 2) & 1
+__device__ __forceinline__ uint64_t make_desc_k16_sw32(uint32_t saddr) {
+  uint64_t d = (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(256 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;
+  return d;
+}
+// D=f32, A=B=bf16, N=256, M=256 (cta_group::2): both MN-major (wx) / both K-major (dw)
+constexpr uint32_t T2_IDESC_BF16 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(256 >> 3) << 17) |
+                                   ((uint32_t)(256 >> 4) << 24);
+constexpr uint32_t D2_IDESC_BF16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+constexpr int TC_FLAG_NO_MIXED = 1024;   // set_tc_flags bit 10: 2-CTA kernels fall back to 3xTF32 (A/B timing, tests)
+
+// prep for the mixed mode: hi = tf32-truncated W pre-tiled as split_w_kernel does, img = per (128-channel block, 16-row K
+// block) an 8 KB shared-memory image [bf16(W) tile | bf16(W - tf32(W)) tile] in the MN-major layout above (ONE bulk copy
+// per stage); K rows >= Kd are zero
+__global__ void split_w_mixed_kernel(const float* __restrict__ W, int64_t ldw, int w_trans, int M, int Kd, float* __restrict__ hi,
+                                     uint8_t* __restrict__ img) {
+  const int KB = (Kd + 15) >> 4;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;        // over (o / 4, k padded)
+  const int total = (M >> 2) * KB * 16;
+  if (idx >= total) return;
+  const int o4 = idx % (M >> 2), k = idx / (M >> 2);
+  const int o = o4 * 4;
+  float w[4] = {0.f, 0.f, 0.f, 0.f};
+  if (k < Kd) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) w[i] = w_trans ? W[(int64_t)k * ldw + o + i] : W[(int64_t)(o + i) * ldw + k];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {                               // the fp32 (tf32 leading term) copy, [o / 32][k][32] tiling
+      const int oo = o + i;
+      hi[((int64_t)(oo >> 5) * Kd + k) * 32 + (oo & 31)] = __uint_as_float(__float_as_uint(w[i]) & 0xFFFFE000u);
+    }
+  }
+  uint2 bh, bl;
+  split_bf16_quad(make_float4(w[0], w[1], w[2], w[3]), bh, bl);
+  uint8_t* tile = img + ((int64_t)(o >> 7) * KB + (k >> 4)) * 8192;
+  const uint32_t off = mn16_off((uint32_t)(o & 127), (uint32_t)(k & 15));
+  *reinterpret_cast<uint2*>(tile + off) = bh;
+  *reinterpret_cast<uint2*>(tile + 4096 + off) = bl;
+}
+
 template <int PRO, int EPI, int NS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
     gemm_wx_tc2_kernel(const __grid_constant__ CUtensorMap map_whi, const __grid_constant__ CUtensorMap map_wlo,
@@ -1161,7 +1269,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           mbar_expect_tx(bar_full(s), T2_TX_BYTES);
           const int k0 = kb * TC_BK;
           tma_load_3d(sb + T2_OFF_WHI, &map_whi, bar_full(s), 0, k0, o0 >> 5);
-          tma_load_3d(sb + T2_OFF_WLO, &map_wlo, bar_full(s), 0, k0, o0 >> 5);
+          if (P.mixed) {      // [bf16(W) | bf16(W - tf32(W))] image of this (channel block, K block): one 8 KB bulk copy
+            const uint8_t* src = P.wimg + ((int64_t)(o0 >> 7) * KB + kb) * 8192;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(sb + T2_OFF_WLO),
+                         "l"(src), "r"(8192u), "r"(bar_full(s))
+                         : "memory");
+          } else {
+            tma_load_3d(sb + T2_OFF_WLO, &map_wlo, bar_full(s), 0, k0, o0 >> 5);
+          }
           tma_load_4d(sb + T2_OFF_XHI, &map_x2, bar_full(s), 0, k0, (t0 >> 5) + 4 * (int)rank, n);
         }
       }
@@ -1181,15 +1296,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
           mbar_wait(bar_ready(s), ph);
           tc_fence_after();
           const uint32_t sb = base + s * T2_STAGE_BYTES;
+          if (P.mixed) {
+            tc_mma_bf16_2cta(d_tmem, make_desc_mn16_sw128(sb + T2_OFF_WLO + 4096), make_desc_mn16_sw128(sb + T2_OFF_XLO), T2_IDESC_BF16,
+                             kb != 0 ? 1u : 0u);                                      // (W - tf32 W) . X
+            tc_mma_bf16_2cta(d_tmem, make_desc_mn16_sw128(sb + T2_OFF_WLO), make_desc_mn16_sw128(sb + T2_OFF_XLO + 4096), T2_IDESC_BF16,
+                             1u);                                                     // W . (X - tf32 X)
 #pragma unroll
-          for (int ks = 0; ks < TC_BK / 8; ++ks) {
-            const uint64_t a_hi = make_desc_mn_sw128(sb + T2_OFF_WHI + ks * 1024);
-            const uint64_t a_lo = make_desc_mn_sw128(sb + T2_OFF_WLO + ks * 1024);
-            const uint64_t b_hi = make_desc_mn_sw128(sb + T2_OFF_XHI + ks * 1024);
-            const uint64_t b_lo = make_desc_mn_sw128(sb + T2_OFF_XLO + ks * 1024);
-            tc_mma_tf32_2cta(d_tmem, a_lo, b_hi, T2_IDESC, (kb | ks) != 0 ? 1u : 0u);
-            tc_mma_tf32_2cta(d_tmem, a_hi, b_lo, T2_IDESC, 1u);
-            tc_mma_tf32_2cta(d_tmem, a_hi, b_hi, T2_IDESC, 1u);
+            for (int ks = 0; ks < TC_BK / 8; ++ks)                                    // tf32 W . tf32 X
+              tc_mma_tf32_2cta(d_tmem, make_desc_mn_sw128(sb + T2_OFF_WHI + ks * 1024), make_desc_mn_sw128(sb + T2_OFF_XHI + ks * 1024),
+                               T2_IDESC, 1u);
+          } else {
+#pragma unroll
+            for (int ks = 0; ks < TC_BK / 8; ++ks) {
+              const uint64_t a_hi = make_desc_mn_sw128(sb + T2_OFF_WHI + ks * 1024);
+              const uint64_t a_lo = make_desc_mn_sw128(sb + T2_OFF_WLO + ks * 1024);
+              const uint64_t b_hi = make_desc_mn_sw128(sb + T2_OFF_XHI + ks * 1024);
+              const uint64_t b_lo = make_desc_mn_sw128(sb + T2_OFF_XLO + ks * 1024);
+              tc_mma_tf32_2cta(d_tmem, a_lo, b_hi, T2_IDESC, (kb | ks) != 0 ? 1u : 0u);
+              tc_mma_tf32_2cta(d_tmem, a_hi, b_lo, T2_IDESC, 1u);
+              tc_mma_tf32_2cta(d_tmem, a_hi, b_hi, T2_IDESC, 1u);
+            }
           }
           tc_commit_mc2(bar_empty(s));   // frees stage s in BOTH CTAs
         }
@@ -1248,13 +1374,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
               v.z = fmaf(c, prelu_f(v.z, alpha), d); v.w = fmaf(c, prelu_f(v.w, alpha), d);
             }
           }
-          float4 h, l;
-          h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
-          h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
-          h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
-          h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
-          if (PRO != 0 || !P.skip_hi_store) *reinterpret_cast<float4*>(xs_hi + off) = h;
-          *reinterpret_cast<float4*>(xs_lo + off) = l;
+          if (P.mixed) {
+            // raw tile: 4 boxes (32 frames each) x [16 K rows x 128 B], 32-byte granules XORed with (k & 3): recover the
+            // logical (k, t) of this float4 and drop its bf16 hi / lo packets into the MN-major 16-bit tiles
+            const uint32_t k = ((uint32_t)off >> 7) & 15u, c16 = ((uint32_t)off >> 4) & 7u;
+            const uint32_t tt = ((uint32_t)off >> 11) * 32u + ((((c16 >> 1) ^ (k & 3u)) << 3) | ((c16 & 1u) << 2));
+            uint2 bh, bl;
+            split_bf16_quad(v, bh, bl);
+            const uint32_t o16 = mn16_off(tt, k);
+            if (PRO != 0) *reinterpret_cast<float4*>(xs_hi + off) = v;      // the tensor core truncates to tf32 itself
+            *reinterpret_cast<uint2*>(xs_lo + o16) = bh;
+            *reinterpret_cast<uint2*>(xs_lo + 4096 + o16) = bl;
+          } else {
+            float4 h, l;
+            h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+            h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+            h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+            h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+            if (PRO != 0 || !P.skip_hi_store) *reinterpret_cast<float4*>(xs_hi + off) = h;
+            *reinterpret_cast<float4*>(xs_lo + off) = l;
+          }
         }
         fence_proxy_async();
         __syncwarp();
@@ -1539,11 +1678,13 @@ static int launch_tc2_t(const CUtensorMap& mh, const CUtensorMap& ml, const CUte
   return 0;
 }
 
+bool gemm_wx_tc2_instantiated(int pro, int epi) {
+  return (pro == 0 && (epi == 0 || epi == 1 || epi == 2 || epi == 3 || epi == 10)) || (pro == 2 && epi == 2) || (pro == 3 && epi == 0);
+}
+
 int launch_gemm_wx_tc2(const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& mx, TcParams P, int pro, int epi,
                        cudaStream_t st) {
-  if (!((pro == 0 && (epi == 0 || epi == 1 || epi == 2 || epi == 3 || epi == 10)) || (pro == 2 && epi == 2) ||
-        (pro == 3 && epi == 0)))
-    return -100;                                // not instantiated: caller falls back to the 1-CTA kernel
+  if (!gemm_wx_tc2_instantiated(pro, epi)) return -100;   // caller falls back to the 1-CTA kernel
   if (t2_stages(pro, epi) % P.xf_groups) P.xf_groups = 2;   // must divide the ring depth (see launch_gemm_wx_tc)
   P.n_ob = P.g.M / 256;                       // channel PAIRS
   P.n_tiles = P.n_ob * P.n_tt * P.g.n;
@@ -1689,15 +1830,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DW_THREADS, 1)
           mbar_wait(bar_ready(s), ph);
           tc_fence_after();
           const uint32_t sb = base + s * D2_STAGE_BYTES;
+          if (P.mixed) {      // [bf16(x) | bf16(x - tf32 x)] tiles of 128 rows x 32 B sit where the fp32 lo tile was
+            tc_mma_bf16_2cta(d_tmem, make_desc_k16_sw32(sb + D2_OFF_ALO + 4096), make_desc_k16_sw32(sb + D2_OFF_BLO), D2_IDESC_BF16,
+                             kb != kb_lo ? 1u : 0u);
+            tc_mma_bf16_2cta(d_tmem, make_desc_k16_sw32(sb + D2_OFF_ALO), make_desc_k16_sw32(sb + D2_OFF_BLO + 4096), D2_IDESC_BF16, 1u);
 #pragma unroll
-          for (int ks = 0; ks < DW_BK / 8; ++ks) {
-            const uint64_t a_hi = make_desc_k_sw64(sb + D2_OFF_AHI + ks * 32);
-            const uint64_t a_lo = make_desc_k_sw64(sb + D2_OFF_ALO + ks * 32);
-            const uint64_t b_hi = make_desc_k_sw64(sb + D2_OFF_BHI + ks * 32);
-            const uint64_t b_lo = make_desc_k_sw64(sb + D2_OFF_BLO + ks * 32);
-            tc_mma_tf32_2cta(d_tmem, a_lo, b_hi, D2_IDESC, (kb != kb_lo || ks != 0) ? 1u : 0u);
-            tc_mma_tf32_2cta(d_tmem, a_hi, b_lo, D2_IDESC, 1u);
-            tc_mma_tf32_2cta(d_tmem, a_hi, b_hi, D2_IDESC, 1u);
+            for (int ks = 0; ks < DW_BK / 8; ++ks)
+              tc_mma_tf32_2cta(d_tmem, make_desc_k_sw64(sb + D2_OFF_AHI + ks * 32), make_desc_k_sw64(sb + D2_OFF_BHI + ks * 32), D2_IDESC, 1u);
+          } else {
+#pragma unroll
+            for (int ks = 0; ks < DW_BK / 8; ++ks) {
+              const uint64_t a_hi = make_desc_k_sw64(sb + D2_OFF_AHI + ks * 32);
+              const uint64_t a_lo = make_desc_k_sw64(sb + D2_OFF_ALO + ks * 32);
+              const uint64_t b_hi = make_desc_k_sw64(sb + D2_OFF_BHI + ks * 32);
+              const uint64_t b_lo = make_desc_k_sw64(sb + D2_OFF_BLO + ks * 32);
+              tc_mma_tf32_2cta(d_tmem, a_lo, b_hi, D2_IDESC, (kb != kb_lo || ks != 0) ? 1u : 0u);
+              tc_mma_tf32_2cta(d_tmem, a_hi, b_lo, D2_IDESC, 1u);
+              tc_mma_tf32_2cta(d_tmem, a_hi, b_hi, D2_IDESC, 1u);
+            }
           }
           tc_commit_mc2(bar_empty(s));   // frees stage s in BOTH CTAs
         }
@@ -1790,13 +1940,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DW_THREADS, 1)
             v.z = prelu_f(fmaf(c_, v.z, d_), alpha); v.w = prelu_f(fmaf(c_, v.w, d_), alpha);
           }
         }
-        float4 h, l;
-        h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
-        h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
-        h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
-        h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
-        if (!P.skip_hi_store || (PRO_B >= 1 && is_b)) *reinterpret_cast<float4*>(hi_p) = h;
-        *reinterpret_cast<float4*>(lo_p) = l;
+        if (P.mixed) {
+          // raw K-major tile: rows of 64 B, 16-byte chunk XORed with (row >> 1) & 3 -> logical K offset of this float4; the
+          // bf16 tiles have rows of 32 B with the 32-byte swizzle (chunk ^= (row >> 2) & 1)
+          const uint32_t r = (uint32_t)off >> 6, lc = (((uint32_t)off >> 4) & 3u) ^ ((r >> 1) & 3u);
+          const uint32_t o16 = r * 32u + (((lc >> 1) ^ ((r >> 2) & 1u)) << 4) + (lc & 1u) * 8u;
+          uint8_t* t16 = st + (is_b ? D2_OFF_BLO : D2_OFF_ALO);
+          uint2 bh, bl;
+          split_bf16_quad(v, bh, bl);
+          if (PRO_B >= 1 && is_b) *reinterpret_cast<float4*>(hi_p) = v;   // the tensor core truncates to tf32 itself
+          *reinterpret_cast<uint2*>(t16 + o16) = bh;
+          *reinterpret_cast<uint2*>(t16 + 4096 + o16) = bl;
+        } else {
+          float4 h, l;
+          h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+          h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+          h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+          h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+          if (!P.skip_hi_store || (PRO_B >= 1 && is_b)) *reinterpret_cast<float4*>(hi_p) = h;
+          *reinterpret_cast<float4*>(lo_p) = l;
+        }
       }
       fence_proxy_async();
       __syncwarp();
@@ -1875,6 +2038,7 @@ int launch_gemm_dw_tc2(const GemmDwP& p, int pro_b, cudaStream_t st) {
   P.n_cb = cdiv(p.N, 256);
   P.n_tiles = P.n_ob * P.n_cb * p.n;
   P.skip_hi_store = (g_tc_flags & 1) ? 0 : 1;
+  P.mixed = (g_tc_flags & 1024) ? 0 : 1;   // tf32 leading term + bf16 cross terms (default)
   static int n_sm = 0;
   if (!n_sm) {
     int dev = 0;

@@ -436,6 +436,8 @@ class DecoderMasksFn(torch.autograd.Function):
             raise RuntimeError("decoder masks: encoder output / mask width mismatch")
         m = new_act(n, M, T, e.device)
         S = conv1x1_raw(e, Wc, False, M, bias=bc, epi=3, R=w_cat, Y2=m)
+        if DEBUG_STASH is not None:
+            DEBUG_STASH.update(decoder_m=m)
         ctx.wshapes = [w.shape for w in ws]
         ctx.save_for_backward(e, w_cat, Wc, m)
         return S
