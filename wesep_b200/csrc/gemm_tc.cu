@@ -596,7 +596,9 @@ int launch_gemm_wx_tc(const GemmWxP& p, bool a_trans, int pro, int epi, void* ws
   float* wlo = whi + (size_t)M32 * p.Kd;
   // the 2-CTA kernel runs the mixed tf32 + bf16 split product (its weight operand is prepared differently)
   const bool use2 = gemm_wx_tc2_eligible(p, pro, epi) && gemm_wx_tc2_instantiated(pro, epi);
-  const bool mixed = use2 && !(g_tc_flags & 1024);
+  // (measured, profiles/r02_*: with an operand prologue (PRO >= 2: gLN-apply + PReLU, result stored back as the tf32 operand) the
+  // transform warps of the 4-stage ring become the critical path and the mixed mode is 18 % slower than 3xTF32 there)
+  const bool mixed = use2 && pro < 2 && !(g_tc_flags & 1024);
   if (!p.ws_presplit) {   // loops that reuse one weight split it once and set ws_presplit
     if (mixed) {
       const int total = (p.M >> 2) * (((p.Kd + 15) >> 4) * 16);
