@@ -355,8 +355,11 @@ def run_pbsrnn(args, rank, world, dev, pk, barrier):
         launches = graphed.launches_per_step * args.steps
     ms_e2e, _, loss_e2e = time_steps(lambda: step(host, True), 1, args.steps, barrier, world, dev)
     if rank != 0:
+        step(resident, False)          # the CUPTI pass below is one more COLLECTIVE step: every rank takes part
+        barrier()
         return None
     agg, tot = kernel_shares(lambda: step(resident, False))
+    barrier()
     rec = {k: v for k, v in agg.items() if "lstm_rec" in k}
     rec_us = sum(v[1] for v in rec.values())
     rec_n = sum(v[0] for v in rec.values())
@@ -447,6 +450,8 @@ def run_ours(args, rank, world, local):
     value = n * world * args.steps / (ms_res * 1e-3)
     e2e = n * world * args.steps / (ms_e2e * 1e-3)
     roof = None
+    if rank != 0:
+        one(resident, False)           # the CUPTI pass of rank 0 is one more COLLECTIVE step: every rank takes part
     if rank == 0:
         agg, tot = kernel_shares(lambda: one(resident, False))
         roof = pick_roofline(agg, tot, SPEX_KERNELS, n, pk, 3,
@@ -461,6 +466,7 @@ def run_ours(args, rank, world, local):
                                      "copy bandwidth - the binding roofline of the Spex+ step")
             roof["top_kernels"] = [dict(kernel=k[:70], share=v[1] / tot, count=v[0])
                                    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:6]]
+    barrier()
     # free the Spex+ state before the second model
     del model, opt, reducer, resident, graphed
     torch.cuda.empty_cache()

@@ -18,7 +18,9 @@ def init_from_env(backend=None):
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
             torch.cuda.set_device(local)
-        dist.init_process_group(backend=backend)
+        # a mismatched collective must fail fast (default watchdog: 10 min of a box's GPU time per hang)
+        import datetime
+        dist.init_process_group(backend=backend, timeout=datetime.timedelta(seconds=int(os.environ.get("WESEP_DIST_TIMEOUT_S", "180"))))
     return rank, world, local
 
 
