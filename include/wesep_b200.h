@@ -45,8 +45,10 @@ int wesep_b200_set_gemm_backend(int backend);
  * ignores the 13 low mantissa bits of tf32 inputs — measured identical results — so the raw tile serves as hi).
  * bit 1: disable the 2-CTA (cta_group::2) GEMM variants.  bits 2-3: transform-warp groups (0 = default 2, 1 = one group, 2 = two, 3 = four; clamped so it divides the ring depth).
  * bits 4-7: timing experiments on the 2-CTA conv GEMM (16 no epilogue loads, 32 no epilogue stores, 64 no operand
- * transform, 128 single store box) — results are WRONG with 16/32/64 set.  bit 8 (256): force the balanced stream-K
- * split in the weight-gradient GEMMs.  bit 9 (512): weight-gradient GEMMs on the 1-CTA kernel. */
+ * transform, 128 single store box) — results are WRONG with 16/32/64 set: those three are compiled out of release builds
+ * (-DWESEP_TC_DEBUG enables them; otherwise the call returns -2).  bit 8 (256): force the balanced stream-K split in the
+ * weight-gradient GEMMs.  bit 9 (512): weight-gradient GEMMs on the 1-CTA kernel.  bit 10 (1024): 2-CTA kernels in 3xTF32
+ * instead of the mixed tf32 + bf16 split product (A/B timing, tests). */
 int wesep_b200_set_tc_flags(int flags);
 /* Workspace bytes the tcgen05 GEMM needs for an [M x Kd] weight (split hi/lo copies). */
 int64_t wesep_b200_gemm_ws_bytes(int M, int Kd);

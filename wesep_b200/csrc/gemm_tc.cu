@@ -169,6 +169,17 @@ struct TcParams {
 };
 int g_tc_flags = 0;
 
+// SM count of the CURRENT device (a process may drive several devices: no single function-static value)
+static int sm_count(int* out) {
+  static int cache[64] = {0};
+  int dev = 0;
+  WB_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail(-3, "device index out of range");
+  if (!cache[dev]) WB_CUDA(cudaDeviceGetAttribute(&cache[dev], cudaDevAttrMultiProcessorCount, dev));
+  *out = cache[dev];
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------ main kernel
 template <int PRO, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -568,12 +579,8 @@ template <int PRO, int EPI>
 static int launch_tc_t(const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& mx, const TcParams& P, cudaStream_t st) {
   auto k = gemm_wx_tc_kernel<PRO, EPI>;
   WB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-  static int n_sm = 0;
-  if (!n_sm) {
-    int dev = 0;
-    WB_CUDA(cudaGetDevice(&dev));
-    WB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-  }
+  int n_sm = 0;
+  if (int rc = sm_count(&n_sm)) return rc;     // per current device (cached per device index)
   int grid = P.n_tiles < n_sm ? P.n_tiles : n_sm;
   k<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mh, ml, mx, P);
   WB_LAUNCH_CHECK("gemm_wx_tc");
@@ -639,7 +646,11 @@ int launch_gemm_wx_tc(const GemmWxP& p, bool a_trans, int pro, int epi, void* ws
   {
     const int sel = (g_tc_flags >> 2) & 3;
     P.xf_groups = sel == 1 ? 1 : sel == 3 ? 4 : 2;
+#ifdef WESEP_TC_DEBUG   // the wrong-result timing switches (bits 4-6) exist in debug builds only
     P.dbg = (g_tc_flags >> 4) & 15;
+#else
+    P.dbg = (g_tc_flags >> 4) & 8;    // release: only 'single store box' (correct results) is reachable
+#endif
   }
   P.mixed = mixed ? 1 : 0;
   P.wimg = reinterpret_cast<const uint8_t*>(wlo);
@@ -661,6 +672,9 @@ int launch_gemm_wx_tc(const GemmWxP& p, bool a_trans, int pro, int epi, void* ws
 }  // namespace wb
 
 extern "C" int wesep_b200_set_tc_flags(int flags) {
+#ifndef WESEP_TC_DEBUG
+  if (flags & (16 | 32 | 64)) return wb::fail(-2, "set_tc_flags: bits 4-6 (timing experiments with wrong results) need a -DWESEP_TC_DEBUG build");
+#endif
   wb::g_tc_flags = flags;
   return 0;
 }
@@ -1000,12 +1014,8 @@ int launch_gemm_dw_tc(const GemmDwP& p, int pro_b, cudaStream_t st) {
   P.n_tiles = P.n_ob * P.n_cb * p.n;
   P.skip_hi_store = (g_tc_flags & 1) ? 0 : 1;
   P.mixed = 0;
-  static int n_sm = 0;
-  if (!n_sm) {
-    int dev = 0;
-    WB_CUDA(cudaGetDevice(&dev));
-    WB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-  }
+  int n_sm = 0;
+  if (int rc = sm_count(&n_sm)) return rc;     // per current device (cached per device index)
   // stream-K grid: one CTA per SM, but never fewer than 8 k-blocks per CTA
   const int64_t units = (int64_t)P.n_tiles * cdiv(p.T, DW_BK);
   int grid = n_sm;
@@ -1668,12 +1678,8 @@ static int launch_tc2_t(const CUtensorMap& mh, const CUtensorMap& ml, const CUte
   static_assert((3 * NS + 4 + 8 * T2_NL) * 8 + 4 <= T2_BAR_BYTES, "barrier area too small");
   auto k = gemm_wx_tc2_kernel<PRO, EPI, NS>;
   WB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-  static int n_sm = 0;
-  if (!n_sm) {
-    int dev = 0;
-    WB_CUDA(cudaGetDevice(&dev));
-    WB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-  }
+  int n_sm = 0;
+  if (int rc = sm_count(&n_sm)) return rc;     // per current device (cached per device index)
   int clusters = P.n_tiles < n_sm / 2 ? P.n_tiles : n_sm / 2;
   k<<<2 * clusters, TC_THREADS, SMEM, st>>>(mh, ml, mx, my, mr, my2, P);
   WB_LAUNCH_CHECK("gemm_wx_tc2");
@@ -2041,12 +2047,8 @@ int launch_gemm_dw_tc2(const GemmDwP& p, int pro_b, cudaStream_t st) {
   P.n_tiles = P.n_ob * P.n_cb * p.n;
   P.skip_hi_store = (g_tc_flags & 1) ? 0 : 1;
   P.mixed = (g_tc_flags & 1024) ? 0 : 1;   // tf32 leading term + bf16 cross terms (default)
-  static int n_sm = 0;
-  if (!n_sm) {
-    int dev = 0;
-    WB_CUDA(cudaGetDevice(&dev));
-    WB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-  }
+  int n_sm = 0;
+  if (int rc = sm_count(&n_sm)) return rc;     // per current device (cached per device index)
   const int max_clusters = n_sm / 2;
   const int64_t units = (int64_t)P.n_tiles * cdiv(p.T, DW_BK);
   int clusters = max_clusters;

@@ -195,6 +195,7 @@ extern "C" int wesep_b200_bn_act_pool_fwd(const WesepBnActPoolFwdArgs* a, void* 
   if (a->n <= 0 || a->C <= 0 || a->T <= 0 || !(a->pool == 1 || a->pool == 3)) return fail(-1, "bn_act_pool_fwd: bad shape");
   const int Tp = a->pool == 3 ? a->T / 3 : a->T;
   if (Tp <= 0) return fail(-1, "bn_act_pool_fwd: sequence shorter than the pooling window");
+  if ((int64_t)a->n * a->C > 65535) return fail(-2, "bn_act_pool_fwd: n * C exceeds 65535 (gridDim.y): split the batch");
   bn_act_pool_fwd_kernel<<<dim3(cdiv(Tp, 256), a->n * a->C), 256, 0, (cudaStream_t)stream>>>(*a);
   WB_LAUNCH_CHECK("bn_act_pool_fwd");
   return 0;
@@ -203,6 +204,7 @@ extern "C" int wesep_b200_bn_act_pool_bwd(const WesepBnActPoolBwdArgs* a, void* 
   if (a->n <= 0 || a->C <= 0 || a->T <= 0 || !(a->pool == 1 || a->pool == 3)) return fail(-1, "bn_act_pool_bwd: bad shape");
   const int Tp = a->pool == 3 ? a->T / 3 : a->T;
   const int slices = cdiv(Tp, 2048);   // <= 8 passes of 256 pooled frames per CTA
+  if ((int64_t)a->n * a->C > 65535) return fail(-2, "bn_act_pool_bwd: n * C exceeds 65535 (gridDim.y): split the batch");
   bn_act_pool_bwd_kernel<<<dim3(slices, a->n * a->C), 256, 0, (cudaStream_t)stream>>>(*a);
   WB_LAUNCH_CHECK("bn_act_pool_bwd");
   return 0;
@@ -210,6 +212,7 @@ extern "C" int wesep_b200_bn_act_pool_bwd(const WesepBnActPoolBwdArgs* a, void* 
 extern "C" int wesep_b200_bn_bwd(const WesepBnBwdArgs* a, void* stream) {
   if ((a->ldgv & 3) || (a->ldx & 3) || (a->lddx & 3) || !aligned16(a->gv) || !aligned16(a->x) || !aligned16(a->dx))
     return fail(-1, "bn_bwd: alignment");
+  if ((int64_t)a->n * a->C > 65535) return fail(-2, "bn_bwd: n * C exceeds 65535 (gridDim.y): split the batch");
   bn_bwd_kernel<<<dim3(cdiv(a->T, 1024), a->n * a->C), 256, 0, (cudaStream_t)stream>>>(*a);
   WB_LAUNCH_CHECK("bn_bwd");
   return 0;
