@@ -505,6 +505,94 @@ typedef struct {
 int wesep_b200_mask_apply_fwd(const WesepMaskApplyArgs* a, void* stream);
 int wesep_b200_mask_apply_bwd(const WesepMaskApplyArgs* a, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Evaluation scoring: replaces the per-utterance numpy path of wesep/bin/infer.py:124-129
+ * (peak rule: if every row of the batch has a positive sample, est = est / max|est| * 0.9 per row) and
+ * wesep/utils/score.py:7-36 (cal_SISNR / cal_SISNRi) for a whole batch in three launches.
+ *   sisnr[r]  = 20 log10(eps + |t| / (|x~ - t| + eps)),  t = <x~,r~> r~ / (|r~|^2 + eps), zero-mean, eps = 1e-8
+ *   sisnri[r] = sisnr(est_r, ref_r) - sisnr(mix_r, ref_r)
+ * Moments are taken over the first len[r] samples (infer.py:147-152 trims the three waves to the shortest);
+ * the peak search and the scaling run over all L samples of est, as the reference does before trimming.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int n;                 /* rows (<= 65535) */
+  int L;                 /* samples per row */
+  const int* len;        /* [n] valid samples per row for the scores, or NULL = L */
+  float* est;            /* [n][ld_est] separated waves; scaled IN PLACE when the peak rule fires */
+  int64_t ld_est;
+  const float* ref;      /* [n][ld_ref] clean targets */
+  int64_t ld_ref;
+  const float* mix;      /* [n][ld_mix] mixtures */
+  int64_t ld_mix;
+  int peak_norm;         /* 0: leave est untouched */
+  double* ws;            /* workspace, wesep_b200_score_ws_bytes(n) bytes; zeroed by the call */
+  float* sisnr;          /* out [n] dB */
+  float* sisnri;         /* out [n] dB */
+  int* normed;           /* out [1] 1 if the peak rule fired (may be NULL) */
+} WesepScoreArgs;
+int64_t wesep_b200_score_ws_bytes(int n);
+int wesep_b200_score(const WesepScoreArgs* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Device-side data front end.
+ *
+ * wesep_b200_mix: random_chunk + snr_mixer for M mixtures of S speakers in three streaming launches
+ * (wesep/dataset/processor.py:536-573 get_random_chunk with host-drawn offsets; processor.py:276-320 snr_mixer):
+ *   chunk_s[j] = utt_s[chunk0 + j]            (utterance >= T samples)   |   utt_s[j mod ulen]   (shorter: tiled)
+ *   v_0 = chunk_0;  v_s = chunk_s * sqrt(E_0 / E_s) * 10^(snr_s / 20);  mix = v_0 + v_1 + ...
+ *   everything * 1 / max(max|mix|, max_s max|v_s|)          (left unscaled if that maximum is 0)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int M;                 /* mixtures (<= 65535) */
+  int S;                 /* speakers per mixture, 1..4; speaker 0 is the target of the energy match */
+  int T;                 /* chunk length in samples */
+  const float* pool;     /* source utterances, back to back */
+  const int64_t* start;  /* [M][S] index in pool of sample 0 of each utterance */
+  const int* ulen;       /* [M][S] utterance lengths (> 0) */
+  const int* chunk0;     /* [M][S] chunk start inside the utterance (ignored when ulen < T) */
+  const float* snr_db;   /* [M][S] SNR of speaker s against speaker 0 in dB (entry 0 unused), or NULL = 0 dB */
+  float* mix;            /* out [M][ld] */
+  float* spk;            /* out [S][M][ld] the scaled sources (wav_spk1.. of the reference sample) */
+  int64_t ld;
+  double* ws;            /* workspace, wesep_b200_mix_ws_bytes(M) bytes; zeroed by the call */
+} WesepMixArgs;
+int64_t wesep_b200_mix_ws_bytes(int M);
+int wesep_b200_mix(const WesepMixArgs* a, void* stream);
+
+/* wesep_b200_fbank: compute_fbank + apply_cmvn of the enrollment waves (processor.py:480-535), i.e.
+ * torchaudio.compliance.kaldi.fbank(wave * 2^15, num_mel_bins, frame_length 25 ms, frame_shift 10 ms, dither,
+ * window_type "hamming", use_energy False) with its defaults (snip_edges, remove_dc_offset, pre-emphasis 0.97,
+ * round_to_power_of_two, power spectrum, log) followed by the subtraction of the per-utterance mean over frames.
+ * Frames of row r: 1 + (len[r] - frame_len) / frame_shift (0 if shorter than one frame); rows of `out` past that
+ * are zero (the "max" collate mode pads with zeros, wesep/dataset/dataset.py:229-245).  The window and the mel
+ * filterbank are small host-built tables (fp32, as torchaudio builds them). */
+typedef struct {
+  int n;                 /* utterances (<= 65535) */
+  int T;                 /* samples per row of wav */
+  const float* wav;      /* [n][ld_wav] */
+  int64_t ld_wav;
+  const int* len;        /* [n] valid samples per row, or NULL = T */
+  int frame_len;         /* 400 */
+  int frame_shift;       /* 160 */
+  int n_fft;             /* 512 (the only size built) */
+  int num_mel;           /* 80 */
+  float scale;           /* 32768 */
+  float dither;          /* std of the white noise added to every frame sample; 0 = none */
+  uint64_t seed;         /* dither stream */
+  float preemph;         /* 0.97 */
+  int remove_dc;         /* 1 */
+  const float* window;   /* [frame_len] */
+  const float* mel;      /* [num_mel][n_fft/2+1] triangular weights */
+  const int* mel_lo;     /* [num_mel] first non-zero bin */
+  const int* mel_hi;     /* [num_mel] one past the last non-zero bin */
+  float log_floor;       /* fp32 epsilon */
+  float* out;            /* [n][bs_out] = [n][max_frames][num_mel] */
+  int64_t bs_out;
+  int max_frames;
+  int cmn;               /* 1: subtract the per-utterance mean over frames */
+} WesepFbankArgs;
+int wesep_b200_fbank(const WesepFbankArgs* a, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -63,7 +63,10 @@ def run_fixture(name, check_grads=True):
                 assert gn <= 1e-3 and ref <= 1e-3, (name, k, gn, ref)
                 continue
             tn = 5e-2 if p.numel() <= 4 else tol_n     # scalar PReLU slopes: |sum of +/- terms|, fp32-noisy on both sides
-            assert abs(gn - ref) <= tn * ref + 3e-4, (name, k, gn, ref)
+            # scalar slopes: a sum of ~1e6 terms of either sign that cancels to ~2e-3; the two fp32 runs differ by up to
+            # ~5e-4 there (measured 4.5e-4 on spk_model.aux_enc3.2.prelu1.weight at 4 s), hence the larger absolute floor
+            floor = 1e-3 if p.numel() <= 4 else 3e-4
+            assert abs(gn - ref) <= tn * ref + floor, (name, k, gn, ref)
             if ("g/" + k) in z and p.numel() > 4:
                 g = torch.from_numpy(z["g/" + k]).to(DEV)
                 e = float((p.grad - g).double().norm() / (g.double().norm() + 1e-3))
