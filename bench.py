@@ -456,9 +456,11 @@ def run_ours(args, rank, world, local):
         agg, tot = kernel_shares(lambda: one(resident, False))
         roof = pick_roofline(agg, tot, SPEX_KERNELS, n, pk, 3,
                              "kernel with the largest share of one timed step (CUPTI pass inside this run); achieved = executed "
-                             "tensor flops (3 x algorithmic: 3xTF32 split, fp32-grade) / its average duration INSIDE the step / "
-                             "measured sustained bf16 peak (%s); kind::tf32 runs at half the bf16 rate, so 0.5 is this mode's "
-                             "ceiling; traffic: see profiles/ (ncu dram bytes ~ algorithmic bytes)" % pk["src"])
+                             "tensor flops (3 x algorithmic: fp32-grade split products) / its average duration INSIDE the step / "
+                             "measured sustained bf16 peak (%s); kernels without a per-channel prologue (<0, *, *>) run the mixed "
+                             "split = one kind::tf32 product (half the bf16 rate) + two bf16 cross terms = 3 products in 4 "
+                             "bf16-time units, ceiling 0.75; the <2|3, *, *> kernels run 3xTF32, ceiling 0.5; traffic: see "
+                             "profiles/ (ncu dram bytes ~ algorithmic bytes)" % pk["src"])
         if roof is not None:
             step_gbs = SPEX_BYTES_PER_ROW * n * args.steps / (ms_res * 1e-3) / 1e9
             roof["step"] = dict(bound="hbm", achieved=step_gbs, peak=pk["hbm"], unit="GB/s", frac=step_gbs / pk["hbm"],
@@ -494,7 +496,8 @@ def run_ours(args, rank, world, local):
         config=dict(workload="Spex+ (ConvTasNet, examples/librimix/tse/v2/confs/spexplus.yaml) full train step, "
                              "4s@16kHz, %d model rows per GPU" % n,
                     rows_per_gpu=n, global_rows=n * world, samples=T_SAMPLES, parallelism="dp%d" % world,
-                    gemm_mode="3xTF32 split (fp32-grade); tcgen05.mma kind::tf32 cta_group::2 + TMA + TMEM GEMMs, mma.sync for odd shapes",
+                    gemm_mode="fp32-grade split products on tcgen05 (cta_group::2, TMA, TMEM): tf32 hi*hi + 2 bf16 cross terms (mixed), "
+                              "3xTF32 where a per-channel prologue rewrites the operand; mma.sync for odd shapes",
                     l2="inputs and activations >> L2 (126 MB)",
                     loss="0.8/0.1/0.1 SI-SDR + 0.5 CE", optimizer="per-tensor clip 5.0 + Adam(wd 1e-4), exp-decay lr",
                     launch="one CUDA-graph replay per step" if args.cuda_graph else "eager (one launch per kernel)"),

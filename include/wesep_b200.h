@@ -419,6 +419,7 @@ typedef struct {
                                            subsample: [n][C][ldc], bsc = C ldc) */
   const float* x; float* col;           /* fwd */
   const float* gcol; float* gx;         /* bwd */
+  int stride_w;                         /* im2col only: stride along W when it differs from `stride` (DPCCN: (1, 2)); 0 = same */
 } WesepIm2colArgs;
 int wesep_b200_im2col3x3_fwd(const WesepIm2colArgs* a, void* stream);
 int wesep_b200_im2col3x3_bwd(const WesepIm2colArgs* a, void* stream);
@@ -592,6 +593,62 @@ typedef struct {
   int cmn;               /* 1: subtract the per-utterance mean over frames */
 } WesepFbankArgs;
 int wesep_b200_fbank(const WesepFbankArgs* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * pDPCCN building blocks (wesep/models/dpccn.py:206-290, wesep/modules/dpccn/convs.py:28-152).
+ * Feature maps are act tensors [n][C][T*F] (F contiguous = the reference's NCHW maps); the 3x3 convolutions and
+ * transposed convolutions are wesep_b200_im2col3x3_{fwd,bwd} (stride (1, 2)) around wesep_b200_conv1x1.
+ * ---------------------------------------------------------------------------------------------- */
+/* mode 0: y = InstanceNorm(ELU(x)) (Conv2dBlock / ConvTrans2dBlock, convs.py:44-47,66-69);
+ * mode 1: y = ELU(InstanceNorm(x)) (TCNBlock, convs.py:144,148).  Per row (one (n, c) plane), biased variance, eps 1e-5, no affine. */
+typedef struct {
+  int64_t rows; int L; int64_t ld;     /* rows = n * C planes of L valid samples, ld floats apart */
+  int mode; float eps;
+  const float* x; float* y;
+  double* stats;                       /* workspace [rows][2], zeroed by the call */
+  float* mr;                           /* [rows][2] (mean, rstd): written by fwd, read by bwd */
+  const float* gy; float* gx;          /* bwd */
+} WesepEluInArgs;
+int wesep_b200_elu_in_fwd(const WesepEluInArgs* a, void* stream);
+int wesep_b200_elu_in_bwd(const WesepEluInArgs* a, void* stream);
+
+/* depthwise Conv1d(C, C, 3, padding = dil, dilation = dil, groups = C) of TCNBlock (convs.py:122-131) */
+typedef struct {
+  int n, C, L; int64_t ld; int dil;
+  const float* x; const float* w; const float* b;   /* w [C][3], b [C] or NULL */
+  float* y;
+  const float* gy; float* gx; float* gw; float* gb; /* bwd: gw [C][3], gb [C] (or NULL) zeroed by the call */
+} WesepDwConv1dArgs;
+int wesep_b200_dwconv1d_fwd(const WesepDwConv1dArgs* a, void* stream);
+int wesep_b200_dwconv1d_bwd(const WesepDwConv1dArgs* a, void* stream);
+
+/* nn.AvgPool2d(k) on [rows][H*W] planes: Ho = H / k, Wo = W / k (floor; the remainder is dropped) — dpccn.py:196-204 */
+typedef struct {
+  int64_t rows; int H, W, k, Ho, Wo; int64_t ldx, ldy;
+  const float* x; float* y;
+  const float* gy; float* gx;
+} WesepPool2dArgs;
+int wesep_b200_avgpool2d_fwd(const WesepPool2dArgs* a, void* stream);
+int wesep_b200_avgpool2d_bwd(const WesepPool2dArgs* a, void* stream);
+
+/* nn.Upsample(size=(Ho, Wo), mode="bilinear") (align_corners False) — dpccn.py:262-265 */
+typedef struct {
+  int64_t rows; int Hi, Wi, Ho, Wo; int64_t ldi, ldo;
+  const float* x; float* y;
+  const float* gy; float* gx;          /* bwd: gx zeroed by the call */
+} WesepUpsample2dArgs;
+int wesep_b200_upsample2d_fwd(const WesepUpsample2dArgs* a, void* stream);
+int wesep_b200_upsample2d_bwd(const WesepUpsample2dArgs* a, void* stream);
+
+/* 4-D "multiply" speaker fusion (wesep/modules/common/speaker.py:117-121 as called at dpccn.py:240):
+ * y[n][c][t*F + f] = x[n][c][t*F + f] * s[n][f];  bwd: gx = gy * s, gs[n][f] = sum over (c, t) of gy * x. */
+typedef struct {
+  int n, C, T, F; int64_t ld;
+  const float* x; const float* s; float* y;
+  const float* gy; float* gx; float* gs;            /* gs [n][F] zeroed by the call */
+} WesepColScaleArgs;
+int wesep_b200_colscale_fwd(const WesepColScaleArgs* a, void* stream);
+int wesep_b200_colscale_bwd(const WesepColScaleArgs* a, void* stream);
 
 #ifdef __cplusplus
 }

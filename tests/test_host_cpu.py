@@ -127,3 +127,23 @@ def test_gloo_world2_allreduce(tmp_path):
                          capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("ok") == 2
+
+
+def test_dpccn_state_dict_contract():
+    """DPCCN constructs on the host with the reference's keys, order and shapes (oracle.dpccn.make_state_dict restates
+    wesep/models/dpccn.py:58-204), rejects configurations that are not built, and refuses CPU tensors."""
+    import pytest
+    import torch
+    from oracle import dpccn as od
+    from wesep_b200.models import get_model
+    m = get_model("DPCCN")(joint_training=False, tcn_blocks=3, tcn_layers=1)
+    ref = od.make_state_dict(tcn_blocks=3, tcn_layers=1)
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(ref.keys())
+    assert all(sd[k].shape == ref[k].shape for k in ref)
+    with pytest.raises(NotImplementedError):
+        get_model("DPCCN")(joint_training=False, spk_fuse_type="concat")
+    with pytest.raises(NotImplementedError):
+        get_model("DPCCN")(joint_training=False, causal=True)
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 4000), torch.zeros(1, 256))

@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(256) im2col3x3_kernel(WesepIm2colArgs a) {
   const int HWo = a.Ho * a.Wo;
   for (int i = blockIdx.x * 256 + threadIdx.x; i < HWo; i += gridDim.x * 256) {
     const int ho = i / a.Wo, wo = i - ho * a.Wo;
-    const int h = ho * a.stride + kh - 1, w = wo * a.stride + kw - 1;
+    const int h = ho * a.stride + kh - 1, w = wo * (a.stride_w ? a.stride_w : a.stride) + kw - 1;
     col[i] = (h >= 0 && h < a.H && w >= 0 && w < a.W) ? __ldg(x + (int64_t)h * a.W + w) : 0.f;
   }
 }
@@ -32,6 +32,7 @@ __global__ void __launch_bounds__(256) col2im3x3_kernel(WesepIm2colArgs a) {
   const float* gcol = a.gcol + (int64_t)n * a.bsc + (int64_t)(9 * c) * a.ldc;
   float* gx = a.gx + ((int64_t)n * a.C + c) * a.ldx;
   const int HW = a.H * a.W;
+  const int sw = a.stride_w ? a.stride_w : a.stride;
   for (int i = blockIdx.x * 256 + threadIdx.x; i < HW; i += gridDim.x * 256) {
     const int h = i / a.W, w = i - h * a.W;
     float s = 0.f;
@@ -44,8 +45,8 @@ __global__ void __launch_bounds__(256) col2im3x3_kernel(WesepIm2colArgs a) {
 #pragma unroll
       for (int kw = 0; kw < 3; ++kw) {
         const int wn = w + 1 - kw;
-        if (wn < 0 || wn % a.stride) continue;
-        const int wo = wn / a.stride;
+        if (wn < 0 || wn % sw) continue;
+        const int wo = wn / sw;
         if (wo >= a.Wo) continue;
         s += __ldg(gcol + (int64_t)(kh * 3 + kw) * a.ldc + (int64_t)ho * a.Wo + wo);
       }
@@ -200,7 +201,9 @@ using namespace wb;
 
 static int check_i2c(const WesepIm2colArgs* a) {
   if (a->n <= 0 || a->C <= 0 || a->H <= 0 || a->W <= 0 || (a->stride != 1 && a->stride != 2)) return fail(-1, "im2col: shape / stride");
-  if (a->Ho != (a->H - 1) / a->stride + 1 || a->Wo != (a->W - 1) / a->stride + 1) return fail(-1, "im2col: output size (pad 1, k 3)");
+  if (a->stride_w != 0 && a->stride_w != 1 && a->stride_w != 2) return fail(-1, "im2col: stride_w");
+  const int sw_ = a->stride_w ? a->stride_w : a->stride;
+  if (a->Ho != (a->H - 1) / a->stride + 1 || a->Wo != (a->W - 1) / sw_ + 1) return fail(-1, "im2col: output size (pad 1, k 3)");
   if (a->ldx < (int64_t)a->H * a->W || a->ldc < (int64_t)a->Ho * a->Wo || a->bsc < a->ldc) return fail(-1, "im2col: row / batch strides");
   if ((int64_t)a->n > 65535 || 9 * (int64_t)a->C > 65535) return fail(-2, "im2col: too many rows / channels for one launch");
   return 0;

@@ -1,6 +1,7 @@
 """Model registry — reference wesep/models/__init__.py:10-27 (prefix dispatch by name)."""
 import wesep_b200.models.bsrnn as bsrnn
 import wesep_b200.models.convtasnet as convtasnet
+import wesep_b200.models.dpccn as dpccn
 
 
 def get_model(model_name: str):
@@ -8,8 +9,10 @@ def get_model(model_name: str):
         return getattr(convtasnet, model_name)
     if model_name == "BSRNN":          # first correct CUDA path (joint_training=False); see models/bsrnn.py
         return bsrnn.BSRNN
+    if model_name == "DPCCN":
+        return dpccn.DPCCN
     for prefix in ("BSRNN_Multi", "BSRNN_Feats", "BSRNN", "DPCCN", "TFGridNet", "CMGAN"):
         if model_name.startswith(prefix):
-            raise NotImplementedError(model_name + " is not built yet in wesep_b200 (Spex+/ConvTasNet only so far)")
+            raise NotImplementedError(model_name + " is not built yet in wesep_b200 (ConvTasNet / Spex+, BSRNN and DPCCN are)")
     print(model_name + " not found !!!")
     exit(1)

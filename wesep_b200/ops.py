@@ -1187,10 +1187,18 @@ class AddFn(torch.autograd.Function):
         return g, g
 
 
+def _strides2(stride):
+    """int or (sh, sw) -> (sh, sw)."""
+    if isinstance(stride, (tuple, list)):
+        return int(stride[0]), int(stride[1])
+    return int(stride), int(stride)
+
+
 def _i2c_args(n, C, H, W, stride, ldx, ct, **kw):
     """`ct`: the col-side tensor (its row / batch strides)."""
-    return _args("WesepIm2colArgs", n=n, C=C, H=H, W=W, stride=stride, Ho=(H - 1) // stride + 1, Wo=(W - 1) // stride + 1,
-                 ldx=ldx, ldc=ct.stride(1), bsc=ct.stride(0), **kw)
+    sh, sw = _strides2(stride)
+    return _args("WesepIm2colArgs", n=n, C=C, H=H, W=W, stride=sh, stride_w=0 if sw == sh else sw, Ho=(H - 1) // sh + 1,
+                 Wo=(W - 1) // sw + 1, ldx=ldx, ldc=ct.stride(1), bsc=ct.stride(0), **kw)
 
 
 class Im2Col3x3Fn(torch.autograd.Function):
@@ -1203,7 +1211,8 @@ class Im2Col3x3Fn(torch.autograd.Function):
         n, C, HW = x.shape
         if HW != H * W:
             raise RuntimeError("im2col: H * W does not match the tensor")
-        Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+        sh, sw = _strides2(stride)
+        Ho, Wo = (H - 1) // sh + 1, (W - 1) // sw + 1
         Kp = (9 * C + 15) // 16 * 16                    # GEMM-friendly channel count: zero rows beyond 9 C (first conv: 9 -> 16)
         col = new_act(n, Kp, Ho * Wo, x.device)
         if Kp != 9 * C:
@@ -1307,3 +1316,199 @@ class TstpFn(torch.autograd.Function):
         _lib.call("wesep_b200_tstp_bwd", _args("WesepTstpArgs", n=n, R=R, T=T, ld=x.stride(1), x=x, gout=g.contiguous().float(),
                                                gx=gx), _stream())
         return gx
+
+
+# --------------------------------------------------------------------------- pDPCCN building blocks
+class Col2Im3x3Fn(torch.autograd.Function):
+    """The adjoint of Im2Col3x3Fn as a forward op: [n, >= 9C, Ho*Wo] patch rows -> [n, C, H*W] (overlap-add of the 3x3
+    patches).  With the pointwise GEMM in front this is nn.ConvTranspose2d(kernel 3, padding 1, stride (sh, sw))."""
+
+    @staticmethod
+    def forward(ctx, dcol, C, H, W, stride):
+        dcol = as_act(dcol)
+        n, Kp, HWo = dcol.shape
+        sh, sw = _strides2(stride)
+        if Kp < 9 * C or HWo != ((H - 1) // sh + 1) * ((W - 1) // sw + 1):
+            raise RuntimeError("col2im: shape mismatch")
+        y = new_act(n, C, H * W, dcol.device)
+        _lib.call("wesep_b200_im2col3x3_bwd", _i2c_args(n, C, H, W, stride, y.stride(1), dcol, gcol=dcol, gx=y), _stream())
+        ctx.meta = (n, C, H, W, stride, Kp)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        n, C, H, W, stride, Kp = ctx.meta
+        gy = as_act(gy)
+        sh, sw = _strides2(stride)
+        gcol = new_act(n, Kp, ((H - 1) // sh + 1) * ((W - 1) // sw + 1), gy.device)
+        if Kp != 9 * C:
+            gcol[:, 9 * C:].zero_()
+        _lib.call("wesep_b200_im2col3x3_fwd", _i2c_args(n, C, H, W, stride, gy.stride(1), gcol, x=gy, col=gcol), _stream())
+        return gcol, None, None, None, None
+
+
+def conv3x3(x, H, W, weight, bias, stride=1):
+    """nn.Conv2d(Ci, Co, 3, stride, padding 1) on an act map [n, Ci, H*W]: im2col + tcgen05 pointwise GEMM."""
+    col = Im2Col3x3Fn.apply(x, H, W, stride)
+    w2 = weight.reshape(weight.shape[0], -1)
+    if col.shape[1] != w2.shape[1]:
+        w2 = torch.nn.functional.pad(w2, (0, col.shape[1] - w2.shape[1]))
+    return conv1x1_bigk(col, w2, bias)
+
+
+def conv_transpose3x3(x, H, W_out, weight, bias, stride=1):
+    """nn.ConvTranspose2d(Ci, Co, 3, stride, padding 1) on [n, Ci, H*Wi] -> [n, Co, H_out*W_out]: pointwise GEMM with the
+    weight viewed [Ci, Co*9] (transposed product) + col2im.  `weight` is the module's [Ci, Co, 3, 3] tensor."""
+    Ci, Co = weight.shape[0], weight.shape[1]
+    sh, sw = _strides2(stride)
+    if sh != 1:
+        raise RuntimeError("conv_transpose3x3: only stride (1, s) is built")
+    w2 = weight.reshape(Ci, Co * 9)
+    M = (Co * 9 + 3) // 4 * 4
+    if M != Co * 9:
+        w2 = torch.nn.functional.pad(w2, (0, M - Co * 9))
+    dcol = Conv1x1Fn.apply(x, w2, None, True, None)                      # [n, Co*9 (+pad), H*Wi]
+    y = Col2Im3x3Fn.apply(dcol, Co, H, W_out, stride)
+    if bias is not None:
+        y = RowAffineFn.apply(y, None, bias[None].expand(y.shape[0], Co))
+    return y
+
+
+class EluInFn(torch.autograd.Function):
+    """mode 0: InstanceNorm(ELU(x)); mode 1: ELU(InstanceNorm(x)); per (n, c) plane, eps 1e-5, no affine."""
+
+    @staticmethod
+    def forward(ctx, x, mode):
+        x = as_act(x)
+        n, C, L = x.shape
+        dev = x.device
+        y = new_act(n, C, L, dev)
+        stats = torch.empty((n * C, 2), dtype=torch.float64, device=dev)
+        mr = torch.empty((n * C, 2), dtype=torch.float32, device=dev)
+        _lib.call("wesep_b200_elu_in_fwd", _args("WesepEluInArgs", rows=n * C, L=L, ld=x.stride(1), mode=int(mode), eps=1e-5,
+                                                 x=x, y=y, stats=stats, mr=mr), _stream())
+        ctx.mode = int(mode)
+        ctx.save_for_backward(x, mr)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, mr = ctx.saved_tensors
+        n, C, L = x.shape
+        gy = as_act(gy)
+        if gy.stride(1) != x.stride(1):
+            raise RuntimeError("elu_in backward: stride mismatch")
+        gx = new_act(n, C, L, x.device)
+        stats = torch.empty((n * C, 2), dtype=torch.float64, device=x.device)
+        _lib.call("wesep_b200_elu_in_bwd", _args("WesepEluInArgs", rows=n * C, L=L, ld=x.stride(1), mode=ctx.mode, eps=1e-5,
+                                                 x=x, stats=stats, mr=mr, gy=gy, gx=gx), _stream())
+        return gx, None
+
+
+class DwConv1dFn(torch.autograd.Function):
+    """nn.Conv1d(C, C, 3, padding=dil, dilation=dil, groups=C) — weight [C, 1, 3]."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, dil):
+        x = as_act(x)
+        n, C, L = x.shape
+        w = weight.reshape(C, 3).contiguous()
+        y = new_act(n, C, L, x.device)
+        _lib.call("wesep_b200_dwconv1d_fwd", _args("WesepDwConv1dArgs", n=n, C=C, L=L, ld=x.stride(1), dil=int(dil), x=x, w=w,
+                                                   b=None if bias is None else _vec(bias), y=y), _stream())
+        ctx.dil, ctx.wshape, ctx.has_bias = int(dil), weight.shape, bias is not None
+        ctx.save_for_backward(x, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        n, C, L = x.shape
+        gy = as_act(gy)
+        if gy.stride(1) != x.stride(1):
+            raise RuntimeError("dwconv1d backward: stride mismatch")
+        gx = new_act(n, C, L, x.device)
+        gw = torch.empty((C, 3), dtype=torch.float32, device=x.device)
+        gb = torch.empty((C,), dtype=torch.float32, device=x.device) if ctx.has_bias else None
+        _lib.call("wesep_b200_dwconv1d_bwd", _args("WesepDwConv1dArgs", n=n, C=C, L=L, ld=x.stride(1), dil=ctx.dil, x=x, w=w,
+                                                   gy=gy, gx=gx, gw=gw, gb=gb), _stream())
+        return gx, gw.view(ctx.wshape), gb, None
+
+
+class AvgPool2dFn(torch.autograd.Function):
+    """nn.AvgPool2d(k) on an act map [n, C, H*W] -> [n, C, (H//k)*(W//k)]."""
+
+    @staticmethod
+    def forward(ctx, x, H, W, k):
+        x = as_act(x)
+        n, C, _ = x.shape
+        Ho, Wo = H // k, W // k
+        y = new_act(n, C, Ho * Wo, x.device)
+        _lib.call("wesep_b200_avgpool2d_fwd", _args("WesepPool2dArgs", rows=n * C, H=H, W=W, k=k, Ho=Ho, Wo=Wo, ldx=x.stride(1),
+                                                    ldy=y.stride(1), x=x, y=y), _stream())
+        ctx.meta = (n, C, H, W, k, Ho, Wo)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        n, C, H, W, k, Ho, Wo = ctx.meta
+        gy = as_act(gy)
+        gx = new_act(n, C, H * W, gy.device)
+        _lib.call("wesep_b200_avgpool2d_bwd", _args("WesepPool2dArgs", rows=n * C, H=H, W=W, k=k, Ho=Ho, Wo=Wo, ldx=gx.stride(1),
+                                                    ldy=gy.stride(1), gy=gy, gx=gx), _stream())
+        return gx, None, None, None
+
+
+class Upsample2dFn(torch.autograd.Function):
+    """nn.Upsample(size=(Ho, Wo), mode="bilinear") on [n, C, Hi*Wi]."""
+
+    @staticmethod
+    def forward(ctx, x, Hi, Wi, Ho, Wo):
+        x = as_act(x)
+        n, C, _ = x.shape
+        y = new_act(n, C, Ho * Wo, x.device)
+        _lib.call("wesep_b200_upsample2d_fwd", _args("WesepUpsample2dArgs", rows=n * C, Hi=Hi, Wi=Wi, Ho=Ho, Wo=Wo,
+                                                     ldi=x.stride(1), ldo=y.stride(1), x=x, y=y), _stream())
+        ctx.meta = (n, C, Hi, Wi, Ho, Wo)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        n, C, Hi, Wi, Ho, Wo = ctx.meta
+        gy = as_act(gy)
+        gx = new_act(n, C, Hi * Wi, gy.device)
+        _lib.call("wesep_b200_upsample2d_bwd", _args("WesepUpsample2dArgs", rows=n * C, Hi=Hi, Wi=Wi, Ho=Ho, Wo=Wo,
+                                                     ldi=gx.stride(1), ldo=gy.stride(1), gy=gy, gx=gx), _stream())
+        return gx, None, None, None, None
+
+
+class ColScaleFn(torch.autograd.Function):
+    """y[n, c, t*F + f] = x[n, c, t*F + f] * s[n, f] (4-D multiply fusion, speaker.py:117-121)."""
+
+    @staticmethod
+    def forward(ctx, x, s, T, F):
+        x = as_act(x)
+        n, C, L = x.shape
+        if L != T * F or s.shape != (n, F):
+            raise RuntimeError("colscale: shape mismatch")
+        s = s.contiguous().float()
+        y = new_act(n, C, L, x.device)
+        _lib.call("wesep_b200_colscale_fwd", _args("WesepColScaleArgs", n=n, C=C, T=T, F=F, ld=x.stride(1), x=x, s=s, y=y),
+                  _stream())
+        ctx.meta = (T, F)
+        ctx.save_for_backward(x, s)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, s = ctx.saved_tensors
+        T, F = ctx.meta
+        n, C, L = x.shape
+        gy = as_act(gy)
+        if gy.stride(1) != x.stride(1):
+            raise RuntimeError("colscale backward: stride mismatch")
+        gx = new_act(n, C, L, x.device)
+        gs = torch.empty((n, F), dtype=torch.float32, device=x.device)
+        _lib.call("wesep_b200_colscale_bwd", _args("WesepColScaleArgs", n=n, C=C, T=T, F=F, ld=x.stride(1), x=x, s=s, gy=gy,
+                                                   gx=gx, gs=gs), _stream())
+        return gx, gs, None, None
