@@ -36,6 +36,10 @@ BSRNN_ARGS = dict(sr=16000, win=512, stride=128, feature_dim=128, num_repeat=6, 
                   multi_fuse=False, joint_training=True, spk_model="ResNet34", spk_model_init=False,
                   spk_args=dict(feat_dim=80, embed_dim=256, pooling_func="TSTP", two_emb_layer=False), spk_emb_dim=256,
                   spk_model_freeze=False, spk_feat=True, feat_type="consistent", multi_task=False)   # bsrnn.yaml:46-83 verbatim
+DPCCN_ARGS = dict(win=512, stride=128, feature_dim=257, tcn_blocks=10, tcn_layers=2, causal=False, spk_fuse_type="multiply",
+                  use_spk_transform=False, multi_fuse=False, joint_training=True, spk_model="ResNet34", spk_model_init=False,
+                  spk_args=dict(feat_dim=80, embed_dim=256, pooling_func="TSTP", two_emb_layer=False), spk_emb_dim=256,
+                  spk_model_freeze=False, spk_feat=True, feat_type="consistent")                      # dpccn.yaml:40-80 verbatim
 BSRNN_FBANK_FRAMES = 398        # 1 + (64000 - 400) // 160 frames of 25 ms / 10 ms fbank for a 4 s enrollment
 SPEX_BYTES_PER_ROW = 6.4e9      # algorithmic HBM bytes per row per train step (32 x 190 MB + 0.35 GB)
 SPEX_FLOPS_PER_ROW = 396e9      # algorithmic flops per row per train step (132 GFLOP forward x 3)
@@ -389,11 +393,64 @@ def run_pbsrnn(args, rank, world, dev, pk, barrier):
                                      "[n, 398, 80] enrollment fbank features) full train step, 4s@16kHz, %d rows per GPU" % n,
                             loss="SI-SDR", optimizer="per-tensor clip 5.0 + Adam(wd 1e-4)",
                             launch="one CUDA-graph replay per step" if graphed is not None else "eager (one launch per kernel)",
-                            gemm_mode="3xTF32 GEMMs; recurrence fp16 hi/lo (fwd) / bf16 hi/lo (bwd) split products"),
+                            gemm_mode="GEMMs: mixed split (tf32 hi*hi + 2 bf16 cross terms) / 3xTF32; recurrence fp16 hi/lo (fwd) / bf16 hi/lo "
+                                      "(bwd) split products"),
                 e2e=dict(value=n * world * args.steps / (ms_e2e * 1e-3), unit="utterances/s", h2d_bytes_per_step=h2d,
                          d2h_bytes_per_step=4, ms_per_step=ms_e2e / args.steps),
                 gpu_launches=launches, loss=loss_res, loss_e2e=loss_e2e, roofline=roof,
                 top_kernels=[dict(kernel=k[:70], share=v[1] / tot, count=v[0]) for k, v in top])
+
+
+def run_dpccn(args, dev):
+    """Third block (single GPU only): pDPCCN train step, dpccn.yaml network verbatim (jointly trained
+    ResNet34 on fbank features), 4 s @ 16 kHz, `--dpccn-rows` rows, eager launches."""
+    import numpy as np
+    from wesep_b200 import _lib, ops, synth
+    from wesep_b200.models import get_model
+    from wesep_b200.utils.optim import FusedClipAdam
+    n = args.dpccn_rows
+    torch.manual_seed(42)
+    model = get_model("DPCCN")(**DPCCN_ARGS).to(dev).train()
+    opt = FusedClipAdam(model.parameters(), lr=1e-3, weight_decay=1e-4, clip=5.0)
+    host = synth.make_batch(n, T=T_SAMPLES, Te=8, seed=777, pin=True)
+    emb_h = torch.from_numpy(np.random.default_rng(6).standard_normal((n, BSRNN_FBANK_FRAMES, 80)).astype(np.float32)).pin_memory()
+    host = dict(wav_mix=host["wav_mix"], wav_targets=host["wav_targets"], emb=emb_h)
+    resident = {k: v.to(dev) for k, v in host.items()}
+
+    def step(batch, read_loss):
+        mix = batch["wav_mix"].to(dev, non_blocking=True)
+        tgt = batch["wav_targets"].to(dev, non_blocking=True)
+        emb = batch["emb"].to(dev, non_blocking=True)
+        opt.zero_grad()
+        est, _ = model(mix, emb)
+        losses, _ = ops.sisdr_losses([est], tgt)
+        losses[0].backward()
+        opt.step()
+        return losses[0].item() if read_loss else losses[0]
+
+    K = max(1, min(args.steps, 5))
+
+    def sync():
+        torch.cuda.synchronize(dev)
+    ms_res, launches, loss_res = time_steps(lambda: step(resident, False), 3, K, sync, 1, dev)
+    ms_e2e, _, loss_e2e = time_steps(lambda: step(host, True), 1, K, sync, 1, dev)
+    agg, tot = kernel_shares(lambda: step(resident, False))
+    top = sorted(agg.items(), key=lambda kv: -kv[1][1])[:6]
+    out = dict(metric="utterances/sec pDPCCN train step (4s@16kHz)", value=n * K / (ms_res * 1e-3), unit="utterances/s",
+               ms_per_step=ms_res / K, steps=K, rows_per_gpu=n,
+               config=dict(workload="pDPCCN (examples/librimix/tse/v2/confs/dpccn.yaml network: 257 bins, dense conv encoder / "
+                                    "decoder, 2 x 10 TCN blocks, multiply fusion, jointly trained wespeaker ResNet34-TSTP on [n, 398, 80] "
+                                    "fbank features) full train step, 4s@16kHz, %d rows" % n,
+                           loss="SI-SDR", optimizer="per-tensor clip 5.0 + Adam(wd 1e-4)", launch="eager (one launch per kernel)",
+                           conv="3x3 (transposed) convolutions = im2col / col2im + tcgen05 pointwise GEMM"),
+               e2e=dict(value=n * K / (ms_e2e * 1e-3), unit="utterances/s",
+                        h2d_bytes_per_step=sum(v.numel() * v.element_size() for v in host.values()), d2h_bytes_per_step=4,
+                        ms_per_step=ms_e2e / K),
+               gpu_launches=launches, loss=loss_res, loss_e2e=loss_e2e, peak_mem_gb=torch.cuda.max_memory_allocated(dev) / 2 ** 30,
+               top_kernels=[dict(kernel=k[:70], share=v[1] / tot, count=v[0]) for k, v in top])
+    del model, opt, resident
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_ours(args, rank, world, local):
@@ -477,6 +534,12 @@ def run_ours(args, rank, world, local):
         pb = run_pbsrnn(args, rank, world, dev, pk, barrier)
     if rank != 0:
         return
+    dp = None
+    if world == 1 and not args.no_dpccn:
+        try:
+            dp = run_dpccn(args, dev)
+        except Exception as ex:                                 # extra block: never lose the bench line over it
+            dp = dict(error=repr(ex)[:300])
     cpu = eager = None
     if world == 1 and not args.no_cpu_baseline:
         threads = cpu_threads()
@@ -504,7 +567,7 @@ def run_ours(args, rank, world, local):
         e2e=dict(value=e2e, unit="utterances/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
                  ms_per_step=ms_e2e / args.steps),
         gpu_launches=launches, clocks=clocks_spex, loss=loss_res, loss_e2e=loss_e2e,
-        roofline=roof, pbsrnn=pb, cpu_baseline=cpu, gpu_eager_baseline=eager)
+        roofline=roof, pbsrnn=pb, dpccn=dp, cpu_baseline=cpu, gpu_eager_baseline=eager)
     print(json.dumps(line), flush=True)
 
 
@@ -519,6 +582,8 @@ def main():
     ap.add_argument("--ref-rows", type=int, default=2, help="rows per step of the bounded CPU sample (>= 2)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU and GPU-eager baselines")
     ap.add_argument("--no-pbsrnn", action="store_true", help="skip the pBSRNN block")
+    ap.add_argument("--no-dpccn", action="store_true", help="skip the pDPCCN block (single-GPU runs only)")
+    ap.add_argument("--dpccn-rows", type=int, default=4, help="pDPCCN block: model rows")
     ap.add_argument("--no-graph", action="store_true", help="pBSRNN block: eager launches instead of a CUDA-graph replay per step")
     ap.add_argument("--cuda-graph", action="store_true",
                     help="capture the whole Spex+ train step in a CUDA graph and time replays (single GPU)")

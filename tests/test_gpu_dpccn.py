@@ -3,6 +3,7 @@ fp64 torch restatements, and the whole model (forward, SISDR loss, every gradien
 reference (tests/golden/dpccn_*.npz) and the fp64 oracle."""
 import json
 import os
+import re
 
 import numpy as np
 import pytest
@@ -137,6 +138,11 @@ def test_conv_transpose3x3(sw, Co):
     check("gb", b.grad, b64.grad, 5e-5)
 
 
+# the depthwise conv's bias feeds InstanceNorm directly (convs.py:146-148): a constant shift of a plane is removed by the
+# norm, so its gradient is exactly 0 in exact arithmetic and both sides hold round-off only (|g| ~ 1e-7)
+ZERO_GRAD = re.compile(r"tcn_layers\.\d+\.\d+\.dconv1\.bias$")
+
+
 def _golden_case(name, tol_g=2e-3):
     from wesep_b200 import ops, synth
     from wesep_b200.models import get_model
@@ -165,10 +171,13 @@ def _golden_case(name, tol_g=2e-3):
     for k, p in m.named_parameters():
         ref_n = float(z["gnorm/" + k])
         gn = float(p.grad.double().norm())
+        if ZERO_GRAD.search(k):
+            assert gn <= 1e-4 and ref_n <= 1e-4, (name, k, gn, ref_n)
+            continue
         rel = abs(gn - ref_n) / (ref_n + 1e-6)
         worst = max(worst, (rel, k))
         assert abs(gn - ref_n) <= tol_g * ref_n + 1e-5, (name, k, gn, ref_n)
-        key = "g/" + k if "g/" + k in z else "ghead/" + k
+        key ="g/" + k if "g/" + k in z else "ghead/" + k
         rg = torch.from_numpy(z[key]).to(DEV).reshape(-1).double()
         gg = p.grad.reshape(-1)[:rg.numel()].double()
         cos = float((rg * gg).sum() / (rg.norm() * gg.norm() + 1e-30))

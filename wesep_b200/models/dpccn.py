@@ -87,9 +87,9 @@ class DenseBlock(nn.Module):
     def run(self, x, T, F):
         feats = [x]
         for conv in (self.conv1, self.conv2, self.conv3, self.conv4):
-            y, _ = conv.run(feats[0] if len(feats) == 1 else torch.cat(feats, 1), T, F)
+            y, _ = conv.run(ops.cat_act(feats), T, F)
             feats.append(y)
-        y, _ = self.conv5.run(torch.cat(feats, 1), T, F)
+        y, _ = self.conv5.run(ops.cat_act(feats), T, F)
         return y, F
 
 
@@ -289,7 +289,7 @@ class DPCCN(nn.Module):
             out, F = self._run(enc, out, T, F)
             out_list.append((out, F))
 
-        N = out.shape[1]                                            # [B, 384, T*F] is already the TCN's [B, N, T*F] view
+        # [B, 384, T*F] is already the TCN's [B, N, T*F] view (dpccn.py:252-253)
         for layer in self.tcn_layers:
             for blk in layer:
                 out = blk.run(out)
@@ -298,14 +298,14 @@ class DPCCN(nn.Module):
             skip, Fs = out_list[idx]
             if Fs != F or skip.shape[2] != out.shape[2]:
                 raise RuntimeError("DPCCN: skip connection shape mismatch")
-            out, F = self._run(dec, torch.cat([skip, out], 1), T, F)
+            out, F = self._run(dec, ops.cat_act([skip, out]), T, F)
         # pyramidal pooling, dpccn.py:260-267
         pools = [out]
         for sz, avg in zip(self.pool_size, self.avg_pool):
             p = ops.AvgPool2dFn.apply(out, T, F, sz)
             p = ops.Conv1x1Fn.apply(p, avg[1].weight.reshape(8, 32), avg[1].bias, False, None)
             pools.append(ops.Upsample2dFn.apply(p, T // sz, F // sz, T, F))
-        out = ops.Conv1x1Fn.apply(torch.cat(pools, 1), self.avg_proj.weight.reshape(32, 64), self.avg_proj.bias, False, None)
+        out = ops.Conv1x1Fn.apply(ops.cat_act(pools), self.avg_proj.weight.reshape(32, 64), self.avg_proj.bias, False, None)
         out = ops.conv_transpose3x3(out, T, F, self.deconv2d.weight, self.deconv2d.bias, 1)               # [B, 2, T*F]
         # dpccn.py:271-284: [B, 2, T, F] -> [B, 2, F, T] -> complex spectrum -> iSTFT
         est = out.reshape(B, 2, T, F).transpose(2, 3).reshape(B, 2 * F, T)

@@ -1374,6 +1374,33 @@ def conv_transpose3x3(x, H, W_out, weight, bias, stride=1):
     return y
 
 
+class CatActFn(torch.autograd.Function):
+    """torch.cat(xs, 1) written straight into an act tensor (torch.cat would return a dense [n, C, L] tensor that every
+    kernel wrapper then copies into the padded layout); the gradient pieces are channel slices of gy (no copies)."""
+
+    @staticmethod
+    def forward(ctx, *xs):
+        n, L = xs[0].shape[0], xs[0].shape[2]
+        out = new_act(n, sum(x.shape[1] for x in xs), L, xs[0].device)
+        c0, cuts = 0, []
+        for x in xs:
+            if x.shape[0] != n or x.shape[2] != L:
+                raise RuntimeError("cat_act: shape mismatch")
+            out[:, c0:c0 + x.shape[1]].copy_(x)
+            cuts.append((c0, c0 + x.shape[1]))
+            c0 += x.shape[1]
+        ctx.cuts = cuts
+        return out
+
+    @staticmethod
+    def backward(ctx, gy):
+        return tuple(gy[:, a:b] for a, b in ctx.cuts)
+
+
+def cat_act(xs):
+    return xs[0] if len(xs) == 1 else CatActFn.apply(*xs)
+
+
 class EluInFn(torch.autograd.Function):
     """mode 0: InstanceNorm(ELU(x)); mode 1: ELU(InstanceNorm(x)); per (n, c) plane, eps 1e-5, no affine."""
 
