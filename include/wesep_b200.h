@@ -650,6 +650,43 @@ typedef struct {
 int wesep_b200_colscale_fwd(const WesepColScaleArgs* a, void* stream);
 int wesep_b200_colscale_bwd(const WesepColScaleArgs* a, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * TF-GridNet building blocks (wesep/modules/tfgridnet/gridnet_block.py:118-284,
+ * wesep/models/tfgridnet.py:197-302).  Maps are act tensors [B][H*E][T*F] (F contiguous).
+ * ---------------------------------------------------------------------------------------------- */
+/* PReLU (slope per head, or one slope) then LayerNorm over (E, F) of every (b, h, t) with affine gamma / beta [H][E][F]:
+ * AllHeadPReLULayerNormalization4DCF (gridnet_block.py:255-284); with H = 1, E = C: nn.PReLU + LayerNormalization4DCF of
+ * attn_concat_proj (gridnet_block.py:103-110,229-252).  Biased variance, eps inside the square root. */
+typedef struct {
+  int B, H, E, T, F; int64_t ld;
+  int alpha_per_head; float eps;
+  const float* x; const float* alpha; const float* gamma; const float* beta;
+  float* y;
+  float* mr;                           /* [B][H][T][2] (mean, rstd): written by fwd, read by bwd */
+  const float* gy; float* gx;          /* bwd */
+  float* dgamma; float* dbeta;         /* [H][E][F], zeroed by the call */
+  float* dalpha;                       /* [H] or [1], zeroed by the call */
+} WesepHeadLnArgs;
+int wesep_b200_head_ln_fwd(const WesepHeadLnArgs* a, void* stream);
+int wesep_b200_head_ln_bwd(const WesepHeadLnArgs* a, void* stream);
+
+/* y[r][c] = softmax over c < C of scale * x[r][c] (attention matrix, gridnet_block.py:213-214); columns [C, ld) of y and gx are
+ * zeroed so the matrix can be used as a GEMM operand with its padded row length.  bwd: gx = scale * y * (gy - sum_c gy y). */
+typedef struct {
+  int64_t rows; int C; int64_t ld; float scale;
+  const float* x; float* y;
+  const float* gy; float* gx;
+} WesepSoftmaxArgs;
+int wesep_b200_softmax_fwd(const WesepSoftmaxArgs* a, void* stream);
+int wesep_b200_softmax_bwd(const WesepSoftmaxArgs* a, void* stream);
+
+/* torch.std(x, dim=1) (unbiased) of every row and its reciprocal: the RMS normalisation of tfgridnet.py:217-218,297 */
+typedef struct {
+  int n; int L; int64_t ld;
+  const float* x; float* std; float* inv_std;
+} WesepRowStdArgs;
+int wesep_b200_rowstd(const WesepRowStdArgs* a, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

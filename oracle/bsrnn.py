@@ -36,7 +36,7 @@ def hann(win, dtype):
     return torch.hann_window(win, dtype=torch.float32).to(dtype)
 
 
-def stft(x, win=512, hop=128):
+def stft(x, win=512, hop=128, window=None):
     """torch.stft(x, n_fft=win, hop_length=hop, window=hann, center=True (reflect), onesided, not normalised,
     return_complex=True), bsrnn.py:309-316.  x [B, L] -> (re, im) each [B, win/2+1, 1 + L//hop]."""
     B, L = x.shape
@@ -46,7 +46,7 @@ def stft(x, win=512, hop=128):
     xp = torch.cat([left, x, right], 1)                       # reflect padding
     T = 1 + L // hop
     idx = (torch.arange(T) * hop)[:, None] + torch.arange(win)[None, :]
-    fr = xp[:, idx] * hann(win, x.dtype)                      # [B, T, win]
+    fr = xp[:, idx] * (hann(win, x.dtype) if window is None else window)   # [B, T, win]
     k = torch.arange(win, dtype=torch.float64)
     f = torch.arange(win // 2 + 1, dtype=torch.float64)
     ang = 2.0 * math.pi * f[:, None] * k[None, :] / win      # [F, win]
@@ -56,7 +56,7 @@ def stft(x, win=512, hop=128):
     return re, im
 
 
-def istft(re, im, win=512, hop=128, length=None):
+def istft(re, im, win=512, hop=128, length=None, window=None):
     """torch.istft(spec, n_fft=win, hop_length=hop, window=hann, center=True, length=length), bsrnn.py:382-389:
     frame = irfft(X_t) * w; y = overlap_add(frame) / overlap_add(w^2); drop win/2 samples at the start."""
     B, F, T = re.shape
@@ -70,7 +70,7 @@ def istft(re, im, win=512, hop=128, length=None):
     ci = (-wgt[:, None] * torch.sin(ang) / win).to(re.dtype)
     ci[0] = 0.0                                               # irfft ignores the imaginary part of DC / Nyquist
     ci[-1] = 0.0
-    w = hann(win, re.dtype)
+    w = hann(win, re.dtype) if window is None else window
     fr = (torch.einsum("fk,bft->btk", cr, re) + torch.einsum("fk,bft->btk", ci, im)) * w   # [B, T, win]
     n_out = win + hop * (T - 1)
     y = torch.zeros(B, n_out, dtype=re.dtype)

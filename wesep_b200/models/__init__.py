@@ -2,6 +2,7 @@
 import wesep_b200.models.bsrnn as bsrnn
 import wesep_b200.models.convtasnet as convtasnet
 import wesep_b200.models.dpccn as dpccn
+import wesep_b200.models.tfgridnet as tfgridnet
 
 
 def get_model(model_name: str):
@@ -11,8 +12,10 @@ def get_model(model_name: str):
         return bsrnn.BSRNN
     if model_name == "DPCCN":
         return dpccn.DPCCN
+    if model_name == "TFGridNet":
+        return tfgridnet.TFGridNet
     for prefix in ("BSRNN_Multi", "BSRNN_Feats", "BSRNN", "DPCCN", "TFGridNet", "CMGAN"):
         if model_name.startswith(prefix):
-            raise NotImplementedError(model_name + " is not built yet in wesep_b200 (ConvTasNet / Spex+, BSRNN and DPCCN are)")
+            raise NotImplementedError(model_name + " is not built yet in wesep_b200 (ConvTasNet / Spex+, BSRNN, DPCCN and TFGridNet are)")
     print(model_name + " not found !!!")
     exit(1)

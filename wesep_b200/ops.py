@@ -1007,10 +1007,12 @@ def group_norm1(x, weight, bias, eps=GN_EPS):
     return GroupNorm1Fn.apply(x, weight, bias, eps)
 
 
-def res_rnn(x, norm_w, norm_b, lstm, proj_w, proj_b):
+def res_rnn(x, norm_w, norm_b, lstm, proj_w, proj_b, layer_norm_eps=None):
     """ResRNN.forward (bsrnn.py:38-46) on an act tensor x [Q, C, S] (rows = sequences): GroupNorm -> time-major ->
-    BLSTM -> Linear -> back to [Q, C, S] + x.  `lstm` = the 8 nn.LSTM parameters in (forward, reverse) order."""
-    xh = group_norm1(x, norm_w, norm_b)
+    BLSTM -> Linear -> back to [Q, C, S] + x.  `lstm` = the 8 nn.LSTM parameters in (forward, reverse) order.
+    With `layer_norm_eps` the norm is nn.LayerNorm(C, eps) at every (sequence, step) instead — the intra / inter paths of a
+    TF-GridNet block with emb_ks == emb_hs == 1 (gridnet_block.py:139-146,166-172)."""
+    xh = group_norm1(x, norm_w, norm_b) if layer_norm_eps is None else cln(x, norm_w, norm_b, layer_norm_eps)
     xn = SwapOIFn.apply(xh, 1, None)                                   # [S, C, Q]
     h = LstmTmFn.apply(xn, *lstm)                                       # [S, 2Hd, Q]
     p = Conv1x1Fn.apply(h, proj_w, proj_b, False, None)                 # [S, C, Q]
@@ -1539,3 +1541,131 @@ class ColScaleFn(torch.autograd.Function):
         _lib.call("wesep_b200_colscale_bwd", _args("WesepColScaleArgs", n=n, C=C, T=T, F=F, ld=x.stride(1), x=x, s=s, gy=gy,
                                                    gx=gx, gs=gs), _stream())
         return gx, gs, None, None
+
+
+# --------------------------------------------------------------------------- TF-GridNet building blocks
+class HeadLnFn(torch.autograd.Function):
+    """PReLU (slope per head or single) -> LayerNorm over (E, F) of every (b, h, t), affine gamma / beta [H, E, F], on an act map
+    [B, H*E, T*F] (gridnet_block.py:229-284)."""
+
+    @staticmethod
+    def forward(ctx, x, alpha, gamma, beta, H, T, F, eps):
+        x = as_act(x)
+        B, HE, L = x.shape
+        E = HE // H
+        if HE != H * E or L != T * F or gamma.numel() != H * E * F or beta.numel() != H * E * F or alpha.numel() not in (1, H):
+            raise RuntimeError("head_ln: shape mismatch")
+        al, ga, be = _vec(alpha).float(), _vec(gamma).float(), _vec(beta).float()
+        y = new_act(B, HE, L, x.device)
+        mr = torch.empty((B, H, T, 2), dtype=torch.float32, device=x.device)
+        a = _args("WesepHeadLnArgs", B=B, H=H, E=E, T=T, F=F, ld=x.stride(1), alpha_per_head=int(alpha.numel() == H and H > 1),
+                  eps=float(eps), x=x, alpha=al, gamma=ga, beta=be, y=y, mr=mr)
+        _lib.call("wesep_b200_head_ln_fwd", a, _stream())
+        ctx.meta = (H, E, T, F, float(eps), alpha.shape, gamma.shape, beta.shape)
+        ctx.save_for_backward(x, al, ga, be, mr)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, al, ga, be, mr = ctx.saved_tensors
+        H, E, T, F, eps, sha, shg, shb = ctx.meta
+        B, HE, L = x.shape
+        gy = as_act(gy)
+        if gy.stride(1) != x.stride(1):
+            raise RuntimeError("head_ln backward: stride mismatch")
+        gx = new_act(B, HE, L, x.device)
+        dg = torch.empty(H * E * F, dtype=torch.float32, device=x.device)
+        db = torch.empty(H * E * F, dtype=torch.float32, device=x.device)
+        da = torch.empty(al.numel(), dtype=torch.float32, device=x.device)
+        a = _args("WesepHeadLnArgs", B=B, H=H, E=E, T=T, F=F, ld=x.stride(1), alpha_per_head=int(al.numel() == H and H > 1),
+                  eps=eps, x=x, alpha=al, gamma=ga, beta=be, mr=mr, gy=gy, gx=gx, dgamma=dg, dbeta=db, dalpha=da)
+        _lib.call("wesep_b200_head_ln_bwd", a, _stream())
+        return gx, da.view(sha), dg.view(shg), db.view(shb), None, None, None, None
+
+
+class SoftmaxFn(torch.autograd.Function):
+    """softmax(scale * x, dim=-1) over the C valid columns of an act tensor [n, R, C]; padding columns come out zero."""
+
+    @staticmethod
+    def forward(ctx, x, scale):
+        x = as_act(x)
+        n, R, C = x.shape
+        y = new_act(n, R, C, x.device)
+        _lib.call("wesep_b200_softmax_fwd", _args("WesepSoftmaxArgs", rows=n * R, C=C, ld=x.stride(1), scale=float(scale), x=x,
+                                                  y=y), _stream())
+        ctx.scale = float(scale)
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        y, = ctx.saved_tensors
+        n, R, C = y.shape
+        gy = as_act(gy)
+        if gy.stride(1) != y.stride(1):
+            raise RuntimeError("softmax backward: stride mismatch")
+        gx = new_act(n, R, C, y.device)
+        _lib.call("wesep_b200_softmax_bwd", _args("WesepSoftmaxArgs", rows=n * R, C=C, ld=y.stride(1), scale=ctx.scale, y=y,
+                                                  gy=gy, gx=gx), _stream())
+        return gx, None
+
+
+def row_std(x):
+    """(torch.std(x, dim=1), its reciprocal) for a [n, L] signal batch (unbiased; data only, no gradient)."""
+    x, ld = _sig(x)
+    n, L = x.shape
+    sd = torch.empty(n, dtype=torch.float32, device=x.device)
+    inv = torch.empty(n, dtype=torch.float32, device=x.device)
+    _lib.call("wesep_b200_rowstd", _args("WesepRowStdArgs", n=n, L=L, ld=ld, x=x, std=sd, inv_std=inv), _stream())
+    return sd, inv
+
+
+def attention_rows(Qm, Kt, Vm):
+    """softmax(Qm Kt / sqrt(d)) Vm for ONE (batch, head) pair (gridnet_block.py:213-215) on the pointwise GEMMs:
+    Qm [T, d] dense, Kt [d, T], Vm [T, dv] -> [T, dv].  The score and the probability matrices are act tensors whose padded row
+    length (a multiple of 32) is used as the contraction length of the second product (padding columns are zero)."""
+    T, d = Qm.shape
+    Tp, dp = (T + 3) // 4 * 4, (d + 3) // 4 * 4                     # GEMM contraction / output-row counts: multiples of 4
+    pad = torch.nn.functional.pad
+    Kx = as_act(pad(Kt, (0, 0, 0, dp - d))[None])                   # [1, dp, T]
+    S = Conv1x1Fn.apply(Kx, pad(Qm, (0, dp - d, 0, Tp - T)).contiguous(), None, False, None)   # [1, Tp(t), T(s)] = Qm @ Kt
+    P = SoftmaxFn.apply(S, 1.0 / (d ** 0.5))                        # (the Tp - T extra rows are uniform and dropped below)
+    ld = P.stride(1)
+    if P.stride(0) != Tp * ld:
+        raise RuntimeError("attention: probability matrix layout")
+    Pw = _ActAsMatrixFn.apply(P)
+    dv = Vm.shape[1]
+    Vx = new_act(1, ld, dv, Vm.device, zero=True)                   # contraction rows padded with zeros
+    Vx = _RowsIntoFn.apply(Vx, Vm)
+    return Conv1x1Fn.apply(Vx, Pw, None, False, None)[0, :T]        # [T, dv]
+
+
+class _ActAsMatrixFn(torch.autograd.Function):
+    """act [1, R, C] -> the dense [R, ld] matrix over the same memory (padding columns included); the gradient of the
+    padding columns is dropped."""
+
+    @staticmethod
+    def forward(ctx, P):
+        _, R, C = P.shape
+        ld = P.stride(1)
+        ctx.C = C
+        return P.detach().as_strided((R, ld), (ld, 1))
+
+    @staticmethod
+    def backward(ctx, g):
+        return g[:, :ctx.C].unsqueeze(0)
+
+
+class _RowsIntoFn(torch.autograd.Function):
+    """buf[0, :T] = rows (buf zero-filled act [1, Kp, dv]); gradient = the same slice."""
+
+    @staticmethod
+    def forward(ctx, buf, rows):
+        buf[0, :rows.shape[0]].copy_(rows)
+        ctx.T = rows.shape[0]
+        ctx.mark_dirty(buf)
+        return buf
+
+    @staticmethod
+    def backward(ctx, g):
+        return None, g[0, :ctx.T]

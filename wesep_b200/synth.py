@@ -50,7 +50,7 @@ def fill_state_dict_(sd, seed=0):
             val = np.zeros(shape, np.float32)
         elif name.endswith("running_var"):
             val = np.ones(shape, np.float32)
-        elif "prelu" in name.lower():
+        elif "prelu" in name.lower() or name.endswith(".act.weight") or "attn_concat_proj.1." in name:   # (TF-GridNet PReLUs)
             val = 0.25 + 0.05 * rng.standard_normal(shape)
         elif len(shape) >= 2 and not (len(shape) == 2 and shape[1] == 1):
             fan_in = int(np.prod(shape[1:]))
