@@ -40,6 +40,11 @@ DPCCN_ARGS = dict(win=512, stride=128, feature_dim=257, tcn_blocks=10, tcn_layer
                   use_spk_transform=False, multi_fuse=False, joint_training=True, spk_model="ResNet34", spk_model_init=False,
                   spk_args=dict(feat_dim=80, embed_dim=256, pooling_func="TSTP", two_emb_layer=False), spk_emb_dim=256,
                   spk_model_freeze=False, spk_feat=True, feat_type="consistent")                      # dpccn.yaml:40-80 verbatim
+TFGRIDNET_ARGS = dict(n_srcs=1, sr=16000, n_fft=128, stride=64, window="hann", n_imics=1, n_layers=6, lstm_hidden_units=192,
+                      attn_n_head=4, attn_approx_qk_dim=512, emb_dim=128, emb_ks=1, emb_hs=1, activation="prelu", eps=1.0e-5,
+                      use_spk_transform=False, spk_fuse_type="multiply", joint_training=True, spk_model="ResNet34",
+                      spk_model_init=False, spk_args=dict(feat_dim=80, embed_dim=256, pooling_func="TSTP", two_emb_layer=False),
+                      spk_emb_dim=256, spk_model_freeze=False, spk_feat=True, feat_type="consistent")   # tfgridnet.yaml:42-84 minus multi_fuse
 BSRNN_FBANK_FRAMES = 398        # 1 + (64000 - 400) // 160 frames of 25 ms / 10 ms fbank for a 4 s enrollment
 SPEX_BYTES_PER_ROW = 6.4e9      # algorithmic HBM bytes per row per train step (32 x 190 MB + 0.35 GB)
 SPEX_FLOPS_PER_ROW = 396e9      # algorithmic flops per row per train step (132 GFLOP forward x 3)
@@ -401,16 +406,16 @@ def run_pbsrnn(args, rank, world, dev, pk, barrier):
                 top_kernels=[dict(kernel=k[:70], share=v[1] / tot, count=v[0]) for k, v in top])
 
 
-def run_dpccn(args, dev):
-    """Third block (single GPU only): pDPCCN train step, dpccn.yaml network verbatim (jointly trained
-    ResNet34 on fbank features), 4 s @ 16 kHz, `--dpccn-rows` rows, eager launches."""
+def run_extra(args, dev, which):
+    """Further blocks (single GPU only): pDPCCN and TF-GridNet (row a24, BASELINE config 5) train steps on
+    the recipe networks verbatim (jointly trained ResNet34 on fbank features), 4 s @ 16 kHz, eager launches."""
     import numpy as np
     from wesep_b200 import _lib, ops, synth
     from wesep_b200.models import get_model
     from wesep_b200.utils.optim import FusedClipAdam
-    n = args.dpccn_rows
+    n = args.dpccn_rows if which == "DPCCN" else args.tfgridnet_rows
     torch.manual_seed(42)
-    model = get_model("DPCCN")(**DPCCN_ARGS).to(dev).train()
+    model = get_model(which)(**(DPCCN_ARGS if which == "DPCCN" else TFGRIDNET_ARGS)).to(dev).train()
     opt = FusedClipAdam(model.parameters(), lr=1e-3, weight_decay=1e-4, clip=5.0)
     host = synth.make_batch(n, T=T_SAMPLES, Te=8, seed=777, pin=True)
     emb_h = torch.from_numpy(np.random.default_rng(6).standard_normal((n, BSRNN_FBANK_FRAMES, 80)).astype(np.float32)).pin_memory()
@@ -436,13 +441,22 @@ def run_dpccn(args, dev):
     ms_e2e, _, loss_e2e = time_steps(lambda: step(host, True), 1, K, sync, 1, dev)
     agg, tot = kernel_shares(lambda: step(resident, False))
     top = sorted(agg.items(), key=lambda kv: -kv[1][1])[:6]
-    out = dict(metric="utterances/sec pDPCCN train step (4s@16kHz)", value=n * K / (ms_res * 1e-3), unit="utterances/s",
+    if which == "DPCCN":
+        metric = "utterances/sec pDPCCN train step (4s@16kHz)"
+        cfg = dict(workload="pDPCCN (examples/librimix/tse/v2/confs/dpccn.yaml network: 257 bins, dense conv encoder / "
+                            "decoder, 2 x 10 TCN blocks, multiply fusion, jointly trained wespeaker ResNet34-TSTP on [n, 398, 80] "
+                            "fbank features) full train step, 4s@16kHz, %d rows" % n,
+                   conv="3x3 (transposed) convolutions = im2col / col2im + tcgen05 pointwise GEMM")
+    else:
+        metric = "utterances/sec TF-GridNet train step (4s@16kHz)"
+        cfg = dict(workload="TF-GridNet (examples/librimix/tse/v2/confs/tfgridnet.yaml network: n_fft 128, 6 GridNet blocks, 128 "
+                            "channels, BLSTM hidden 192, 4 heads, multiply fusion, jointly trained wespeaker ResNet34-TSTP on "
+                            "[n, 398, 80] fbank features) full train step, 4s@16kHz, %d rows (BASELINE config 5)" % n,
+                   blstm="persistent cluster recurrence kernel (hidden 192, 6 CTAs per cluster)",
+                   attention="two pointwise GEMMs + row softmax per (batch, head)")
+    out = dict(metric=metric, value=n * K / (ms_res * 1e-3), unit="utterances/s",
                ms_per_step=ms_res / K, steps=K, rows_per_gpu=n,
-               config=dict(workload="pDPCCN (examples/librimix/tse/v2/confs/dpccn.yaml network: 257 bins, dense conv encoder / "
-                                    "decoder, 2 x 10 TCN blocks, multiply fusion, jointly trained wespeaker ResNet34-TSTP on [n, 398, 80] "
-                                    "fbank features) full train step, 4s@16kHz, %d rows" % n,
-                           loss="SI-SDR", optimizer="per-tensor clip 5.0 + Adam(wd 1e-4)", launch="eager (one launch per kernel)",
-                           conv="3x3 (transposed) convolutions = im2col / col2im + tcgen05 pointwise GEMM"),
+               config=dict(cfg, loss="SI-SDR", optimizer="per-tensor clip 5.0 + Adam(wd 1e-4)", launch="eager (one launch per kernel)"),
                e2e=dict(value=n * K / (ms_e2e * 1e-3), unit="utterances/s",
                         h2d_bytes_per_step=sum(v.numel() * v.element_size() for v in host.values()), d2h_bytes_per_step=4,
                         ms_per_step=ms_e2e / K),
@@ -537,9 +551,15 @@ def run_ours(args, rank, world, local):
     dp = None
     if world == 1 and not args.no_dpccn:
         try:
-            dp = run_dpccn(args, dev)
+            dp = run_extra(args, dev, "DPCCN")
         except Exception as ex:                                 # extra block: never lose the bench line over it
             dp = dict(error=repr(ex)[:300])
+    tg = None
+    if world == 1 and not args.no_tfgridnet:
+        try:
+            tg = run_extra(args, dev, "TFGridNet")
+        except Exception as ex:
+            tg = dict(error=repr(ex)[:300])
     cpu = eager = None
     if world == 1 and not args.no_cpu_baseline:
         threads = cpu_threads()
@@ -567,7 +587,7 @@ def run_ours(args, rank, world, local):
         e2e=dict(value=e2e, unit="utterances/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
                  ms_per_step=ms_e2e / args.steps),
         gpu_launches=launches, clocks=clocks_spex, loss=loss_res, loss_e2e=loss_e2e,
-        roofline=roof, pbsrnn=pb, dpccn=dp, cpu_baseline=cpu, gpu_eager_baseline=eager)
+        roofline=roof, pbsrnn=pb, dpccn=dp, tfgridnet=tg, cpu_baseline=cpu, gpu_eager_baseline=eager)
     print(json.dumps(line), flush=True)
 
 
@@ -584,6 +604,8 @@ def main():
     ap.add_argument("--no-pbsrnn", action="store_true", help="skip the pBSRNN block")
     ap.add_argument("--no-dpccn", action="store_true", help="skip the pDPCCN block (single-GPU runs only)")
     ap.add_argument("--dpccn-rows", type=int, default=4, help="pDPCCN block: model rows")
+    ap.add_argument("--no-tfgridnet", action="store_true", help="skip the TF-GridNet block (single-GPU runs only)")
+    ap.add_argument("--tfgridnet-rows", type=int, default=4, help="TF-GridNet block: model rows (BASELINE config 5: 4)")
     ap.add_argument("--no-graph", action="store_true", help="pBSRNN block: eager launches instead of a CUDA-graph replay per step")
     ap.add_argument("--cuda-graph", action="store_true",
                     help="capture the whole Spex+ train step in a CUDA graph and time replays (single GPU)")
