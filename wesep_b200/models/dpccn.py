@@ -85,12 +85,11 @@ class DenseBlock(nn.Module):
         self.conv5 = Conv2dBlock(in_dims=in_dims * (n + 4), out_dims=out_dims, **kargs)
 
     def run(self, x, T, F):
-        feats = [x]
-        for conv in (self.conv1, self.conv2, self.conv3, self.conv4):
-            y, _ = conv.run(ops.cat_act(feats), T, F)
-            feats.append(y)
-        y, _ = self.conv5.run(ops.cat_act(feats), T, F)
-        return y, F
+        convs = (self.conv1, self.conv2, self.conv3, self.conv4, self.conv5)
+        if any(c.stride != (1, 1) for c in convs):
+            raise NotImplementedError("pDPCCN: dense blocks use stride (1, 1) (dpccn.py:140,172)")
+        wb = [t for c in convs for t in (c.conv2d.weight, c.conv2d.bias)]
+        return ops.DenseBlockFn.apply(x, T, F, *wb), F
 
 
 class TCNBlock(nn.Module):

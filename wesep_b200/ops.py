@@ -1403,6 +1403,103 @@ def cat_act(xs):
     return xs[0] if len(xs) == 1 else CatActFn.apply(*xs)
 
 
+def _gemm_rows_chunked(X, W2d, M, bias):
+    """Y = W2d X (+ bias) with the contraction split into <= 1008-row chunks (the tcgen05 kernels take <= 1024), the later
+    chunks accumulating in place (epilogue `+= R`)."""
+    Kd = X.shape[1]
+    Y = None
+    for k0 in range(0, Kd, 1008):
+        k1 = min(Kd, k0 + 1008)
+        Wc = W2d[:, k0:k1].contiguous() if (k0 or k1 != Kd) else W2d
+        if Y is None:
+            Y = conv1x1_raw(X[:, k0:k1], Wc, False, M, bias=bias)
+        else:
+            conv1x1_raw(X[:, k0:k1], Wc, False, M, epi=2, R=Y, Y=Y)
+    return Y
+
+
+class DenseBlockFn(torch.autograd.Function):
+    """DenseBlock.forward (wesep/modules/dpccn/convs.py:99-106): five Conv2dBlocks (3x3 / pad 1 / stride 1 -> ELU ->
+    InstanceNorm) where conv k reads cat([x, y1 .. y_{k-1}]).  One patch buffer per block: every map is gathered (im2col) ONCE into
+    its 9 C rows and conv k multiplies the row prefix; the backward accumulates W_k^T g_k into one gradient patch buffer (GEMM
+    epilogue +=) and scatters each map's rows back once (col2im) — no concatenations, a third of the gather traffic.
+    Arguments: x act [n, C0, T*F], T, F, then (weight_k [Co, Ci, 3, 3], bias_k) for k = 1..5."""
+
+    @staticmethod
+    def forward(ctx, x, T, F, *wb):
+        x = as_act(x)
+        n, C0, L = x.shape
+        Ws, Bs = wb[0::2], wb[1::2]
+        Cg = Ws[0].shape[0]
+        Ctot = C0 + 4 * Cg
+        if any(Ws[k].shape[1] != C0 + k * Cg for k in range(5)) or any(Ws[k].shape[0] != Cg for k in range(4)):
+            raise RuntimeError("dense block: weight shapes")
+        if (9 * C0) % 16 or (9 * Cg) % 16:
+            raise RuntimeError("dense block: channel counts must be multiples of 16")
+        dev = x.device
+        col = new_act(n, 9 * Ctot, L, dev)
+        st = _stream()
+        zs, mrs = [], []
+        feat, c_lo = x, 0
+        for k in range(5):
+            Cf = feat.shape[1]
+            rows = col[:, 9 * c_lo:9 * (c_lo + Cf)]
+            _lib.call("wesep_b200_im2col3x3_fwd", _i2c_args(n, Cf, T, F, 1, feat.stride(1), rows, x=feat, col=rows), st)
+            c_lo += Cf
+            Co = Ws[k].shape[0]
+            z = _gemm_rows_chunked(col[:, :9 * c_lo], Ws[k].reshape(Co, 9 * c_lo), Co, _vec(Bs[k]))
+            y = new_act(n, Co, L, dev)
+            stats = torch.empty((n * Co, 2), dtype=torch.float64, device=dev)
+            mr = torch.empty((n * Co, 2), dtype=torch.float32, device=dev)
+            _lib.call("wesep_b200_elu_in_fwd", _args("WesepEluInArgs", rows=n * Co, L=L, ld=z.stride(1), mode=0, eps=1e-5, x=z, y=y,
+                                                     stats=stats, mr=mr), st)
+            zs.append(z)
+            mrs.append(mr)
+            feat = y
+        ctx.meta = (n, C0, Cg, T, F, L)
+        ctx.save_for_backward(col, *zs, *mrs, *Ws)
+        return feat
+
+    @staticmethod
+    def backward(ctx, g):
+        n, C0, Cg, T, F, L = ctx.meta
+        saved = ctx.saved_tensors
+        col, zs, mrs, Ws = saved[0], saved[1:6], saved[6:11], saved[11:16]
+        dev = col.device
+        st = _stream()
+        g = as_act(g)
+        Ctot = C0 + 4 * Cg
+        dcol = new_act(n, 9 * Ctot, L, dev)
+        grads = [None] * 10
+        for k in range(4, -1, -1):
+            z, mr = zs[k], mrs[k]
+            Co = z.shape[1]
+            c_hi = C0 + k * Cg
+            if g.stride(1) != z.stride(1):
+                raise RuntimeError("dense block backward: stride mismatch")
+            gz = new_act(n, Co, L, dev)
+            stats = torch.empty((n * Co, 2), dtype=torch.float64, device=dev)
+            _lib.call("wesep_b200_elu_in_bwd", _args("WesepEluInArgs", rows=n * Co, L=L, ld=z.stride(1), mode=0, eps=1e-5, x=z,
+                                                     stats=stats, mr=mr, gy=g, gx=gz), st)
+            W2 = Ws[k].reshape(Co, 9 * c_hi)
+            dW = torch.zeros_like(W2)
+            conv1x1_dw_raw(gz, col[:, :9 * c_hi], dW)
+            grads[2 * k] = dW.view(Ws[k].shape)
+            grads[2 * k + 1] = rowsum_raw(gz).sum(0)
+            rows = dcol[:, :9 * c_hi]
+            if k == 4:
+                conv1x1_raw(gz, W2, True, 9 * c_hi, Y=rows)
+            else:
+                conv1x1_raw(gz, W2, True, 9 * c_hi, epi=2, R=rows, Y=rows)
+            # gradient of the map this convolution's input list ends with (y_k, or x when k == 0): its rows are complete now
+            Cf, c_lo = (Cg, c_hi - Cg) if k > 0 else (C0, 0)
+            gmap = new_act(n, Cf, L, dev)
+            src = dcol[:, 9 * c_lo:9 * (c_lo + Cf)]
+            _lib.call("wesep_b200_im2col3x3_bwd", _i2c_args(n, Cf, T, F, 1, gmap.stride(1), src, gcol=src, gx=gmap), st)
+            g = gmap
+        return (g if ctx.needs_input_grad[0] else None, None, None, *grads)
+
+
 class EluInFn(torch.autograd.Function):
     """mode 0: InstanceNorm(ELU(x)); mode 1: ELU(InstanceNorm(x)); per (n, c) plane, eps 1e-5, no affine."""
 
