@@ -687,6 +687,17 @@ typedef struct {
 } WesepRowStdArgs;
 int wesep_b200_rowstd(const WesepRowStdArgs* a, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * NCCL wrappers for the one collective of the path: the in-place all-reduce (SUM) of the flat gradient arena (replaces
+ * torch DDP's bucketed all-reduce behind wesep/bin/train.py:227-228).  libnccl.so.2 is bound with dlopen at the first call.
+ * The caller moves the 128-byte unique id from rank 0 to the other ranks over its own side channel.
+ * ---------------------------------------------------------------------------------------------- */
+int wesep_b200_nccl_available(void);                                      /* 1 if libnccl could be loaded */
+int wesep_b200_nccl_unique_id(void* id128);                               /* rank 0: ncclGetUniqueId into 128 bytes */
+int wesep_b200_nccl_comm_init_rank(void** comm, int nranks, const void* id128, int rank);   /* collective over all ranks */
+int wesep_b200_nccl_allreduce_flat(float* buf, int64_t count, void* comm, void* stream);    /* in place, SUM, async on `stream` */
+int wesep_b200_nccl_comm_destroy(void* comm);
+
 #ifdef __cplusplus
 }
 #endif

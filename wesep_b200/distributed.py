@@ -32,11 +32,53 @@ def shard_rows(n_total, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+class NcclComm:
+    """An NCCL communicator owned through the C-ABI (`wesep_b200_nccl_*`, include/wesep_b200.h): rank 0 draws the unique id,
+    the 128 bytes travel over the existing torch.distributed group (any backend), every rank joins.  `all_reduce(t)` enqueues
+    the in-place SUM on the current CUDA stream — no torch.distributed call on the data path."""
+
+    def __init__(self, group=None):
+        import ctypes
+        from wesep_b200 import _lib
+        if not (dist.is_initialized() and torch.cuda.is_available()):
+            raise RuntimeError("NcclComm needs an initialised process group (for the id exchange) and CUDA")
+        L = _lib.lib()
+        if not L.wesep_b200_nccl_available():
+            raise RuntimeError("libnccl.so.2 could not be loaded")
+        self._L, self._ct = L, ctypes
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        buf = ctypes.create_string_buffer(128)
+        if self.rank == 0 and L.wesep_b200_nccl_unique_id(buf) != 0:
+            raise RuntimeError("nccl_unique_id: " + L.wesep_b200_last_error().decode())
+        box = [bytes(buf.raw)]
+        dist.broadcast_object_list(box, src=0, group=group)
+        self._comm = ctypes.c_void_p()
+        rc = L.wesep_b200_nccl_comm_init_rank(ctypes.byref(self._comm), self.world, ctypes.c_char_p(box[0]), self.rank)
+        if rc != 0:
+            raise RuntimeError("nccl_comm_init_rank: " + L.wesep_b200_last_error().decode())
+
+    def all_reduce(self, t):
+        if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
+            raise RuntimeError("NcclComm.all_reduce: contiguous fp32 CUDA tensor expected")
+        ct = self._ct
+        self._L.wesep_b200_nccl_allreduce_flat.argtypes = [ct.c_void_p, ct.c_int64, ct.c_void_p, ct.c_void_p]
+        rc = self._L.wesep_b200_nccl_allreduce_flat(t.data_ptr(), t.numel(), self._comm, torch.cuda.current_stream().cuda_stream)
+        if rc != 0:
+            raise RuntimeError("nccl_allreduce_flat: " + self._L.wesep_b200_last_error().decode())
+
+    def close(self):
+        if self._comm:
+            self._L.wesep_b200_nccl_comm_destroy(self._comm)
+            self._comm = None
+
+
 class GradAllReducer:
     """All-reduce(SUM) of a flat gradient buffer, in `n_buckets` contiguous pieces (reverse order, like
-    DDP's reverse-registration buckets) so later rounds can overlap them with the backward pass."""
+    DDP's reverse-registration buckets) so later rounds can overlap them with the backward pass.
+    `direct=True` (or WESEP_NCCL_DIRECT=1) routes the collective through the C-ABI NCCL wrappers on the current stream
+    instead of torch.distributed (CUDA tensors only)."""
 
-    def __init__(self, flat_grad, group=None, n_buckets=1):
+    def __init__(self, flat_grad, group=None, n_buckets=1, direct=None):
         self.flat = flat_grad
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -44,9 +86,16 @@ class GradAllReducer:
         step = (n + n_buckets - 1) // n_buckets
         step = (step + 3) // 4 * 4
         self.bounds = [(lo, min(lo + step, n)) for lo in range(0, n, step)]
+        if direct is None:
+            direct = os.environ.get("WESEP_NCCL_DIRECT", "0") == "1"
+        self.comm = NcclComm(group) if (direct and self.world > 1 and flat_grad.is_cuda) else None
 
     def all_reduce(self, async_op=False):
         if self.world == 1:
+            return []
+        if self.comm is not None:                       # stream-ordered: nothing to wait for on the host
+            for lo, hi in reversed(self.bounds):
+                self.comm.all_reduce(self.flat[lo:hi])
             return []
         works = []
         for lo, hi in reversed(self.bounds):
