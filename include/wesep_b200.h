@@ -698,6 +698,17 @@ int wesep_b200_nccl_comm_init_rank(void** comm, int nranks, const void* id128, i
 int wesep_b200_nccl_allreduce_flat(float* buf, int64_t count, void* comm, void* stream);    /* in place, SUM, async on `stream` */
 int wesep_b200_nccl_comm_destroy(void* comm);
 
+/* "Consistent" in-model enrollment features (`spk_feat: False`, `feat_type: consistent`; wesep/models/bsrnn.py:231-241,343-351 and
+ * the same block in convtasnet.py / dpccn.py / tfgridnet.py): PreEmphasis (wesep/modules/common/speaker.py:10-23), then
+ * torchaudio.transforms.MelSpectrogram(n_fft = win, hop = stride, f_min 20, hamming window, power 2) + 1e-8, log, minus the mean
+ * over frames, permuted to [B, frames, n_mels].  The STFT and the mel projection run on wesep_b200_frames / wesep_b200_conv1x1. */
+typedef struct { int n, L; const float* x; int64_t ldx; float coef; float* y; int64_t ldy; } WesepPreEmphArgs;
+int wesep_b200_preemphasis(const WesepPreEmphArgs* a, void* stream);     /* y[t] = x[t] - coef x[t-1], x[-1] := x[1] (reflect) */
+typedef struct { int n, F, T; const float* spec; int64_t ld, bs; float* pw; int64_t ldp, bsp; } WesepPowerSpecArgs;
+int wesep_b200_power_spec(const WesepPowerSpecArgs* a, void* stream);    /* pw[n][f][t] = re^2 + im^2 (spec rows [0,F) re, [F,2F) im) */
+typedef struct { int n, M, T; const float* mel; int64_t ld; float eps; float* out; } WesepLogCmnArgs;
+int wesep_b200_log_cmn(const WesepLogCmnArgs* a, void* stream);          /* out[n][t][m] = log(mel[n][m][t] + eps) - its mean over t */
+
 #ifdef __cplusplus
 }
 #endif

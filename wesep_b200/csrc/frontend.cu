@@ -257,6 +257,55 @@ __global__ void __launch_bounds__(512) fbank_cmn_kernel(WesepFbankArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------ "consistent" features
+// The in-model enrollment features of the recipes with `spk_feat: False`, `feat_type: consistent`
+// (wesep/models/bsrnn.py:231-241,343-351 and the same block in convtasnet / dpccn / tfgridnet): PreEmphasis
+// (wesep/modules/common/speaker.py:10-23) -> torchaudio MelSpectrogram (hamming, power 2, HTK mel) + 1e-8 -> log -> minus the
+// mean over frames -> [B, frames, n_mels].  The STFT and the mel projection are the DFT / pointwise GEMMs; these three
+// kernels are the elementwise rest.
+__global__ void __launch_bounds__(256) preemph_kernel(WesepPreEmphArgs a) {
+  const int r = blockIdx.y;
+  const float* x = a.x + (int64_t)r * a.ldx;
+  float* y = a.y + (int64_t)r * a.ldy;
+  for (int t = blockIdx.x * 256 + threadIdx.x; t < a.L; t += gridDim.x * 256) {
+    const float prev = t > 0 ? __ldg(x + t - 1) : __ldg(x + (a.L > 1 ? 1 : 0));      // F.pad(.., (1, 0), "reflect")
+    y[t] = __fmaf_rn(-a.coef, prev, __ldg(x + t));
+  }
+}
+// pw[n][f][t] = re^2 + im^2 from spec rows [0, F) (real) and [F, 2F) (imaginary)
+__global__ void __launch_bounds__(256) power_spec_kernel(WesepPowerSpecArgs a) {
+  const int f = blockIdx.y, n = blockIdx.z;
+  const float* re = a.spec + (int64_t)n * a.bs + (int64_t)f * a.ld;
+  const float* im = re + (int64_t)a.F * a.ld;
+  float* pw = a.pw + (int64_t)n * a.bsp + (int64_t)f * a.ldp;
+  for (int t = blockIdx.x * 256 + threadIdx.x; t < a.T; t += gridDim.x * 256) {
+    const float r = __ldg(re + t), i = __ldg(im + t);
+    pw[t] = fmaf(r, r, i * i);
+  }
+}
+// out[n][t][m] = log(mel[n][m][t] + eps) - mean_t log(mel[n][m][t] + eps)     (one CTA per (m, n))
+__global__ void __launch_bounds__(256) log_cmn_kernel(WesepLogCmnArgs a) {
+  __shared__ double red[8];
+  __shared__ float s_mean;
+  const int m = blockIdx.x, n = blockIdx.y, tid = threadIdx.x;
+  const float* x = a.mel + ((int64_t)n * a.M + m) * a.ld;
+  double s = 0.0;
+  for (int t = tid; t < a.T; t += 256) s += (double)logf(__ldg(x + t) + a.eps);
+  s = warp_sum(s);
+  if ((tid & 31) == 0) red[tid >> 5] = s;
+  __syncthreads();
+  if (tid == 0) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += red[w];
+    s_mean = (float)(v / (double)a.T);
+  }
+  __syncthreads();
+  const float mean = s_mean;
+  float* out = a.out + (int64_t)n * a.T * a.M + m;
+  for (int t = tid; t < a.T; t += 256) out[(int64_t)t * a.M] = logf(__ldg(x + t) + a.eps) - mean;
+}
+
 }  // namespace wb
 
 using namespace wb;
@@ -296,5 +345,25 @@ extern "C" int wesep_b200_fbank(const WesepFbankArgs* a, void* stream) {
     fbank_cmn_kernel<<<a->n, 512, 0, st>>>(*a);
     WB_LAUNCH_CHECK("fbank_cmn");
   }
+  return 0;
+}
+
+extern "C" int wesep_b200_preemphasis(const WesepPreEmphArgs* a, void* stream) {
+  if (!a || a->n <= 0 || a->n > 65535 || a->L <= 0 || a->ldx < a->L || a->ldy < a->L || !a->x || !a->y) return fail(-1, "preemphasis: bad arguments");
+  preemph_kernel<<<dim3(cdiv(a->L, 2048), a->n), 256, 0, (cudaStream_t)stream>>>(*a);
+  WB_LAUNCH_CHECK("preemphasis");
+  return 0;
+}
+extern "C" int wesep_b200_power_spec(const WesepPowerSpecArgs* a, void* stream) {
+  if (!a || a->n <= 0 || a->n > 65535 || a->F <= 0 || a->F > 65535 || a->T <= 0 || a->ld < a->T || a->ldp < a->T || !a->spec || !a->pw)
+    return fail(-1, "power_spec: bad arguments");
+  power_spec_kernel<<<dim3(cdiv(a->T, 1024), a->F, a->n), 256, 0, (cudaStream_t)stream>>>(*a);
+  WB_LAUNCH_CHECK("power_spec");
+  return 0;
+}
+extern "C" int wesep_b200_log_cmn(const WesepLogCmnArgs* a, void* stream) {
+  if (!a || a->n <= 0 || a->n > 65535 || a->M <= 0 || a->T <= 0 || a->ld < a->T || !a->mel || !a->out) return fail(-1, "log_cmn: bad arguments");
+  log_cmn_kernel<<<dim3(a->M, a->n), 256, 0, (cudaStream_t)stream>>>(*a);
+  WB_LAUNCH_CHECK("log_cmn");
   return 0;
 }

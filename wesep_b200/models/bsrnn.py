@@ -124,9 +124,8 @@ class BSRNN(nn.Module):
         self.spk_transform = nn.Identity()
         if joint_training:                                         # bsrnn.py:216-250
             from wesep_b200.modules.speaker.resnet import get_speaker_model
-            if not spk_feat:
-                raise NotImplementedError("spk_feat=False (fbank computed inside the model from raw enrollment audio, "
-                                          "bsrnn.py:231-241) is not built: the recipes feed fbank features (bsrnn.yaml:15,82)")
+            if not spk_feat and feat_type != "consistent":
+                raise NotImplementedError("spk_feat=False is built for feat_type='consistent' (bsrnn.py:231-241)")
             self.spk_model = get_speaker_model(spk_model)(**(spk_args or {}))
             if spk_model_init:
                 pretrained = torch.load(spk_model_init, map_location="cpu")
@@ -140,8 +139,14 @@ class BSRNN(nn.Module):
             if spk_model_freeze:
                 for param in self.spk_model.parameters():
                     param.requires_grad = False
-            self.preEmphasis = nn.Identity()
-            self.spk_encoder = nn.Identity()
+            if not spk_feat:                                       # bsrnn.py:231-241: features computed inside the model
+                from wesep_b200.modules.speaker.consistent import MelSpectrogram, PreEmphasis
+                self.preEmphasis = PreEmphasis()
+                self.spk_encoder = MelSpectrogram(sample_rate=sr, n_fft=win, hop_length=stride, f_min=20.0,
+                                                  n_mels=(spk_args or {})["feat_dim"])
+            else:
+                self.preEmphasis = nn.Identity()
+                self.spk_encoder = nn.Identity()
             self.pred_linear = nn.Linear(spk_emb_dim, spksInTrain) if multi_task else nn.Identity()
         self.BN = nn.ModuleList([nn.Sequential(nn.GroupNorm(1, bw * 2, self.eps), nn.Conv1d(bw * 2, feature_dim, 1))
                                  for bw in self.band_width])
@@ -244,6 +249,9 @@ class BSRNN(nn.Module):
         predict_speaker_lable = torch.zeros((), device=dev)          # dummy, bsrnn.py:340-341 (a fill kernel: graph-capturable)
         spk_in = embeddings
         if self.joint_training:                                    # bsrnn.py:342-357
+            if not self.spk_feat:
+                from wesep_b200.modules.speaker.consistent import consistent_features
+                spk_in = consistent_features(spk_in, self.preEmphasis, self.spk_encoder)
             tmp = self.spk_model(spk_in)
             spk_in = tmp[-1] if isinstance(tmp, tuple) else tmp
             if self.multi_task:

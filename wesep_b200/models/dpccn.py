@@ -165,9 +165,8 @@ class DPCCN(nn.Module):
         self.spk_transform = nn.Identity()
         if joint_training:                                         # dpccn.py:70-105
             from wesep_b200.modules.speaker.resnet import get_speaker_model
-            if not spk_feat:
-                raise NotImplementedError("spk_feat=False (mel features computed inside the model, dpccn.py:88-99) is not "
-                                          "built: the recipes feed fbank features (dpccn.yaml:15,80)")
+            if not spk_feat and feat_type != "consistent":
+                raise NotImplementedError("spk_feat=False is built for feat_type='consistent' (dpccn.py:88-99)")
             self.spk_model = get_speaker_model(spk_model)(**(spk_args or {}))
             if spk_model_init:
                 pretrained = torch.load(spk_model_init, map_location="cpu")
@@ -181,8 +180,14 @@ class DPCCN(nn.Module):
             if spk_model_freeze:
                 for param in self.spk_model.parameters():
                     param.requires_grad = False
-            self.preEmphasis = nn.Identity()
-            self.spk_encoder = nn.Identity()
+            if not spk_feat:                                       # dpccn.py:88-99
+                from wesep_b200.modules.speaker.consistent import MelSpectrogram, PreEmphasis
+                self.preEmphasis = PreEmphasis()
+                self.spk_encoder = MelSpectrogram(sample_rate=sr, n_fft=win, hop_length=stride, f_min=20.0,
+                                                  n_mels=(spk_args or {})["feat_dim"])
+            else:
+                self.preEmphasis = nn.Identity()
+                self.spk_encoder = nn.Identity()
             self.pred_linear = nn.Linear(spk_emb_dim, spksInTrain) if multi_task else nn.Identity()
         self.spk_fuse = SpeakerFuseLayer(embed_dim=spk_emb_dim, feat_dim=feature_dim, fuse_type=spk_fuse_type)
         self.tcn_layers = nn.Sequential(*[
@@ -273,6 +278,9 @@ class DPCCN(nn.Module):
         predict_speaker_lable = torch.zeros((), device=dev)          # dummy, dpccn.py:229-230
         spk_in = aux
         if self.joint_training:                                    # dpccn.py:231-249
+            if not self.spk_feat:
+                from wesep_b200.modules.speaker.consistent import consistent_features
+                spk_in = consistent_features(spk_in, self.preEmphasis, self.spk_encoder)
             tmp = self.spk_model(spk_in)
             spk_in = tmp[-1] if isinstance(tmp, tuple) else tmp
             if self.multi_task:
