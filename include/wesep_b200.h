@@ -406,6 +406,8 @@ typedef struct {
   const float* x; const float* gamma; const float* beta; float eps;
   float* y; double* stats;
   const float* gy; float* dx; float* dgamma; float* dbeta;
+  double* bsum;          /* bwd workspace [n][2] for rows of >= 2^19 elements (a (chunk, channel, row) grid with fp64 atomics instead
+                            of one CTA per row: TF-GridNet's utterance-wide GroupNorm); may be NULL for shorter rows */
 } WesepGroupNorm1Args;
 int wesep_b200_groupnorm1_fwd(const WesepGroupNorm1Args* a, void* stream);
 int wesep_b200_groupnorm1_bwd(const WesepGroupNorm1Args* a, void* stream);

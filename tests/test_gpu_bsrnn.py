@@ -232,7 +232,8 @@ def test_lstm_second_backward_raises():
         h.sum().backward()
 
 
-@pytest.mark.parametrize("n,C,T,sliced", [(5, 6, 501, False), (70, 16, 32, False), (3, 128, 501, True), (9, 32, 37, True)])
+@pytest.mark.parametrize("n,C,T,sliced", [(5, 6, 501, False), (70, 16, 32, False), (3, 128, 501, True), (9, 32, 37, True),
+                                            (2, 16, 40003, False), (2, 8, 70001, True)])   # the last two: wide rows (>= 2^19 elements)
 def test_group_norm1(n, C, T, sliced):
     """GroupNorm(1, C) one-CTA-per-row kernels vs torch.nn.functional.group_norm in fp64 (forward, dx, dgamma, dbeta);
     `sliced`: the input is a channel slice of a larger act tensor (batch stride > C * ld)."""

@@ -159,3 +159,18 @@ def test_online_mixer_rows():
     random.seed(4)
     seen = [r[0] for r in OnlineMixer(utts, DEV, chunk_len=48000).draw(6)[0]]
     assert sorted(seen) == list(range(6))
+
+
+@pytest.mark.parametrize("name,win,hop,lens", [("w512", 512, 128, [24000, 24000]), ("w128", 128, 64, [9001])])
+def test_consistent_features_golden(name, win, hop, lens):
+    """In-model enrollment features (spk_feat False, feat_type consistent; bsrnn.py:345-351) vs the REAL reference PreEmphasis +
+    torchaudio MelSpectrogram (tests/golden/consistent_feats.npz).  Log-mel after mean removal, fp32 on both sides: the
+    low-energy TF-GridNet bins (80 mel filters over 65 frequency bins leave empty filters = log(1e-8)) agree exactly."""
+    from wesep_b200.modules.speaker.consistent import MelSpectrogram, PreEmphasis, consistent_features
+    ref = np.load("tests/golden/consistent_feats.npz")[name]
+    x = torch.from_numpy(np.stack(frontend_waves(33, lens))).to(DEV)
+    pre, enc = PreEmphasis().to(DEV), MelSpectrogram(16000, win, hop, 20.0, 80).to(DEV)
+    got = consistent_features(x, pre, enc).cpu().numpy()
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() <= 2e-3, np.abs(got - ref).max()
+    assert np.sqrt(((got - ref) ** 2).mean()) <= 1e-4

@@ -116,3 +116,29 @@ def test_bsrnn_yaml_model_args_construct():
                            spk_model_init=False, spk_args=dict(feat_dim=80, embed_dim=256, pooling_func="TSTP", two_emb_layer=False),
                            spk_emb_dim=256, spk_model_freeze=False, spk_feat=True, feat_type="consistent", multi_task=False)
     assert sum(p.numel() for p in m.parameters()) == 28069608
+
+
+def test_bsrnn_joint_training_raw_enrollment():
+    """`spk_feat: False`, `feat_type: consistent` (bsrnn.yaml:15 alternative): the model computes the enrollment features itself
+    (pre-emphasis + log-mel + mean removal, no gradient) and trains the speaker encoder through them; equals feeding the same
+    features to the `spk_feat: True` model."""
+    from wesep_b200 import synth
+    from wesep_b200.models import get_model
+    from wesep_b200.modules.speaker.consistent import consistent_features
+    args = dict(sr=16000, win=512, stride=128, feature_dim=16, num_repeat=1, spk_fuse_type="multiply", use_spk_transform=False,
+                multi_fuse=False, joint_training=True, spk_model="ResNet18", spk_model_init=False,
+                spk_args=dict(feat_dim=80, embed_dim=256, pooling_func="TSTP", two_emb_layer=False), spk_emb_dim=256,
+                spk_model_freeze=False, feat_type="consistent", multi_task=False)
+    torch.manual_seed(0)
+    m_raw = get_model("BSRNN")(**dict(args, spk_feat=False)).to(DEV).train()
+    m_fb = get_model("BSRNN")(**dict(args, spk_feat=True)).to(DEV).train()
+    sd = {k: v for k, v in m_raw.state_dict().items() if not k.startswith(("preEmphasis", "spk_encoder"))}
+    m_fb.load_state_dict(sd)
+    b = synth.make_batch(2, T=6000, Te=9000, seed=3, device=DEV)
+    est_raw, emb_raw = m_raw(b["wav_mix"], b["spk_embeds"])
+    feats = consistent_features(b["spk_embeds"], m_raw.preEmphasis, m_raw.spk_encoder)
+    assert feats.shape == (2, 1 + 9000 // 128, 80)
+    est_fb, emb_fb = m_fb(b["wav_mix"], feats)
+    assert torch.equal(est_raw, est_fb) and torch.equal(emb_raw, emb_fb)
+    est_raw.square().mean().backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m_raw.parameters())

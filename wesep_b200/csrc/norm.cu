@@ -121,6 +121,94 @@ __global__ void __launch_bounds__(GN_THREADS) gn1_bwd_kernel(WesepGroupNorm1Args
   }
 }
 
+// ------------------------------------------------------------------------------------------------ wide rows
+// Rows of millions of elements (TF-GridNet's GroupNorm(1, emb_dim) over (C, T, F) of an utterance, tfgridnet.py:174-176): one CTA
+// per row would leave all but n SMs idle, so a (chunk, channel, row) grid accumulates the row sums with fp64 atomics.
+constexpr int GNW_CHUNK = 8192;
+constexpr int64_t GNW_MIN_ROW = 1 << 19;      // rows of at least this many elements take the wide path
+
+__global__ void __launch_bounds__(256) gn1w_stats_kernel(WesepGroupNorm1Args a) {
+  __shared__ double red[2][8];
+  const int c = blockIdx.y, n = blockIdx.z, tid = threadIdx.x;
+  const float* x = a.x + (int64_t)n * a.bsx + (int64_t)c * a.ldx;
+  const int c0 = blockIdx.x * GNW_CHUNK, end = min(c0 + GNW_CHUNK, a.T);
+  double s0 = 0.0, s1 = 0.0;
+  for (int t = c0 + tid; t < end; t += 256) {
+    const double v = (double)__ldg(x + t);
+    s0 += v; s1 = fma(v, v, s1);
+  }
+  s0 = warp_sum(s0); s1 = warp_sum(s1);
+  if ((tid & 31) == 0) { red[0][tid >> 5] = s0; red[1][tid >> 5] = s1; }
+  __syncthreads();
+  if (tid < 2) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[tid][w];
+    atomicAdd(a.stats + (int64_t)n * 2 + tid, s);
+  }
+}
+__device__ __forceinline__ void gnw_mean_rstd(const WesepGroupNorm1Args& a, int n, float& mu, float& rs) {
+  const double cnt = (double)a.C * (double)a.T;
+  const double mean = a.stats[(int64_t)n * 2] / cnt;
+  const double var = fmax(a.stats[(int64_t)n * 2 + 1] / cnt - mean * mean, 0.0);
+  mu = (float)mean;
+  rs = (float)(1.0 / sqrt(var + (double)a.eps));
+}
+__global__ void __launch_bounds__(256) gn1w_apply_kernel(WesepGroupNorm1Args a) {
+  const int c = blockIdx.y, n = blockIdx.z, tid = threadIdx.x;
+  float mu, rs;
+  gnw_mean_rstd(a, n, mu, rs);
+  const float g = __ldg(a.gamma + c) * rs, b = __ldg(a.beta + c);
+  const float* x = a.x + (int64_t)n * a.bsx + (int64_t)c * a.ldx;
+  float* y = a.y + (int64_t)n * a.bsy + (int64_t)c * a.ldy;
+  const int c0 = blockIdx.x * GNW_CHUNK, end = min(c0 + GNW_CHUNK, a.T);
+  for (int t = c0 + tid; t < end; t += 256) y[t] = fmaf(__ldg(x + t) - mu, g, b);
+}
+__global__ void __launch_bounds__(256) gn1w_bwd_reduce_kernel(WesepGroupNorm1Args a) {
+  __shared__ double red[2][8];
+  const int c = blockIdx.y, n = blockIdx.z, tid = threadIdx.x;
+  float mu, rs;
+  gnw_mean_rstd(a, n, mu, rs);
+  const float* x = a.x + (int64_t)n * a.bsx + (int64_t)c * a.ldx;
+  const float* gy = a.gy + (int64_t)n * a.bsg + (int64_t)c * a.ldg;
+  const int c0 = blockIdx.x * GNW_CHUNK, end = min(c0 + GNW_CHUNK, a.T);
+  double s0 = 0.0, s1 = 0.0;
+  for (int t = c0 + tid; t < end; t += 256) {
+    const float g = __ldg(gy + t);
+    s0 += (double)g;
+    s1 = fma((double)g, (double)((__ldg(x + t) - mu) * rs), s1);
+  }
+  s0 = warp_sum(s0); s1 = warp_sum(s1);
+  if ((tid & 31) == 0) { red[0][tid >> 5] = s0; red[1][tid >> 5] = s1; }
+  __syncthreads();
+  if (tid == 0) {
+    double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { v0 += red[0][w]; v1 += red[1][w]; }
+    atomicAdd(a.dbeta + c, (float)v0);
+    atomicAdd(a.dgamma + c, (float)v1);
+    const double gm = (double)__ldg(a.gamma + c);
+    atomicAdd(a.bsum + (int64_t)n * 2, gm * v0);
+    atomicAdd(a.bsum + (int64_t)n * 2 + 1, gm * v1);
+  }
+}
+__global__ void __launch_bounds__(256) gn1w_bwd_apply_kernel(WesepGroupNorm1Args a) {
+  const int c = blockIdx.y, n = blockIdx.z, tid = threadIdx.x;
+  float mu, rs;
+  gnw_mean_rstd(a, n, mu, rs);
+  const double cnt = (double)a.C * (double)a.T;
+  const float m0 = (float)(a.bsum[(int64_t)n * 2] / cnt), m1 = (float)(a.bsum[(int64_t)n * 2 + 1] / cnt);
+  const float gm = __ldg(a.gamma + c);
+  const float* x = a.x + (int64_t)n * a.bsx + (int64_t)c * a.ldx;
+  const float* gy = a.gy + (int64_t)n * a.bsg + (int64_t)c * a.ldg;
+  float* dx = a.dx + (int64_t)n * a.bsdx + (int64_t)c * a.lddx;
+  const int c0 = blockIdx.x * GNW_CHUNK, end = min(c0 + GNW_CHUNK, a.T);
+  for (int t = c0 + tid; t < end; t += 256) {
+    const float xh = (__ldg(x + t) - mu) * rs;
+    dx[t] = rs * (__ldg(gy + t) * gm - m0 - xh * m1);
+  }
+}
+
 }  // namespace wb
 
 using namespace wb;
@@ -138,12 +226,32 @@ static int check_gn(const WesepGroupNorm1Args* a, bool bwd) {
 }
 extern "C" int wesep_b200_groupnorm1_fwd(const WesepGroupNorm1Args* a, void* stream) {
   if (int rc = check_gn(a, false)) return rc;
+  if ((int64_t)a->C * a->T >= GNW_MIN_ROW && a->n <= 65535) {
+    cudaStream_t st = (cudaStream_t)stream;
+    WB_CUDA(cudaMemsetAsync(a->stats, 0, (size_t)a->n * 2 * sizeof(double), st));
+    const dim3 grid(cdiv(a->T, GNW_CHUNK), a->C, a->n);
+    gn1w_stats_kernel<<<grid, 256, 0, st>>>(*a);
+    WB_LAUNCH_CHECK("groupnorm1_wide_stats");
+    gn1w_apply_kernel<<<grid, 256, 0, st>>>(*a);
+    WB_LAUNCH_CHECK("groupnorm1_wide_apply");
+    return 0;
+  }
   gn1_fwd_kernel<<<a->n, GN_THREADS, 0, (cudaStream_t)stream>>>(*a);
   WB_LAUNCH_CHECK("groupnorm1_fwd");
   return 0;
 }
 extern "C" int wesep_b200_groupnorm1_bwd(const WesepGroupNorm1Args* a, void* stream) {
   if (int rc = check_gn(a, true)) return rc;
+  if ((int64_t)a->C * a->T >= GNW_MIN_ROW && a->n <= 65535 && a->bsum) {
+    cudaStream_t st = (cudaStream_t)stream;
+    WB_CUDA(cudaMemsetAsync(a->bsum, 0, (size_t)a->n * 2 * sizeof(double), st));
+    const dim3 grid(cdiv(a->T, GNW_CHUNK), a->C, a->n);
+    gn1w_bwd_reduce_kernel<<<grid, 256, 0, st>>>(*a);
+    WB_LAUNCH_CHECK("groupnorm1_wide_bwd_reduce");
+    gn1w_bwd_apply_kernel<<<grid, 256, 0, st>>>(*a);
+    WB_LAUNCH_CHECK("groupnorm1_wide_bwd_apply");
+    return 0;
+  }
   gn1_bwd_kernel<<<a->n, GN_THREADS, 0, (cudaStream_t)stream>>>(*a);
   WB_LAUNCH_CHECK("groupnorm1_bwd");
   return 0;

@@ -995,10 +995,11 @@ class GroupNorm1Fn(torch.autograd.Function):
         gy = gy if is_act_slice(gy) else as_act(gy)
         dx = new_act(n, C, T, x.device)
         acc = torch.zeros(2 * C, dtype=torch.float32, device=x.device)
+        bsum = torch.empty((n, 2), dtype=torch.float64, device=x.device)
         _lib.call("wesep_b200_groupnorm1_bwd",
                   _args("WesepGroupNorm1Args", n=n, C=C, T=T, ldx=x.stride(1), bsx=x.stride(0), ldg=gy.stride(1), bsg=gy.stride(0),
                         lddx=dx.stride(1), bsdx=dx.stride(0), x=x, gamma=w, beta=b, eps=ctx.eps, stats=stats, gy=gy, dx=dx,
-                        dgamma=acc[:C], dbeta=acc[C:]), _stream())
+                        dgamma=acc[:C], dbeta=acc[C:], bsum=bsum), _stream())
         return dx, acc[:C], acc[C:], None
 
 
