@@ -36,7 +36,8 @@ int wesep_b200_version(void);
 const char* wesep_b200_last_error(void);
 /* Number of kernels launched by this library in this process (diagnostic; bench.py gpu_launches). */
 uint64_t wesep_b200_launch_count(void);
-/* GEMM precision: 0 = 3xTF32 split (fp32-grade, default), 1 = single-pass TF32. Process-wide. */
+/* GEMM precision: 0 = fp32-grade split products (default), 1 = single-pass TF32. Process-wide DEFAULT: every GEMM entry point
+ * also takes the choice per call (`mode_sel` / `backend_sel` of WesepGemmArgs / WesepGemmDwArgs). */
 int wesep_b200_set_gemm_mode(int mode);
 /* GEMM backend: 0 = legacy tensor path (mma.sync), 1 (default) = tcgen05/UMMA + TMA + TMEM where the shape is eligible
  * (M % 128 == 0, Kd % 16 == 0, Kd <= 512, a workspace is supplied); other shapes stay on backend 0. Process-wide. */
@@ -141,6 +142,8 @@ typedef struct {
   double* ch_stats;                           /* optional [M][2]: += per-channel sum / sumsq of Y (BatchNorm) */
   int64_t bsx, bsy, bsr, bsy2;                /* batch strides in floats; 0 = dense (C*ld): channel-slices of wider tensors */
   void* ws; int64_t ws_bytes;                 /* optional workspace (>= wesep_b200_gemm_ws_bytes(M, Kd)) enabling backend 1 */
+  int mode_sel, backend_sel;                  /* per call: 0 = the process default (wesep_b200_set_gemm_mode / _backend), 1 / 2 = mode or
+                                                 backend 0 / 1 for this launch only */
 } WesepGemmArgs;
 int wesep_b200_conv1x1(const WesepGemmArgs* a, void* stream);
 
@@ -158,6 +161,7 @@ typedef struct {
   const double* row_stats_b; double stat_count; float stat_eps;
   int64_t bsa, bsb;             /* batch strides in floats; 0 = dense */
   int64_t ldc;                  /* row stride of C; 0 = N */
+  int mode_sel, backend_sel;    /* per call, as in WesepGemmArgs */
 } WesepGemmDwArgs;
 int wesep_b200_conv1x1_dw(const WesepGemmDwArgs* a, void* stream);
 

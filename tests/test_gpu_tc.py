@@ -51,6 +51,34 @@ def test_tc_is_used_and_counts_launches():
     _lib.set_gemm_backend(1)
 
 
+def test_gemm_backend_and_mode_per_call():
+    """`mode_sel` / `backend_sel` of the GEMM argument structs choose the kernel for ONE launch without touching the
+    process-wide default: launch counts tell the backends apart, the error level tells the precision modes apart."""
+    from wesep_b200 import _lib, ops
+    x = ops.new_act(2, 128, 600, DEV)
+    x.copy_(rnd(2, 128, 600, seed=1))
+    W = rnd(128, 128, seed=2, scale=1 / math.sqrt(128))
+    ref = torch.einsum("mk,nkt->nmt", W.double(), x.double())
+    before = _lib.launch_count()
+    y1 = ops.conv1x1_raw(x, W, False, 128, backend=1)
+    assert _lib.launch_count() - before == 2                    # weight split + tcgen05 GEMM
+    before = _lib.launch_count()
+    y0 = ops.conv1x1_raw(x, W, False, 128, backend=0)
+    assert _lib.launch_count() - before == 1                    # mma.sync GEMM
+    before = _lib.launch_count()
+    ops.conv1x1_raw(x, W, False, 128)
+    assert _lib.launch_count() - before == 2                    # the process default (tcgen05) is untouched
+    check("tcgen05", y1, ref, 1e-5)
+    check("mma.sync", y0, ref, 1e-5)
+    y_fast = ops.conv1x1_raw(x, W, False, 128, mode=1)          # single-pass TF32 for this call only
+    e = float((y_fast.double() - ref).norm() / ref.norm())
+    assert 1e-5 < e < 2e-3, e
+    check("default again", ops.conv1x1_raw(x, W, False, 128), ref, 1e-5)
+    dW = torch.zeros(128, 128, device=DEV)
+    ops.conv1x1_dw_raw(y1, x, dW, backend=0, mode=0)
+    check("dw", dW, torch.einsum("nmt,nkt->mk", y1.double(), x.double()), 1e-5)
+
+
 def test_tcn_block_full_size_backends(backend):
     _block_case(False, n=2, B=256, H=512, T=6399, dil=16, seed=21)
 

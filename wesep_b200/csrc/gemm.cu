@@ -5,7 +5,7 @@ namespace wb {
 
 int launch_gemm_wx(const GemmWxP& p, bool a_trans, int pro, int epi, cudaStream_t st) {
   if (p.n <= 0 || p.M <= 0 || p.Kd <= 0 || p.T <= 0) return fail(-1, "gemm_wx: empty shape");
-  if (g_gemm_backend == 1 && g_gemm_mode == 0 && p.ws && (size_t)p.ws_bytes >= gemm_wx_tc_ws_bytes(p.M, p.Kd) &&
+  if (eff_gemm_backend(p.backend_sel) == 1 && eff_gemm_mode(p.mode_sel) == 0 && p.ws && (size_t)p.ws_bytes >= gemm_wx_tc_ws_bytes(p.M, p.Kd) &&
       gemm_wx_tc_eligible(p, pro, epi))
     return launch_gemm_wx_tc(p, a_trans, pro, epi, p.ws, st);
   if ((p.ldx & 3) || (p.ldw & 3) || !aligned16(p.X) || !aligned16(p.W)) return fail(-1, "gemm_wx: ldx/ldw/base alignment");
@@ -175,7 +175,7 @@ template <int PRO>
 static int launch_gemm_dw_t(const GemmDwP& p, cudaStream_t st) {
   dim3 grid(cdiv(p.M, G_BM) * cdiv(p.N, G_BN), cdiv(p.T, p.t_chunk), p.n);
   size_t smem = (size_t)G_STAGES * (G_BM + G_BN) * G_A_LD * sizeof(float);
-  if (g_gemm_mode == 0) {
+  if (eff_gemm_mode(p.mode_sel) == 0) {
     auto k = gemm_dw_kernel<PRO, true>;
     WB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, G_THREADS, smem, st>>>(p);
@@ -189,7 +189,7 @@ static int launch_gemm_dw_t(const GemmDwP& p, cudaStream_t st) {
 }
 
 bool gemm_dw_uses_tc(const GemmDwP& p, int pro_b) {
-  return g_gemm_backend == 1 && g_gemm_mode == 0 && gemm_dw_tc_eligible(p, pro_b);
+  return eff_gemm_backend(p.backend_sel) == 1 && eff_gemm_mode(p.mode_sel) == 0 && gemm_dw_tc_eligible(p, pro_b);
 }
 
 int launch_gemm_dw(const GemmDwP& pin, int pro_b, cudaStream_t st) {
@@ -233,6 +233,8 @@ extern "C" int wesep_b200_conv1x1(const WesepGemmArgs* a, void* stream) {
   e.Y2 = a->Y2; e.ldy2 = a->ldy2; e.bsy2 = a->bsy2 ? a->bsy2 : (int64_t)a->M * a->ldy2;
   e.out_stats = a->out_stats; e.out_alpha = a->out_alpha; e.ch_stats = a->ch_stats;
   p.ws = a->ws; p.ws_bytes = a->ws_bytes;
+  if (a->mode_sel < 0 || a->mode_sel > 2 || a->backend_sel < 0 || a->backend_sel > 2) return fail(-2, "conv1x1: mode_sel / backend_sel must be 0..2");
+  p.mode_sel = a->mode_sel; p.backend_sel = a->backend_sel;
   if (a->epi < 0 || a->epi > 3) return fail(-2, "conv1x1: epi must be 0..3");
   if ((a->epi == 2 || a->epi == 3) && (!a->R || (a->ldr & 1))) return fail(-1, "conv1x1: residual/aux missing or odd ldr");
   if (a->epi == 3 && (!a->Y2 || (a->ldy2 & 1))) return fail(-1, "conv1x1: Y2 missing");
@@ -247,5 +249,7 @@ extern "C" int wesep_b200_conv1x1_dw(const WesepGemmDwArgs* a, void* stream) {
   p.C = a->C; p.ldc = a->ldc ? a->ldc : a->N; p.per_row = a->per_row;
   p.xb = XformP{a->alpha_b, a->ch_scale_b, a->ch_shift_b, a->row_stats_b, a->stat_count, a->stat_eps};
   p.t_chunk = 0;
+  if (a->mode_sel < 0 || a->mode_sel > 2 || a->backend_sel < 0 || a->backend_sel > 2) return fail(-2, "conv1x1_dw: mode_sel / backend_sel must be 0..2");
+  p.mode_sel = a->mode_sel; p.backend_sel = a->backend_sel;
   return launch_gemm_dw(p, a->pro_b, (cudaStream_t)stream);
 }

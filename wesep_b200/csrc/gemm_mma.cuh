@@ -69,6 +69,7 @@ struct GemmWxP {
   EpiP ep;
   void* ws; int64_t ws_bytes;   // optional workspace for the tcgen05 backend
   int ws_presplit;              // tcgen05 backend: `ws` already holds this weight's hi / lo tiles (skip the split launch)
+  int mode_sel, backend_sel;    // per-call precision mode / backend: 0 = the process default, otherwise value + 1
 };
 
 // tcgen05 backend (gemm_tc.cu)
@@ -76,6 +77,8 @@ bool gemm_wx_tc_eligible(const GemmWxP& p, int pro, int epi);
 size_t gemm_wx_tc_ws_bytes(int M, int Kd);
 int launch_gemm_wx_tc(const GemmWxP& p, bool a_trans, int pro, int epi, void* ws, cudaStream_t st);
 extern int g_gemm_backend;
+inline int eff_gemm_mode(int sel) { return sel > 0 ? sel - 1 : g_gemm_mode; }
+inline int eff_gemm_backend(int sel) { return sel > 0 ? sel - 1 : g_gemm_backend; }
 
 // ------------------------------------------------------------------------------------ epilogues
 template <int EPI>
@@ -389,7 +392,7 @@ template <bool A_TRANS, int PRO, int EPI>
 inline int launch_gemm_wx_t(const GemmWxP& p, cudaStream_t st) {
   dim3 grid(cdiv(p.T, G_BN), cdiv(p.M, G_BM), p.n);
   size_t smem = gemm_wx_smem(PRO, p.Kd);
-  if (g_gemm_mode == 0) {
+  if (eff_gemm_mode(p.mode_sel) == 0) {
     auto k = gemm_wx_kernel<A_TRANS, PRO, EPI, true>;
     WB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, G_THREADS, smem, st>>>(p);
@@ -414,6 +417,7 @@ struct GemmDwP {
   XformP xb;   // prologue on B: v = sc[c]*prelu(b)+sh[c] with sc = ch_scale*r_n, sh = ch_shift - ch_scale*mu_n*r_n
   int t_chunk; // time steps per CTA (multiple of G_BK)
   float* a_rowsum;  // optional, tcgen05 path only: += [n][M] sum_t A[n][m][t] (a by-product of the operand transform)
+  int mode_sel, backend_sel;   // as in GemmWxP
 };
 int launch_gemm_dw(const GemmDwP& p, int pro_b, cudaStream_t st);
 bool gemm_dw_uses_tc(const GemmDwP& p, int pro_b);   // true when launch_gemm_dw will take the tcgen05 path

@@ -110,7 +110,7 @@ def _sig(x):
 # --------------------------------------------------------------------------- raw calls
 def conv1x1_raw(x, W2d, w_trans, M, *, bias=None, row_bias=None, pro=0, alpha=None, ch_scale=None, ch_shift=None,
                 row_stats=None, stat_count=1.0, stat_eps=0.0, epi=0, R=None, Y=None, Y2=None, out_stats=None,
-                out_alpha=None, ch_stats=None):
+                out_alpha=None, ch_stats=None, mode=None, backend=None):
     n, Kd, T = x.shape
     if Y is None:
         Y = new_act(n, M, T, x.device)
@@ -119,7 +119,8 @@ def conv1x1_raw(x, W2d, w_trans, M, *, bias=None, row_bias=None, pro=0, alpha=No
               ch_shift=ch_shift, row_stats=row_stats, stat_count=float(stat_count), stat_eps=float(stat_eps), epi=epi,
               R=R, ldr=0 if R is None else R.stride(1), Y2=Y2, ldy2=0 if Y2 is None else Y2.stride(1),
               out_stats=out_stats, out_alpha=out_alpha, ch_stats=ch_stats, bsx=x.stride(0), bsy=Y.stride(0),
-              bsr=0 if R is None else R.stride(0), bsy2=0 if Y2 is None else Y2.stride(0))
+              bsr=0 if R is None else R.stride(0), bsy2=0 if Y2 is None else Y2.stride(0),
+              mode_sel=0 if mode is None else int(mode) + 1, backend_sel=0 if backend is None else int(backend) + 1)
     ws = gemm_ws(x.device)
     a.ws, a.ws_bytes = ws.data_ptr(), ws.numel()
     for t_ in (x, Y, R, Y2):
@@ -130,14 +131,15 @@ def conv1x1_raw(x, W2d, w_trans, M, *, bias=None, row_bias=None, pro=0, alpha=No
 
 
 def conv1x1_dw_raw(A, B, C, *, per_row=False, pro_b=0, alpha_b=None, ch_scale_b=None, ch_shift_b=None,
-                   row_stats_b=None, stat_count=1.0, stat_eps=0.0):
+                   row_stats_b=None, stat_count=1.0, stat_eps=0.0, mode=None, backend=None):
     """C[M][N] += sum_n sum_t A[n][M][t] * f(B[n][N][t])  (C dense, zero-initialised by the caller)."""
     n, M, T = A.shape
     N = B.shape[1]
     a = _args("WesepGemmDwArgs", n=n, M=M, N=N, T=T, A=A, lda=A.stride(1), B=B, ldb=B.stride(1), C=C, per_row=int(per_row),
               pro_b=pro_b, alpha_b=alpha_b, ch_scale_b=ch_scale_b, ch_shift_b=ch_shift_b, row_stats_b=row_stats_b,
               stat_count=float(stat_count), stat_eps=float(stat_eps), bsa=A.stride(0), bsb=B.stride(0),
-              ldc=C.stride(0) if C.dim() == 2 else C.stride(1))
+              ldc=C.stride(0) if C.dim() == 2 else C.stride(1),
+              mode_sel=0 if mode is None else int(mode) + 1, backend_sel=0 if backend is None else int(backend) + 1)
     if not (is_act_slice(A) and is_act_slice(B)) or C.stride(-1) != 1:
         raise RuntimeError("conv1x1_dw: operand layout")
     _lib.call("wesep_b200_conv1x1_dw", a, _stream())
