@@ -257,3 +257,47 @@ def test_group_norm1(n, C, T, sliced):
     check("dx", x.grad, x64.grad, 2e-5)
     check("dgamma", w.grad, w64.grad, 2e-5)
     check("dbeta", b.grad, b64.grad, 2e-5)
+
+
+def test_bsrnn_multi_golden():
+    """BSRNN_Multi (bsrnn_multi_optim.py:406-472): first and self-enrolled second estimate, the weighted loss of
+    the recipe (0.4 / 0.6) and every gradient vs the REAL reference run (tests/golden/bsrnn_multi_small.npz); under no_grad
+    the model returns the two-tuple of the first pass.  Raw-wave enrollment -> "consistent" features inside the model."""
+    import json, os
+    import numpy as np
+    from oracle import losses as olosses
+    from tests.util import SqTiny
+    from wesep_b200 import ops, synth
+    from wesep_b200.models import get_model
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bsrnn_multi_small.npz"))
+    meta = json.loads(str(z["meta"]))
+    m = get_model("BSRNN_Multi")(**dict(meta["args"], spk_args=dict(feat_dim=80, embed_dim=256, pooling_func="TSTP",
+                                                                      two_emb_layer=False)))
+    m.spk_model = SqTiny(80, 256)                       # the stand-in the golden run used (wespeaker is external)
+    params = {k: v for k, v in m.state_dict().items() if not k.startswith(("preEmphasis", "spk_encoder"))}
+    synth.fill_state_dict_(params, seed=meta["wseed"])
+    m = m.to(DEV).train()
+    b = synth.make_batch(meta["n"], T=meta["L"], Te=meta["Te"], seed=meta["dseed"], device=DEV)
+    out = m(b["wav_mix"], b["spk_embeds"])
+    assert len(out) == 4
+    s, self_s = out[0], out[1]
+    for i, est in enumerate((s, self_s)):
+        check(f"out{i}", est.detach(), torch.from_numpy(z[f"out{i}"]).to(DEV), 2e-3)
+        rows = olosses.sisdr_per_row(est.detach().double(), b["wav_targets"].double()).cpu().numpy()
+        assert np.max(np.abs(rows - z[f"sisdr_rows{i}"])) <= 0.01, (i, rows, z[f"sisdr_rows{i}"])
+    losses, _ = ops.sisdr_losses([s, self_s], b["wav_targets"])
+    loss = 0.4 * losses[0] + 0.6 * losses[1]
+    assert abs(float(loss.detach()) - float(z["loss"])) <= 2e-3
+    loss.backward()
+    for k, p in m.named_parameters():
+        ref_n, gn = float(z["gnorm/" + k]), float(p.grad.double().norm())
+        assert abs(gn - ref_n) <= 2e-3 * ref_n + 1e-5, (k, gn, ref_n)
+        rg = torch.from_numpy(z["ghead/" + k]).to(DEV).reshape(-1).double()
+        gg = p.grad.reshape(-1)[:rg.numel()].double()
+        if float(rg.norm()) > 1e-6:
+            assert float((rg * gg).sum() / (rg.norm() * gg.norm() + 1e-30)) >= 0.9995, k
+    m.eval()
+    with torch.no_grad():
+        out = m(b["wav_mix"], b["spk_embeds"])
+    assert len(out) == 2
+    check("eval", out[0], torch.from_numpy(z["eval_out0"]).to(DEV), 2e-3)

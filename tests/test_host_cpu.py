@@ -69,7 +69,7 @@ def test_model_registry_and_state_dict_contract():
                                 multi_task=True, spksInTrain=251)
     assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == ospex.state_dict_spec(cfg)
     with pytest.raises(NotImplementedError):
-        get_model("BSRNN_Multi")
+        get_model("BSRNN_Feats")
     with pytest.raises(RuntimeError):                  # pBSRNN: CUDA only (no fallback)
         get_model("BSRNN")(joint_training=False, use_spk_transform=False, feature_dim=16, num_repeat=1,
                            spk_fuse_type="multiply")(torch.zeros(1, 2000), torch.zeros(1, 256))

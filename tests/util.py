@@ -78,3 +78,16 @@ MIX_CASES = [("two_0db", 3, [20000, 17003], 8000, False),
 # name, seed, samples, dtype of the wave handed to compute_fbank (soundfile gives float64, torchaudio.load float32)
 FBANK_CASES = [("f64_4s", 8, 64000, np.float64), ("f32_1s", 9, 16400, np.float32), ("one_frame", 10, 400, np.float64),
                ("odd", 11, 12345, np.float64)]
+
+
+class SqTiny(torch.nn.Module):
+    """Stand-in speaker encoder for the BSRNN_Multi fixtures (the real one, wespeaker's, is an external package): energy per
+    mel bin averaged over frames, then Linear.  Returns wespeaker's (dummy, embedding) tuple.  Plain torch: test scaffolding on
+    both sides, not part of the path under test."""
+
+    def __init__(self, feat_dim=80, embed_dim=256, **kw):
+        super().__init__()
+        self.fc = torch.nn.Linear(feat_dim, embed_dim)
+
+    def forward(self, x):  # x [n, frames, feat_dim]
+        return torch.zeros((), device=x.device), self.fc((x ** 2).mean(1))

@@ -220,11 +220,14 @@ class BSRNN(nn.Module):
             return ops.RowAffineFn.apply(x, v, None)
         return ops.RowAffineFn.apply(x, None, v)
 
-    def forward(self, input, embeddings):
+    def _check(self, input, embeddings):
         if input.dim() != 2:
             raise RuntimeError("BSRNN expects [batch, samples]")
         if not (input.is_cuda and embeddings.is_cuda):
             raise RuntimeError("wesep_b200 kernels need CUDA tensors (no CPU fallback)")
+
+    def _analysis(self, input):
+        """STFT + band split (bsrnn.py:307-338): returns (spec [B, R, T] band-major re | im rows, features [B, nb*N, T])."""
         dev = input.device
         B, L = input.shape
         win, hop, N, nb = self.win, self.stride, self.feature_dim, self.nband
@@ -245,11 +248,13 @@ class BSRNN(nn.Module):
         for i, (o, bw) in enumerate(zip(offs, self.band_width)):
             Wbig[i * N:(i + 1) * N, o:o + 2 * bw] = self.BN[i][1].weight[:, :, 0]
         bbig = torch.cat([self.BN[i][1].bias for i in range(nb)])
-        x = ops.Conv1x1Fn.apply(xhat, Wbig, bbig, False, None)                            # [B, nb*N, T]
-        predict_speaker_lable = torch.zeros((), device=dev)          # dummy, bsrnn.py:340-341 (a fill kernel: graph-capturable)
-        spk_in = embeddings
+        return spec, ops.Conv1x1Fn.apply(xhat, Wbig, bbig, False, None)                   # [B, nb*N, T]
+
+    def _speaker(self, spk_in, raw_wave):
+        """bsrnn.py:340-360: (embedding [B, E], predict_speaker_lable).  `raw_wave`: compute the "consistent" features first."""
+        predict_speaker_lable = torch.zeros((), device=spk_in.device)   # dummy, bsrnn.py:340-341 (a fill kernel: graph-capturable)
         if self.joint_training:                                    # bsrnn.py:342-357
-            if not self.spk_feat:
+            if raw_wave:
                 from wesep_b200.modules.speaker.consistent import consistent_features
                 spk_in = consistent_features(spk_in, self.preEmphasis, self.spk_encoder)
             tmp = self.spk_model(spk_in)
@@ -258,7 +263,15 @@ class BSRNN(nn.Module):
                 predict_speaker_lable = ops.LinearFn.apply(spk_in, self.pred_linear.weight, self.pred_linear.bias)
             else:
                 predict_speaker_lable = spk_in                      # nn.Identity
-        emb = self.spk_transform(spk_in).float()
+        return self.spk_transform(spk_in).float(), predict_speaker_lable
+
+    def _separate(self, x, spec, emb, L):
+        """separator -> mask heads -> iSTFT (bsrnn.py:362-391): features [B, nb*N, T] + embedding -> estimate [B, L]."""
+        dev = x.device
+        B = x.shape[0]
+        win, hop, N, nb = self.win, self.stride, self.feature_dim, self.nband
+        fwd_b, inv_b, offs, R, w2 = self._bases(dev)
+        T = x.shape[2]
         sep = self.separator.separation
         if self.separator.multi_fuse:
             for r in range(len(sep) // 2):
@@ -283,11 +296,42 @@ class BSRNN(nn.Module):
         frames = ops.FixedGemmFn.apply(est, inv_b, False)                                 # [B, win, T]
         n_out = win + hop * (T - 1)
         y = ops.OverlapAddFn.apply(frames, hop, n_out)                                    # [B, n_out]
-        env = self.__dict__.setdefault("_env_cache", {}).get((str(dev), T))
+        env = self.__dict__.setdefault("_env_cache", {}).get((str(dev), T, L))
         if env is None:
             e = torch.zeros(n_out, device=dev)
             for t in range(T):
                 e[t * hop:t * hop + win] += w2
-            env = self._env_cache[(str(dev), T)] = 1.0 / e[win // 2:win // 2 + L]
-        s = y[:, win // 2:win // 2 + L] * env
-        return s, predict_speaker_lable
+            env = self._env_cache[(str(dev), T, L)] = 1.0 / e[win // 2:win // 2 + L]
+        return y[:, win // 2:win // 2 + L] * env
+
+    def forward(self, input, embeddings):
+        self._check(input, embeddings)
+        spec, x = self._analysis(input)
+        emb, predict_speaker_lable = self._speaker(embeddings, raw_wave=self.joint_training and not self.spk_feat)
+        return self._separate(x, spec, emb, input.shape[1]), predict_speaker_lable
+
+
+class BSRNN_Multi(BSRNN):
+    """wesep/models/bsrnn_multi_optim.py:155-472: pBSRNN with the self-enrollment second pass — while gradients are enabled
+    the first estimate (detached) is turned into "consistent" enrollment features, embedded by the same speaker encoder and
+    the separator runs again on the same band features; returns (s, self_s, predict, self_predict), and (s, predict) under
+    no_grad.  Parameters and state_dict are those of BSRNN (bsrnn_multi_optim.yaml: joint_training, spk_feat False)."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        if not self.joint_training or self.spk_feat or self.feat_type != "consistent":
+            raise NotImplementedError("BSRNN_Multi: joint_training=True, spk_feat=False, feat_type='consistent' (the recipe, "
+                                      "bsrnn_multi_optim.yaml:52-68) is built; the reference's own second pass needs them too "
+                                      "(bsrnn_multi_optim.py:409-431)")
+
+    def forward(self, input, embeddings):
+        self._check(input, embeddings)
+        L = input.shape[1]
+        spec, x = self._analysis(input)
+        emb, predict_speaker_lable = self._speaker(embeddings, raw_wave=True)
+        s = self._separate(x, spec, emb, L)
+        if not torch.is_grad_enabled():
+            return s, predict_speaker_lable
+        emb2, self_predict_speaker_lable = self._speaker(s.detach(), raw_wave=True)         # bsrnn_multi_optim.py:406-431
+        self_s = self._separate(x, spec, emb2, L)
+        return s, self_s, predict_speaker_lable, self_predict_speaker_lable
