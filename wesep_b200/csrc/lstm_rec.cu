@@ -364,14 +364,6 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_fwd_kernel(const FwdParam
           for (int k = 0; k < 4; ++k)
             if (k >= nv) { c[g][k] = 0.f; hq[k] = 0.f; pre[0][k] = 0.f; pre[1][k] = 0.f; pre[2][k] = 0.f; pre[3][k] = 0.f; }
         }
-        if (q < p.ld) {
-          float* Gs = p.G + (int64_t)s * p.bsG + row_g + q;
-#pragma unroll
-          for (int gt = 0; gt < 4; ++gt)
-            __stcs(reinterpret_cast<float4*>(Gs + gt * gstride), make_float4(pre[gt][0], pre[gt][1], pre[gt][2], pre[gt][3]));
-          __stcs(reinterpret_cast<float4*>(p.Cs + (int64_t)s * p.bsH + row_h + q), make_float4(c[g][0], c[g][1], c[g][2], c[g][3]));
-          *reinterpret_cast<float4*>(p.H + (int64_t)s * p.bsH + row_h + q) = make_float4(hq[0], hq[1], hq[2], hq[3]);
-        }
         if (t + 1 < S) {
           // B operand of the next step, MN-major: K row = my unit, 4 consecutive sequences = 8 bytes
           uint32_t hi[2], lo[2];
@@ -402,6 +394,16 @@ __global__ void __launch_bounds__(THREADS, 1) lstm_rec_fwd_kernel(const FwdParam
           named_arrive_pub(g);
           LR_STAMP(6);
           prefetch_pre(t + 1, g);          // this group's next pre-activations -> L2
+        }
+        // the activations / cell state / h of this item go to global memory AFTER h_t has been handed to the publisher: they
+        // are off the step's critical path and overlap the next item's accumulator wait
+        if (q < p.ld) {
+          float* Gs = p.G + (int64_t)s * p.bsG + row_g + q;
+#pragma unroll
+          for (int gt = 0; gt < 4; ++gt)
+            __stcs(reinterpret_cast<float4*>(Gs + gt * gstride), make_float4(pre[gt][0], pre[gt][1], pre[gt][2], pre[gt][3]));
+          __stcs(reinterpret_cast<float4*>(p.Cs + (int64_t)s * p.bsH + row_h + q), make_float4(c[g][0], c[g][1], c[g][2], c[g][3]));
+          *reinterpret_cast<float4*>(p.H + (int64_t)s * p.bsH + row_h + q) = make_float4(hq[0], hq[1], hq[2], hq[3]);
         }
       }
     }

@@ -179,4 +179,12 @@ __host__ __device__ constexpr uint32_t idesc_f16(int M, int N, int fmt /* 0 = f1
 }
 
 }  // namespace tcx
+// LDGSTS: 16-byte asynchronous global -> shared copy (L2 only); src_bytes < 16 zero-fills the rest (0: pure zero fill)
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// commit / wait WITH a compiler memory barrier (the shared-memory reads that follow must not be hoisted above the wait)
+__device__ __forceinline__ void cp_async_commit_mem() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all_mem() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
 }  // namespace wb
