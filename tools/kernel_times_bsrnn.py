@@ -50,6 +50,7 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
     step()
     torch.cuda.synchronize()
 agg = collections.defaultdict(lambda: [0, 0.0])
+small = collections.defaultdict(lambda: [0, 0.0])     # launches shorter than 60 us: the per-band glue
 for ev in prof.events():
     if ev.device_type.name != "CUDA":
         continue
@@ -59,6 +60,9 @@ for ev in prof.events():
     a = agg[name]
     a[0] += 1
     a[1] += ev.time_range.end - ev.time_range.start
+    if ev.time_range.end - ev.time_range.start < 60:
+        small[name][0] += 1
+        small[name][1] += ev.time_range.end - ev.time_range.start
 tot = sum(v[1] for v in agg.values())
 lines = [f"# one pBSRNN train step, n={n}, {secs:g} s: CUPTI kernel activity (torch.profiler)", "",
          f"step {ms:.1f} ms by CUDA events ({n / ms * 1e3:.1f} utt/s), host enqueue {t_enq * 1e3:.1f} ms, {launches} wesep_b200 launches; "
@@ -67,6 +71,11 @@ lines = [f"# one pBSRNN train step, n={n}, {secs:g} s: CUPTI kernel activity (to
          "| share | total ms | avg us | count | kernel |", "|---:|---:|---:|---:|---|"]
 for name, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
     lines.append(f"| {100 * t / tot:.2f} % | {t / 1e3:.2f} | {t / c:.1f} | {c} | `{name[:100]}` |")
+st = sum(v[1] for v in small.values())
+lines += ["", f"Launches shorter than 60 us: {sum(v[0] for v in small.values())} activities, {st / 1e3:.1f} ms ({100 * st / tot:.1f} % of kernel time):", "",
+          "| total ms | avg us | count | kernel |", "|---:|---:|---:|---|"]
+for name, (c, t) in sorted(small.items(), key=lambda kv: -kv[1][1])[:14]:
+    lines.append(f"| {t / 1e3:.2f} | {t / c:.1f} | {c} | `{name[:100]}` |")
 txt = "\n".join(lines)
 print(txt)
 if out:
