@@ -455,6 +455,7 @@ typedef struct {
   int n, R, T; int64_t ld;
   const float* x; float* out;
   const float* gout; float* gx;
+  float eps;             /* added to the variance under the square root; 0 = 1e-7 (TSTP); ASTP's global context uses 1e-10 */
 } WesepTstpArgs;
 int wesep_b200_tstp_fwd(const WesepTstpArgs* a, void* stream);
 int wesep_b200_tstp_bwd(const WesepTstpArgs* a, void* stream);
@@ -714,6 +715,35 @@ typedef struct { int n, F, T; const float* spec; int64_t ld, bs; float* pw; int6
 int wesep_b200_power_spec(const WesepPowerSpecArgs* a, void* stream);    /* pw[n][f][t] = re^2 + im^2 (spec rows [0,F) re, [F,2F) im) */
 typedef struct { int n, M, T; const float* mel; int64_t ld; float eps; float* out; } WesepLogCmnArgs;
 int wesep_b200_log_cmn(const WesepLogCmnArgs* a, void* stream);          /* out[n][t][m] = log(mel[n][m][t] + eps) - its mean over t */
+
+/* ------------------------------------------------------------------------------------------------
+ * wespeaker ECAPA-TDNN building blocks (speaker encoder `ECAPA_TDNN_GLOB_c512` of dpccn.yaml:59-64 /
+ * bsrnn_feats.yaml; wespeaker/models/ecapa_tdnn.py + pooling_layers.ASTP, an external package: parity unpinned).
+ * ---------------------------------------------------------------------------------------------- */
+/* patches of nn.Conv1d(C, Co, K, dilation = dil, padding = dil (K - 1) / 2): col[n][c*K + k][t] = x[n][c][t + (k - (K-1)/2) dil] (0 outside);
+ * the convolution is wesep_b200_conv1x1 over the K C gathered rows; bwd = the adjoint gather. */
+typedef struct {
+  int n, C, T, K, dil; int64_t ldx, ldc, bsc;
+  const float* x; float* col;
+  const float* gcol; float* gx;
+} WesepIm2col1dArgs;
+int wesep_b200_im2col1d_fwd(const WesepIm2col1dArgs* a, void* stream);
+int wesep_b200_im2col1d_bwd(const WesepIm2col1dArgs* a, void* stream);
+
+/* elementwise y = f(x) over `count` contiguous floats: mode 0 ReLU, 1 sigmoid (the SE block, ecapa_tdnn.py SE_Connect); bwd from y */
+typedef struct { int64_t count; int mode; const float* x; float* y; const float* gy; float* gx; } WesepUnaryArgs;
+int wesep_b200_unary_fwd(const WesepUnaryArgs* a, void* stream);
+int wesep_b200_unary_bwd(const WesepUnaryArgs* a, void* stream);     /* gx = gy * f'(.) expressed through y */
+
+/* attentive statistics (pooling_layers.ASTP.forward tail): alpha [n][C][ld] = softmax over time (given), x [n][C][ld] ->
+ * out [n][2C] = (sum_t alpha x | sqrt(clamp(sum_t alpha x^2 - mean^2, 1e-10))); bwd: gx and galpha (both [n][C][ld]). */
+typedef struct {
+  int n, C, T; int64_t ld;
+  const float* x; const float* alpha; float* out;
+  const float* gout; float* gx; float* galpha;
+} WesepAstpArgs;
+int wesep_b200_astp_fwd(const WesepAstpArgs* a, void* stream);
+int wesep_b200_astp_bwd(const WesepAstpArgs* a, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,134 @@
+// wespeaker ECAPA-TDNN building blocks: the dilated Conv1d of the TDNN / Res2 layers as a gather (im2col1d)
+// in front of the tcgen05 pointwise GEMM, the squeeze-excitation gate's ReLU / sigmoid, and the attentive statistics of ASTP.
+// BatchNorm1d, the 1x1 convolutions, tanh, the softmax over time and the global-context statistics reuse bn2 / conv1x1 / tanh /
+// softmax / tstp.  All HBM-bound streaming kernels on act tensors [n][C][T].
+#include "common.cuh"
+
+namespace wb {
+
+// col[n][c*K + k][t] = x[n][c][t + (k - (K-1)/2) * dil]
+__global__ void __launch_bounds__(256) im2col1d_kernel(WesepIm2col1dArgs a) {
+  const int r = blockIdx.y, n = blockIdx.z;
+  const int c = r / a.K, k = r - c * a.K;
+  const int sh = (k - (a.K - 1) / 2) * a.dil;
+  const float* x = a.x + ((int64_t)n * a.C + c) * a.ldx;
+  float* col = a.col + (int64_t)n * a.bsc + (int64_t)r * a.ldc;
+  for (int t = blockIdx.x * 256 + threadIdx.x; t < a.T; t += gridDim.x * 256) {
+    const int s = t + sh;
+    col[t] = (s >= 0 && s < a.T) ? __ldg(x + s) : 0.f;
+  }
+}
+// gx[n][c][s] = sum_k gcol[n][c*K + k][s - (k - (K-1)/2) dil]
+__global__ void __launch_bounds__(256) col2im1d_kernel(WesepIm2col1dArgs a) {
+  const int c = blockIdx.y, n = blockIdx.z;
+  const float* g = a.gcol + (int64_t)n * a.bsc + (int64_t)c * a.K * a.ldc;
+  float* gx = a.gx + ((int64_t)n * a.C + c) * a.ldx;
+  for (int s = blockIdx.x * 256 + threadIdx.x; s < a.T; s += gridDim.x * 256) {
+    float acc = 0.f;
+    for (int k = 0; k < a.K; ++k) {
+      const int t = s - (k - (a.K - 1) / 2) * a.dil;
+      if (t >= 0 && t < a.T) acc += __ldg(g + (int64_t)k * a.ldc + t);
+    }
+    gx[s] = acc;
+  }
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(256) unary_kernel(WesepUnaryArgs a) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < a.count; i += (int64_t)gridDim.x * 256) {
+    if (!BWD) {
+      const float v = __ldg(a.x + i);
+      a.y[i] = a.mode == 0 ? fmaxf(v, 0.f) : 1.f / (1.f + __expf(-v));
+    } else {
+      const float y = __ldg(a.y + i), g = __ldg(a.gy + i);
+      a.gx[i] = a.mode == 0 ? (y > 0.f ? g : 0.f) : g * y * (1.f - y);
+    }
+  }
+}
+
+// one warp per (n, c) row
+template <bool BWD>
+__global__ void __launch_bounds__(256) astp_kernel(WesepAstpArgs a) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= a.n * a.C) return;
+  const int n = row / a.C, c = row - n * a.C;
+  const float* x = a.x + (int64_t)row * a.ld;
+  const float* al = a.alpha + (int64_t)row * a.ld;
+  float s0 = 0.f, s1 = 0.f;
+  for (int t = lane; t < a.T; t += 32) {
+    const float v = __ldg(x + t), w = __ldg(al + t);
+    s0 = fmaf(w, v, s0);
+    s1 = fmaf(w * v, v, s1);
+  }
+  s0 = warp_sum(s0); s1 = warp_sum(s1);
+  const float mean = s0, var = s1 - mean * mean;
+  const bool live = var > 1e-10f;
+  const float sd = sqrtf(live ? var : 1e-10f);
+  if constexpr (!BWD) {
+    if (lane == 0) {
+      a.out[(int64_t)n * 2 * a.C + c] = mean;
+      a.out[(int64_t)n * 2 * a.C + a.C + c] = sd;
+    }
+  } else {
+    const float gm = __ldg(a.gout + (int64_t)n * 2 * a.C + c), gs = __ldg(a.gout + (int64_t)n * 2 * a.C + a.C + c);
+    const float dvar = live ? gs / (2.f * sd) : 0.f;           // clamp(min = 1e-10): no gradient below the floor
+    const float dmean = gm - 2.f * mean * dvar;
+    float* gx = a.gx + (int64_t)row * a.ld;
+    float* ga = a.galpha + (int64_t)row * a.ld;
+    for (int t = lane; t < a.T; t += 32) {
+      const float v = __ldg(x + t), w = __ldg(al + t);
+      gx[t] = w * fmaf(2.f * v, dvar, dmean);
+      ga[t] = v * fmaf(v, dvar, dmean);
+    }
+  }
+}
+
+}  // namespace wb
+
+using namespace wb;
+
+static int check_i1(const WesepIm2col1dArgs* a) {
+  if (!a || a->n <= 0 || a->n > 65535 || a->C <= 0 || a->T <= 0 || a->K <= 0 || !(a->K & 1) || a->dil <= 0) return fail(-1, "im2col1d: shape (odd K)");
+  if ((int64_t)a->C * a->K > 65535) return fail(-2, "im2col1d: too many gathered rows for one launch");
+  if (a->ldx < a->T || a->ldc < a->T || a->bsc < (int64_t)a->C * a->K * a->ldc) return fail(-1, "im2col1d: strides");
+  return 0;
+}
+extern "C" int wesep_b200_im2col1d_fwd(const WesepIm2col1dArgs* a, void* stream) {
+  if (int rc = check_i1(a)) return rc;
+  if (!a->x || !a->col) return fail(-1, "im2col1d: pointers");
+  im2col1d_kernel<<<dim3(cdiv(a->T, 1024), a->C * a->K, a->n), 256, 0, (cudaStream_t)stream>>>(*a);
+  WB_LAUNCH_CHECK("im2col1d_fwd");
+  return 0;
+}
+extern "C" int wesep_b200_im2col1d_bwd(const WesepIm2col1dArgs* a, void* stream) {
+  if (int rc = check_i1(a)) return rc;
+  if (!a->gcol || !a->gx) return fail(-1, "col2im1d: pointers");
+  col2im1d_kernel<<<dim3(cdiv(a->T, 1024), a->C, a->n), 256, 0, (cudaStream_t)stream>>>(*a);
+  WB_LAUNCH_CHECK("im2col1d_bwd");
+  return 0;
+}
+extern "C" int wesep_b200_unary_fwd(const WesepUnaryArgs* a, void* stream) {
+  if (!a || a->count <= 0 || (a->mode != 0 && a->mode != 1) || !a->x || !a->y) return fail(-1, "unary: bad arguments");
+  unary_kernel<false><<<(unsigned)((a->count + 1023) / 1024 < 4096 ? (a->count + 1023) / 1024 : 4096), 256, 0, (cudaStream_t)stream>>>(*a);
+  WB_LAUNCH_CHECK("unary_fwd");
+  return 0;
+}
+extern "C" int wesep_b200_unary_bwd(const WesepUnaryArgs* a, void* stream) {
+  if (!a || a->count <= 0 || (a->mode != 0 && a->mode != 1) || !a->y || !a->gy || !a->gx) return fail(-1, "unary_bwd: bad arguments");
+  unary_kernel<true><<<(unsigned)((a->count + 1023) / 1024 < 4096 ? (a->count + 1023) / 1024 : 4096), 256, 0, (cudaStream_t)stream>>>(*a);
+  WB_LAUNCH_CHECK("unary_bwd");
+  return 0;
+}
+extern "C" int wesep_b200_astp_fwd(const WesepAstpArgs* a, void* stream) {
+  if (!a || a->n <= 0 || a->C <= 0 || a->T <= 0 || a->ld < a->T || !a->x || !a->alpha || !a->out) return fail(-1, "astp: bad arguments");
+  astp_kernel<false><<<cdiv((int64_t)a->n * a->C, 8), 256, 0, (cudaStream_t)stream>>>(*a);
+  WB_LAUNCH_CHECK("astp_fwd");
+  return 0;
+}
+extern "C" int wesep_b200_astp_bwd(const WesepAstpArgs* a, void* stream) {
+  if (!a || a->n <= 0 || a->C <= 0 || a->T <= 0 || a->ld < a->T || !a->x || !a->alpha || !a->gout || !a->gx || !a->galpha)
+    return fail(-1, "astp_bwd: bad arguments");
+  astp_kernel<true><<<cdiv((int64_t)a->n * a->C, 8), 256, 0, (cudaStream_t)stream>>>(*a);
+  WB_LAUNCH_CHECK("astp_bwd");
+  return 0;
+}

@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(256) tstp_kernel(WesepTstpArgs a) {
   for (int t = lane; t < a.T; t += 32) { const float d = __ldg(x + t) - mean; s1 = fmaf(d, d, s1); }
   s1 = warp_sum(s1);
   const float var = s1 / (float)(a.T - 1);
-  const float sd = sqrtf(var + 1e-7f);
+  const float sd = sqrtf(var + (a.eps > 0.f ? a.eps : 1e-7f));
   if constexpr (!BWD) {
     if (lane == 0) {
       a.out[(int64_t)n * 2 * a.R + r] = mean;

@@ -138,4 +138,7 @@ def get_speaker_model(model_name):
     """wespeaker.models.speaker_model.get_speaker_model for the encoders built here."""
     if model_name in ("ResNet18", "ResNet34"):
         return globals()[model_name]
-    raise NotImplementedError("speaker model %s is not built in wesep_b200 (ResNet18 / ResNet34 only)" % model_name)
+    if model_name in ("ECAPA_TDNN_c512", "ECAPA_TDNN_GLOB_c512", "ECAPA_TDNN_c1024", "ECAPA_TDNN_GLOB_c1024"):
+        from wesep_b200.modules.speaker import ecapa
+        return getattr(ecapa, model_name)
+    raise NotImplementedError("speaker model %s is not built in wesep_b200 (ResNet18 / ResNet34 / ECAPA_TDNN_* only)" % model_name)

@@ -1177,6 +1177,14 @@ def conv1x1_bigk(x, W2d, bias=None):
     return y
 
 
+def conv1x1_bigk_relu(x, W2d, bias):
+    """relu(conv1x1) for any number of input channels: the ReLU is fused into the GEMM epilogue when one launch covers the
+    contraction, otherwise applied to the accumulated sum."""
+    if x.shape[1] <= 1024:
+        return Conv1x1Fn.apply(x, W2d, bias, False, "relu")
+    return as_act(UnaryFn.apply(conv1x1_bigk(x, W2d, bias), 0))
+
+
 class AddFn(torch.autograd.Function):
     """a + b for two act tensors (the gradient is shared, not copied)."""
 
@@ -1305,11 +1313,12 @@ class TstpFn(torch.autograd.Function):
     """wespeaker TSTP pooling: [n, R, T] -> [n, 2R] = (mean | sqrt(unbiased var + 1e-7)) over time."""
 
     @staticmethod
-    def forward(ctx, x):
+    def forward(ctx, x, eps=0.0):
         x = as_act(x)
         n, R, T = x.shape
         out = torch.empty((n, 2 * R), dtype=torch.float32, device=x.device)
-        _lib.call("wesep_b200_tstp_fwd", _args("WesepTstpArgs", n=n, R=R, T=T, ld=x.stride(1), x=x, out=out), _stream())
+        _lib.call("wesep_b200_tstp_fwd", _args("WesepTstpArgs", n=n, R=R, T=T, ld=x.stride(1), x=x, out=out, eps=float(eps)), _stream())
+        ctx.eps = float(eps)
         ctx.save_for_backward(x)
         return out
 
@@ -1319,8 +1328,8 @@ class TstpFn(torch.autograd.Function):
         n, R, T = x.shape
         gx = new_act(n, R, T, x.device)
         _lib.call("wesep_b200_tstp_bwd", _args("WesepTstpArgs", n=n, R=R, T=T, ld=x.stride(1), x=x, gout=g.contiguous().float(),
-                                               gx=gx), _stream())
-        return gx
+                                               gx=gx, eps=ctx.eps), _stream())
+        return gx, None
 
 
 # --------------------------------------------------------------------------- pDPCCN building blocks
@@ -1769,3 +1778,93 @@ class _RowsIntoFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         return None, g[0, :ctx.T]
+
+
+# --------------------------------------------------------------------------- wespeaker ECAPA-TDNN building blocks (SURVEY 8f-2)
+class Im2Col1dFn(torch.autograd.Function):
+    """[n, C, T] -> [n, C*K (padded to a multiple of 4), T]: the taps of nn.Conv1d(kernel K odd, dilation d, padding d (K-1)/2);
+    rows ordered (c, k) = the Conv1d weight viewed [Cout, Cin*K]."""
+
+    @staticmethod
+    def forward(ctx, x, K, dil):
+        x = as_act(x)                                   # dense [n, C, ld] (a channel slice of a wider tensor is copied)
+        n, C, T = x.shape
+        Kp = (C * K + 3) // 4 * 4
+        col = new_act(n, Kp, T, x.device)
+        if Kp != C * K:
+            col[:, C * K:].zero_()
+        _lib.call("wesep_b200_im2col1d_fwd", _args("WesepIm2col1dArgs", n=n, C=C, T=T, K=int(K), dil=int(dil), ldx=x.stride(1),
+                                                   ldc=col.stride(1), bsc=col.stride(0), x=x, col=col), _stream())
+        ctx.meta = (n, C, T, int(K), int(dil))
+        return col
+
+    @staticmethod
+    def backward(ctx, gcol):
+        n, C, T, K, dil = ctx.meta
+        gcol = as_act(gcol)
+        gx = new_act(n, C, T, gcol.device)
+        _lib.call("wesep_b200_im2col1d_bwd", _args("WesepIm2col1dArgs", n=n, C=C, T=T, K=K, dil=dil, ldx=gx.stride(1),
+                                                   ldc=gcol.stride(1), bsc=gcol.stride(0), gcol=gcol, gx=gx), _stream())
+        return gx, None, None
+
+
+def conv1d_k(x, weight, bias, dil=1, act=None):
+    """nn.Conv1d(Ci, Co, K, dilation=dil, padding=dil*(K-1)//2) (+ ReLU in the GEMM epilogue) on an act tensor."""
+    Co, Ci, K = weight.shape
+    if K == 1:
+        return Conv1x1Fn.apply(x, weight[:, :, 0], bias, False, act)
+    col = Im2Col1dFn.apply(as_act(x), K, dil)
+    w2 = weight.reshape(Co, Ci * K)
+    if col.shape[1] != w2.shape[1]:
+        w2 = torch.nn.functional.pad(w2, (0, col.shape[1] - w2.shape[1]))
+    if col.shape[1] > 1024:
+        if act is not None:
+            raise RuntimeError("conv1d_k: fused activation with more than 1024 gathered channels")
+        return conv1x1_bigk(col, w2, bias)
+    return Conv1x1Fn.apply(col, w2, bias, False, act)
+
+
+class UnaryFn(torch.autograd.Function):
+    """Elementwise ReLU (mode 0) / sigmoid (mode 1) on a contiguous tensor."""
+
+    @staticmethod
+    def forward(ctx, x, mode):
+        _check_cuda(x)
+        x = x.contiguous().float()
+        y = torch.empty_like(x)
+        _lib.call("wesep_b200_unary_fwd", _args("WesepUnaryArgs", count=x.numel(), mode=int(mode), x=x, y=y), _stream())
+        ctx.mode = int(mode)
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (y,) = ctx.saved_tensors
+        gy = gy.contiguous().float()
+        gx = torch.empty_like(y)
+        _lib.call("wesep_b200_unary_bwd", _args("WesepUnaryArgs", count=y.numel(), mode=ctx.mode, y=y, gy=gy, gx=gx), _stream())
+        return gx, None
+
+
+class AstpFn(torch.autograd.Function):
+    """Attentive statistics: x, alpha (softmax over time) [n, C, T] -> [n, 2C] = (sum alpha x | sqrt(clamp(sum alpha x^2 - mean^2)))."""
+
+    @staticmethod
+    def forward(ctx, x, alpha):
+        x, alpha = as_act(x), as_act(alpha)
+        n, C, T = x.shape
+        if alpha.shape != x.shape or alpha.stride(1) != x.stride(1):
+            raise RuntimeError("astp: layout mismatch")
+        out = torch.empty((n, 2 * C), dtype=torch.float32, device=x.device)
+        _lib.call("wesep_b200_astp_fwd", _args("WesepAstpArgs", n=n, C=C, T=T, ld=x.stride(1), x=x, alpha=alpha, out=out), _stream())
+        ctx.save_for_backward(x, alpha)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, alpha = ctx.saved_tensors
+        n, C, T = x.shape
+        gx, ga = new_act(n, C, T, x.device), new_act(n, C, T, x.device)
+        _lib.call("wesep_b200_astp_bwd", _args("WesepAstpArgs", n=n, C=C, T=T, ld=x.stride(1), x=x, alpha=alpha,
+                                               gout=g.contiguous().float(), gx=gx, galpha=ga), _stream())
+        return gx, ga
