@@ -73,9 +73,12 @@ def test_model_registry_and_state_dict_contract():
     with pytest.raises(RuntimeError):                  # pBSRNN: CUDA only (no fallback)
         get_model("BSRNN")(joint_training=False, use_spk_transform=False, feature_dim=16, num_repeat=1,
                            spk_fuse_type="multiply")(torch.zeros(1, 2000), torch.zeros(1, 256))
-    with pytest.raises(NotImplementedError):           # only the BasicBlock ResNets of wespeaker are built
-        get_model("BSRNN")(joint_training=True, use_spk_transform=False, spk_feat=True, spk_model="ECAPA_TDNN_GLOB_c512",
+    with pytest.raises(NotImplementedError):           # wespeaker's ResNet18 / 34 and ECAPA-TDNN families are built, nothing else
+        get_model("BSRNN")(joint_training=True, use_spk_transform=False, spk_feat=True, spk_model="CAMPPlus",
                            spk_args=dict(feat_dim=80, embed_dim=192))
+    e = get_model("BSRNN")(joint_training=True, use_spk_transform=False, spk_feat=True, spk_model="ECAPA_TDNN_GLOB_c512",
+                           spk_args=dict(feat_dim=80, embed_dim=192, pooling_func="ASTP"), spk_emb_dim=192, feature_dim=16, num_repeat=1)
+    assert sum(p.numel() for p in e.spk_model.parameters()) == 6190720      # wespeaker's published size of ECAPA_TDNN_GLOB_c512
     with pytest.raises(RuntimeError):
         m(torch.zeros(1, 1, 100), torch.zeros(1, 100))     # >= 3-D input, convtasnet.py:163-166
 
