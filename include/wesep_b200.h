@@ -745,6 +745,14 @@ typedef struct {
 int wesep_b200_astp_fwd(const WesepAstpArgs* a, void* stream);
 int wesep_b200_astp_bwd(const WesepAstpArgs* a, void* stream);
 
+/* Plain elementwise helpers so that residual sums and the iSTFT envelope normalisation stay inside the library:
+ * out = a + b over `count` floats (16-byte aligned buffers; may alias), and y[r][t] = x[r][t] * v[t] (the 1 / sum w^2 envelope of
+ * torch.istft, wesep/models/bsrnn.py:382-389; its adjoint is the same call on the gradient). */
+typedef struct { int64_t count; const float* a; const float* b; float* out; } WesepAddArgs;
+int wesep_b200_add(const WesepAddArgs* a, void* stream);
+typedef struct { int64_t rows; int L; const float* x; int64_t ldx; const float* v; float* y; int64_t ldy; } WesepColVecArgs;
+int wesep_b200_colvec_mul(const WesepColVecArgs* a, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

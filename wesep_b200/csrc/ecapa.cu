@@ -46,6 +46,21 @@ __global__ void __launch_bounds__(256) unary_kernel(WesepUnaryArgs a) {
   }
 }
 
+// out = a + b over `count` floats (float4 body)
+__global__ void __launch_bounds__(256) add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int64_t count) {
+  const int64_t n4 = count >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
+    const float4 x = __ldg(reinterpret_cast<const float4*>(a) + i), y = __ldg(reinterpret_cast<const float4*>(b) + i);
+    reinterpret_cast<float4*>(out)[i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+  }
+  for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * 256 + threadIdx.x; i < count; i += (int64_t)gridDim.x * 256) out[i] = __ldg(a + i) + __ldg(b + i);
+}
+// y[r][t] = x[r][t] * v[t]
+__global__ void __launch_bounds__(256) colvec_mul_kernel(WesepColVecArgs a) {
+  const int64_t r = blockIdx.y;
+  for (int t = blockIdx.x * 256 + threadIdx.x; t < a.L; t += gridDim.x * 256) a.y[r * a.ldy + t] = __ldg(a.x + r * a.ldx + t) * __ldg(a.v + t);
+}
+
 // one warp per (n, c) row
 template <bool BWD>
 __global__ void __launch_bounds__(256) astp_kernel(WesepAstpArgs a) {
@@ -130,5 +145,20 @@ extern "C" int wesep_b200_astp_bwd(const WesepAstpArgs* a, void* stream) {
     return fail(-1, "astp_bwd: bad arguments");
   astp_kernel<true><<<cdiv((int64_t)a->n * a->C, 8), 256, 0, (cudaStream_t)stream>>>(*a);
   WB_LAUNCH_CHECK("astp_bwd");
+  return 0;
+}
+
+extern "C" int wesep_b200_add(const WesepAddArgs* p, void* stream) {
+  if (!p || !p->a || !p->b || !p->out || p->count <= 0) return fail(-1, "add: bad arguments");
+  if (!aligned16(p->a) || !aligned16(p->b) || !aligned16(p->out)) return fail(-1, "add: 16-byte alignment");
+  const int64_t blocks = (p->count / 4 + 255) / 256;
+  add_kernel<<<(unsigned)(blocks < 1 ? 1 : (blocks > 65535 ? 65535 : blocks)), 256, 0, (cudaStream_t)stream>>>(p->a, p->b, p->out, p->count);
+  WB_LAUNCH_CHECK("add");
+  return 0;
+}
+extern "C" int wesep_b200_colvec_mul(const WesepColVecArgs* a, void* stream) {
+  if (!a || a->rows <= 0 || a->rows > 65535 || a->L <= 0 || a->ldx < a->L || a->ldy < a->L || !a->x || !a->v || !a->y) return fail(-1, "colvec_mul: bad arguments");
+  colvec_mul_kernel<<<dim3(cdiv(a->L, 2048), (unsigned)a->rows), 256, 0, (cudaStream_t)stream>>>(*a);
+  WB_LAUNCH_CHECK("colvec_mul");
   return 0;
 }

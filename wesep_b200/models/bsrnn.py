@@ -302,7 +302,7 @@ class BSRNN(nn.Module):
             for t in range(T):
                 e[t * hop:t * hop + win] += w2
             env = self._env_cache[(str(dev), T, L)] = 1.0 / e[win // 2:win // 2 + L]
-        return y[:, win // 2:win // 2 + L] * env
+        return ops.ColVecMulFn.apply(y[:, win // 2:win // 2 + L], env)
 
     def forward(self, input, embeddings):
         self._check(input, embeddings)

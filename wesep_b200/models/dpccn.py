@@ -327,4 +327,4 @@ class DPCCN(nn.Module):
             for t in range(T):
                 e[t * hop:t * hop + win] += w2
             env = self._env_cache[(str(dev), T)] = 1.0 / e[win // 2:win // 2 + L]
-        return y[:, win // 2:win // 2 + L] * env, predict_speaker_lable
+        return ops.ColVecMulFn.apply(y[:, win // 2:win // 2 + L], env), predict_speaker_lable

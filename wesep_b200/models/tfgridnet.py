@@ -293,6 +293,6 @@ class TFGridNet(nn.Module):
             for t in range(T):
                 e[t * hop:t * hop + win] += w2
             env = self._env_cache[(str(dev), T, L)] = 1.0 / e[win // 2:win // 2 + L]
-        s = y[:, win // 2:win // 2 + L] * env
+        s = ops.ColVecMulFn.apply(y[:, win // 2:win // 2 + L], env)
         s = ops.RowAffineFn.apply(s[:, None, :], std[:, None], None)[:, 0]                   # tfgridnet.py:297
         return s, predict_speaker_lable

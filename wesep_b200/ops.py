@@ -1192,7 +1192,9 @@ class AddFn(torch.autograd.Function):
     def forward(ctx, a, b):
         a, b = as_act(a), as_act(b)
         out = new_act(a.shape[0], a.shape[1], a.shape[2], a.device)
-        torch.add(a, b, out=out)
+        if a.shape != b.shape or a.stride() != b.stride():
+            raise RuntimeError("add: layout mismatch")
+        _lib.call("wesep_b200_add", _args("WesepAddArgs", count=a.shape[0] * a.stride(0), a=a, b=b, out=out), _stream())
         return out
 
     @staticmethod
@@ -1868,3 +1870,31 @@ class AstpFn(torch.autograd.Function):
         _lib.call("wesep_b200_astp_bwd", _args("WesepAstpArgs", n=n, C=C, T=T, ld=x.stride(1), x=x, alpha=alpha,
                                                gout=g.contiguous().float(), gx=gx, galpha=ga), _stream())
         return gx, ga
+
+
+class ColVecMulFn(torch.autograd.Function):
+    """y[r, t] = x[r, t] * v[t] for a [rows, L] signal batch and a constant vector (the iSTFT envelope 1 / sum_k w^2)."""
+
+    @staticmethod
+    def forward(ctx, x, v):
+        _check_cuda(x, v)
+        if x.dim() != 2 or x.stride(1) != 1 or x.dtype != torch.float32:
+            x = x.contiguous().float()
+        rows, L = x.shape
+        v = v.contiguous().float()
+        if v.numel() != L:
+            raise RuntimeError("colvec_mul: vector length")
+        y = torch.empty((rows, L), dtype=torch.float32, device=x.device)
+        _lib.call("wesep_b200_colvec_mul", _args("WesepColVecArgs", rows=rows, L=L, x=x, ldx=x.stride(0), v=v, y=y, ldy=L), _stream())
+        ctx.save_for_backward(v)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (v,) = ctx.saved_tensors
+        if g.stride(1) != 1 or g.dtype != torch.float32:
+            g = g.contiguous().float()
+        rows, L = g.shape
+        gx = torch.empty((rows, L), dtype=torch.float32, device=g.device)
+        _lib.call("wesep_b200_colvec_mul", _args("WesepColVecArgs", rows=rows, L=L, x=g, ldx=g.stride(0), v=v, y=gx, ldy=L), _stream())
+        return gx, None
