@@ -188,21 +188,42 @@ __global__ void __launch_bounds__(256) upsample_fwd_kernel(WesepUpsample2dArgs a
     y[i] = (1.f - lh) * ((1.f - lw) * v00 + lw * v01) + lh * ((1.f - lw) * v10 + lw * v11);
   }
 }
-__global__ void __launch_bounds__(256) upsample_bwd_kernel(WesepUpsample2dArgs a) {   // gx zeroed by the entry point
+// gx zeroed by the entry point.  The low-resolution map of one plane is small (<= UP_SMEM_MAX floats): every CTA accumulates its
+// chunk of output pixels into a shared-memory copy of the map and flushes it with one global atomic per touched element
+// (a 32 x 32 pooling level concentrates 128 k scatter-adds on 120 addresses: global atomics alone took 440 us per launch).
+constexpr int UP_SMEM_MAX = 10240;
+constexpr int UP_CHUNK = 8192;
+__global__ void __launch_bounds__(256) upsample_bwd_kernel(WesepUpsample2dArgs a) {
+  extern __shared__ float up_acc[];
   const int64_t row = blockIdx.y;
   const float* gy = a.gy + row * a.ldo;
   float* gx = a.gx + row * a.ldi;
+  const int nin = a.Hi * a.Wi;
+  const bool use_smem = nin <= UP_SMEM_MAX;
+  if (use_smem) {
+    for (int i = threadIdx.x; i < nin; i += 256) up_acc[i] = 0.f;
+    __syncthreads();
+  }
+  float* acc = use_smem ? up_acc : gx;
   const float sh = (float)a.Hi / (float)a.Ho, sw = (float)a.Wi / (float)a.Wo;
-  for (int i = blockIdx.x * 256 + threadIdx.x; i < a.Ho * a.Wo; i += gridDim.x * 256) {
+  const int c0 = blockIdx.x * UP_CHUNK, end = min(c0 + UP_CHUNK, a.Ho * a.Wo);
+  for (int i = c0 + threadIdx.x; i < end; i += 256) {
     const int ho = i / a.Wo, wo = i - ho * a.Wo;
     int h0, h1, w0, w1; float lh, lw;
     bl_coord(ho, sh, a.Hi, h0, h1, lh);
     bl_coord(wo, sw, a.Wi, w0, w1, lw);
     const float g = __ldg(gy + i);
-    atomicAdd(gx + (int64_t)h0 * a.Wi + w0, (1.f - lh) * (1.f - lw) * g);
-    atomicAdd(gx + (int64_t)h0 * a.Wi + w1, (1.f - lh) * lw * g);
-    atomicAdd(gx + (int64_t)h1 * a.Wi + w0, lh * (1.f - lw) * g);
-    atomicAdd(gx + (int64_t)h1 * a.Wi + w1, lh * lw * g);
+    atomicAdd(acc + h0 * a.Wi + w0, (1.f - lh) * (1.f - lw) * g);
+    atomicAdd(acc + h0 * a.Wi + w1, (1.f - lh) * lw * g);
+    atomicAdd(acc + h1 * a.Wi + w0, lh * (1.f - lw) * g);
+    atomicAdd(acc + h1 * a.Wi + w1, lh * lw * g);
+  }
+  if (use_smem) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < nin; i += 256) {
+      const float v = up_acc[i];
+      if (v != 0.f) atomicAdd(gx + i, v);
+    }
   }
 }
 
@@ -332,7 +353,8 @@ extern "C" int wesep_b200_upsample2d_bwd(const WesepUpsample2dArgs* a, void* str
   if (!a->gy || !a->gx) return fail(-1, "upsample2d: null buffer");
   cudaStream_t st = (cudaStream_t)stream;
   WB_CUDA(cudaMemsetAsync(a->gx, 0, (size_t)a->rows * a->ldi * sizeof(float), st));
-  upsample_bwd_kernel<<<dim3(cdiv((int64_t)a->Ho * a->Wo, 1024), (unsigned)a->rows), 256, 0, st>>>(*a);
+  const size_t smem = (size_t)a->Hi * a->Wi <= (size_t)UP_SMEM_MAX ? (size_t)a->Hi * a->Wi * sizeof(float) : 0;
+  upsample_bwd_kernel<<<dim3(cdiv((int64_t)a->Ho * a->Wo, UP_CHUNK), (unsigned)a->rows), 256, smem, st>>>(*a);
   WB_LAUNCH_CHECK("upsample2d_bwd");
   return 0;
 }
