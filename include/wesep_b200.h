@@ -726,6 +726,8 @@ typedef struct {
   int n, C, T, K, dil; int64_t ldx, ldc, bsc;
   const float* x; float* col;
   const float* gcol; float* gx;
+  int unfold, stride;    /* unfold = 1: F.unfold(x[..., None], (K, 1), stride = (stride, 1)) — no padding, dilation 1, (T - K) / stride + 1
+                            columns (TF-GridNet with emb_ks > 1, gridnet_block.py:147-160; its adjoint is ConvTranspose1d's overlap-add) */
 } WesepIm2col1dArgs;
 int wesep_b200_im2col1d_fwd(const WesepIm2col1dArgs* a, void* stream);
 int wesep_b200_im2col1d_bwd(const WesepIm2col1dArgs* a, void* stream);

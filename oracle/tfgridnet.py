@@ -7,8 +7,8 @@ DFT sums).  Backward = torch autograd of this forward.  Pinned: tests/golden/tfg
 gradient summaries of the REAL reference module (tests/golden/make_golden_tfgridnet.py); tests/test_oracle_tfgridnet.py
 compares this file with them.
 
-Scope: ``joint_training=False`` (a given speaker embedding), ``emb_ks == emb_hs == 1`` (tfgridnet.yaml:52-53), one
-source, one microphone, ``multiply`` fusion.
+Scope: ``joint_training=False`` (a given speaker embedding), ``emb_ks == emb_hs == 1`` (tfgridnet.yaml:52-53) or
+``emb_ks != emb_hs`` (the class default 4 / 1), one source, one microphone, ``multiply`` fusion.
 """
 import math
 
@@ -56,20 +56,33 @@ def ln_4dcf(x, sd, pre, eps):
     return (x - mu) / std * sd[pre + "gamma"] + sd[pre + "beta"]
 
 
-def gridnet_block(x, sd, pre, n_head, eps):
-    """gridnet_block.py:118-227 with emb_ks == emb_hs == 1.  x [B, C, T, Q]."""
-    B, C, T, Q = x.shape
+def _rnn_path(v, sd, pre, name, ks, hs, eps):
+    """One of the two recurrent paths of a block on v [B, A, S, C] (sequences along S): LayerNorm(C) -> (unfold) -> BLSTM ->
+    Linear or ConvTranspose1d -> + v (gridnet_block.py:135-161 / 163-187)."""
+    B, A, S, C = v.shape
+    y = layer_norm_c(v, sd[pre + name + "_norm.weight"], sd[pre + name + "_norm.bias"], eps).reshape(B * A, S, C)
+    if ks == hs:
+        y = blstm(y, sd, pre + name + "_rnn.") @ sd[pre + name + "_linear.weight"].t() + sd[pre + name + "_linear.bias"]
+        return y.view(B, A, S, C) + v
+    y = F.unfold(y.transpose(1, 2)[..., None], (ks, 1), stride=(hs, 1)).transpose(1, 2)       # [BA, L, C*ks]
+    y = blstm(y, sd, pre + name + "_rnn.").transpose(1, 2)                                    # [BA, 2H, L]
+    y = F.conv_transpose1d(y, sd[pre + name + "_linear.weight"], sd[pre + name + "_linear.bias"], stride=hs)   # [BA, C, S]
+    return y.view(B, A, C, S).transpose(-2, -1) + v
+
+
+def gridnet_block(x, sd, pre, n_head, eps, ks=1, hs=1):
+    """gridnet_block.py:118-227.  x [B, C, T, Q]."""
+    B, C, old_T, old_Q = x.shape
+    olp = ks - hs
+    T = math.ceil((old_T + 2 * olp - ks) / hs) * hs + ks
+    Q = math.ceil((old_Q + 2 * olp - ks) / hs) * hs + ks
     x = x.permute(0, 2, 3, 1)                                            # [B, T, Q, C]
-    inp = x
-    y = layer_norm_c(inp, sd[pre + "intra_norm.weight"], sd[pre + "intra_norm.bias"], eps).reshape(B * T, Q, C)
-    y = blstm(y, sd, pre + "intra_rnn.") @ sd[pre + "intra_linear.weight"].t() + sd[pre + "intra_linear.bias"]
-    y = y.view(B, T, Q, C) + inp
+    x = F.pad(x, (0, 0, olp, Q - old_Q - olp, olp, T - old_T - olp))
+    y = _rnn_path(x, sd, pre, "intra", ks, hs, eps)                      # along Q
     y = y.transpose(1, 2)                                                # [B, Q, T, C]
-    inp = y
-    z = layer_norm_c(inp, sd[pre + "inter_norm.weight"], sd[pre + "inter_norm.bias"], eps).reshape(B * Q, T, C)
-    z = blstm(z, sd, pre + "inter_rnn.") @ sd[pre + "inter_linear.weight"].t() + sd[pre + "inter_linear.bias"]
-    z = z.view(B, Q, T, C) + inp
-    batch = z.permute(0, 3, 2, 1)                                        # [B, C, T, Q]
+    z = _rnn_path(y, sd, pre, "inter", ks, hs, eps)                      # along T
+    batch = z.permute(0, 3, 2, 1)[..., olp:olp + old_T, olp:olp + old_Q]  # [B, C, T, Q]
+    T, Q = old_T, old_Q
     E = sd[pre + "attn_conv_Q.weight"].shape[0] // n_head
     Ev = C // n_head
     Qh = all_head_prelu_ln(F.conv2d(batch, sd[pre + "attn_conv_Q.weight"], sd[pre + "attn_conv_Q.bias"]), sd, pre + "attn_norm_Q.",
@@ -90,7 +103,7 @@ def gridnet_block(x, sd, pre, n_head, eps):
     return p + batch
 
 
-def tfgridnet_forward(sd, mix, emb, n_fft=128, stride=64, n_layers=6, n_head=4, eps=1e-5):
+def tfgridnet_forward(sd, mix, emb, n_fft=128, stride=64, n_layers=6, n_head=4, eps=1e-5, emb_ks=1, emb_hs=1):
     """tfgridnet.py:197-302 with joint_training=False: returns the estimate [B, L]."""
     B, L = mix.shape
     std = torch.std(mix, dim=1, keepdim=True)
@@ -105,14 +118,14 @@ def tfgridnet_forward(sd, mix, emb, n_fft=128, stride=64, n_layers=6, n_head=4, 
     gain = F.linear(emb, sd["spk_fuse.fc.linear.weight"], sd["spk_fuse.fc.linear.bias"])   # [B, F]
     for i in range(n_layers):
         batch = batch * gain[:, None, None, :]                            # speaker.py:117-121 (4-D multiply)
-        batch = gridnet_block(batch, sd, f"blocks.{i}.", n_head, eps)
+        batch = gridnet_block(batch, sd, f"blocks.{i}.", n_head, eps, emb_ks, emb_hs)
     out = F.conv_transpose2d(batch, sd["deconv.weight"], sd["deconv.bias"], padding=(1, 1))   # [B, 2, T, F]
     est = ob.istft(out[:, 0].transpose(1, 2), out[:, 1].transpose(1, 2), n_fft, stride, length=L, window=window)
     return est * std
 
 
 def make_state_dict(n_layers=6, emb_dim=128, hidden=192, n_head=4, approx_qk_dim=512, n_fft=128, spk_emb_dim=256,
-                    dtype=torch.float32):
+                    dtype=torch.float32, emb_ks=1, emb_hs=1):
     """Keys / shapes / ORDER of TFGridNet(joint_training=False, emb_ks=1, emb_hs=1).state_dict()
     (tfgridnet.py:169-195, gridnet_block.py:45-111)."""
     Fq = n_fft // 2 + 1
@@ -134,11 +147,11 @@ def make_state_dict(n_layers=6, emb_dim=128, hidden=192, n_head=4, approx_qk_dim
             sd[pre + path + "_norm.weight"] = t(emb_dim)
             sd[pre + path + "_norm.bias"] = t(emb_dim)
             for suf in ("", "_reverse"):
-                sd[pre + path + "_rnn.weight_ih_l0" + suf] = t(4 * hidden, emb_dim)
+                sd[pre + path + "_rnn.weight_ih_l0" + suf] = t(4 * hidden, emb_dim * emb_ks)
                 sd[pre + path + "_rnn.weight_hh_l0" + suf] = t(4 * hidden, hidden)
                 sd[pre + path + "_rnn.bias_ih_l0" + suf] = t(4 * hidden)
                 sd[pre + path + "_rnn.bias_hh_l0" + suf] = t(4 * hidden)
-            sd[pre + path + "_linear.weight"] = t(emb_dim, 2 * hidden)
+            sd[pre + path + "_linear.weight"] = t(emb_dim, 2 * hidden) if emb_ks == emb_hs else t(2 * hidden, emb_dim, emb_ks)
             sd[pre + path + "_linear.bias"] = t(emb_dim)
         for name, co, e in (("Q", n_head * E, E), ("K", n_head * E, E), ("V", emb_dim, emb_dim // n_head)):
             sd[pre + f"attn_conv_{name}.weight"] = t(co, emb_dim, 1, 1)

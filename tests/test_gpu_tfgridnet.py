@@ -132,7 +132,7 @@ def _golden_case(name, tol_g=3e-3):
     a = meta["args"]
     m = get_model("TFGridNet")(**a)
     ref_sd = ot.make_state_dict(n_layers=a["n_layers"], emb_dim=a["emb_dim"], hidden=a["lstm_hidden_units"], n_head=a["attn_n_head"],
-                                approx_qk_dim=a["attn_approx_qk_dim"], n_fft=a["n_fft"])
+                                approx_qk_dim=a["attn_approx_qk_dim"], n_fft=a["n_fft"], emb_ks=a["emb_ks"], emb_hs=a["emb_hs"])
     assert list(m.state_dict().keys()) == list(ref_sd.keys())
     assert all(m.state_dict()[k].shape == ref_sd[k].shape for k in ref_sd)
     synth.fill_state_dict_(m.state_dict(), seed=meta["wseed"])
@@ -178,3 +178,37 @@ def test_tfgridnet_golden_small():
 def test_tfgridnet_golden_recipe_net():
     """tfgridnet.yaml network (6 blocks, 128 channels, hidden 192, 4 heads, qk 512) on 0.5 s: forward + SISDR + backward."""
     _golden_case("tfgridnet_full_train_05s")
+
+
+def test_tfgridnet_golden_unfold_path():
+    """emb_ks 4 / emb_hs 1 (the class default window): zero padding to whole windows, F.unfold, BLSTM over the windows,
+    ConvTranspose1d as transposed product + overlap-add, crop; forward + SISDR + every gradient vs the real reference."""
+    _golden_case("tfgridnet_small_ks4")
+
+
+@pytest.mark.parametrize("K,hs,T", [(4, 1, 71), (3, 2, 40), (4, 2, 10)])
+def test_unfold_fold_1d(K, hs, T):
+    """Unfold1dFn == F.unfold(x[..., None], (K, 1), stride=(hs, 1)); Fold1dFn == its adjoint (F.fold); both gradients."""
+    import torch.nn.functional as F
+    from wesep_b200 import ops
+    n, C = 3, 8
+    L = (T - K) // hs + 1
+    x0 = rnd(n, C, T, seed=1)
+    x = _act(x0)
+    col = ops.Unfold1dFn.apply(x, K, hs)
+    g0 = rnd(n, C * K, L, seed=2)
+    col.backward(g0)
+    x64 = x0.double().requires_grad_(True)
+    ref = F.unfold(x64[..., None], (K, 1), stride=(hs, 1))
+    ref.backward(g0.double())
+    check("unfold", col.detach(), ref.detach(), 1e-7)
+    check("unfold grad", x.grad, x64.grad, 1e-6)
+    c = _act(g0)
+    y = ops.Fold1dFn.apply(c, C, T, K, hs)
+    gy = rnd(n, C, T, seed=3)
+    y.backward(gy)
+    c64 = g0.double().requires_grad_(True)
+    ref2 = F.fold(c64, (T, 1), (K, 1), stride=(hs, 1))[..., 0]
+    ref2.backward(gy.double())
+    check("fold", y.detach(), ref2.detach(), 1e-6)
+    check("fold grad", c.grad, c64.grad, 1e-7)

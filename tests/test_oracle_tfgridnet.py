@@ -12,19 +12,24 @@ from wesep_b200 import synth
 def state_dict(meta):
     a = meta["args"]
     sd = ot.make_state_dict(n_layers=a["n_layers"], emb_dim=a["emb_dim"], hidden=a["lstm_hidden_units"], n_head=a["attn_n_head"],
-                            approx_qk_dim=a["attn_approx_qk_dim"], n_fft=a["n_fft"])
+                            approx_qk_dim=a["attn_approx_qk_dim"], n_fft=a["n_fft"], emb_ks=a["emb_ks"], emb_hs=a["emb_hs"])
     synth.fill_state_dict_(sd, seed=meta["wseed"])
     return sd
 
 
-def test_tfgridnet_small_golden():
-    """forward, per-row SI-SDR, loss and every gradient norm of the small case, oracle in fp64 vs the fp32 reference run."""
-    z, meta = load("tfgridnet_small_train")
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("name", ["tfgridnet_small_train", "tfgridnet_small_ks4"])
+def test_tfgridnet_small_golden(name):
+    """forward, per-row SI-SDR, loss and every gradient norm of the small cases (emb_ks 1 and the unfold path emb_ks 4 / emb_hs 1),
+    oracle in fp64 vs the fp32 reference run."""
+    z, meta = load(name)
     a = meta["args"]
     sd = {k: v.double().requires_grad_(True) for k, v in state_dict(meta).items()}
     mix, tgt, emb = inputs(meta, torch.float64)
     est = ot.tfgridnet_forward(sd, mix, emb, n_fft=a["n_fft"], stride=a["stride"], n_layers=a["n_layers"], n_head=a["attn_n_head"],
-                               eps=a["eps"])
+                               eps=a["eps"], emb_ks=a["emb_ks"], emb_hs=a["emb_hs"])
     ref = torch.from_numpy(z["out0"]).double()
     assert est.shape == ref.shape
     assert float((est.detach() - ref).norm() / ref.norm()) <= 2e-4

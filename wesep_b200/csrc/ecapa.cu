@@ -6,28 +6,39 @@
 
 namespace wb {
 
-// col[n][c*K + k][t] = x[n][c][t + (k - (K-1)/2) * dil]
+// col[n][c*K + k][l] = x[n][c][l * stride + k * dil - pad]   (0 outside [0, T)), l < Tout.
+// 'same' Conv1d: stride 1, pad = dil (K-1)/2, Tout = T;  F.unfold(kernel (K, 1), stride (hs, 1)): dil 1, pad 0, Tout = (T-K)/hs + 1
+__device__ __forceinline__ void i1_geom(const WesepIm2col1dArgs& a, int& stride, int& pad, int& Tout) {
+  stride = a.stride > 0 ? a.stride : 1;
+  pad = a.unfold ? 0 : a.dil * (a.K - 1) / 2;
+  Tout = a.unfold ? (a.T - a.K) / stride + 1 : a.T;
+}
 __global__ void __launch_bounds__(256) im2col1d_kernel(WesepIm2col1dArgs a) {
   const int r = blockIdx.y, n = blockIdx.z;
   const int c = r / a.K, k = r - c * a.K;
-  const int sh = (k - (a.K - 1) / 2) * a.dil;
+  int stride, pad, Tout;
+  i1_geom(a, stride, pad, Tout);
   const float* x = a.x + ((int64_t)n * a.C + c) * a.ldx;
   float* col = a.col + (int64_t)n * a.bsc + (int64_t)r * a.ldc;
-  for (int t = blockIdx.x * 256 + threadIdx.x; t < a.T; t += gridDim.x * 256) {
-    const int s = t + sh;
-    col[t] = (s >= 0 && s < a.T) ? __ldg(x + s) : 0.f;
+  for (int l = blockIdx.x * 256 + threadIdx.x; l < Tout; l += gridDim.x * 256) {
+    const int s = l * stride + k * a.dil - pad;
+    col[l] = (s >= 0 && s < a.T) ? __ldg(x + s) : 0.f;
   }
 }
-// gx[n][c][s] = sum_k gcol[n][c*K + k][s - (k - (K-1)/2) dil]
+// adjoint: gx[n][c][s] = sum over (k, l) with l * stride + k * dil - pad == s of gcol[n][c*K + k][l]
 __global__ void __launch_bounds__(256) col2im1d_kernel(WesepIm2col1dArgs a) {
   const int c = blockIdx.y, n = blockIdx.z;
+  int stride, pad, Tout;
+  i1_geom(a, stride, pad, Tout);
   const float* g = a.gcol + (int64_t)n * a.bsc + (int64_t)c * a.K * a.ldc;
   float* gx = a.gx + ((int64_t)n * a.C + c) * a.ldx;
   for (int s = blockIdx.x * 256 + threadIdx.x; s < a.T; s += gridDim.x * 256) {
     float acc = 0.f;
     for (int k = 0; k < a.K; ++k) {
-      const int t = s - (k - (a.K - 1) / 2) * a.dil;
-      if (t >= 0 && t < a.T) acc += __ldg(g + (int64_t)k * a.ldc + t);
+      const int num = s + pad - k * a.dil;
+      if (num < 0 || num % stride) continue;
+      const int l = num / stride;
+      if (l < Tout) acc += __ldg(g + (int64_t)k * a.ldc + l);
     }
     gx[s] = acc;
   }
@@ -102,16 +113,20 @@ __global__ void __launch_bounds__(256) astp_kernel(WesepAstpArgs a) {
 
 using namespace wb;
 
+static int tout_of(const WesepIm2col1dArgs* a) { return a->unfold ? (a->T - a->K) / (a->stride > 0 ? a->stride : 1) + 1 : a->T; }
 static int check_i1(const WesepIm2col1dArgs* a) {
-  if (!a || a->n <= 0 || a->n > 65535 || a->C <= 0 || a->T <= 0 || a->K <= 0 || !(a->K & 1) || a->dil <= 0) return fail(-1, "im2col1d: shape (odd K)");
+  if (!a || a->n <= 0 || a->n > 65535 || a->C <= 0 || a->T <= 0 || a->K <= 0 || a->dil <= 0 || a->stride < 0) return fail(-1, "im2col1d: shape");
+  if (!a->unfold && (!(a->K & 1) || a->stride > 1)) return fail(-1, "im2col1d: the 'same' convolution needs an odd kernel and stride 1");
+  if (a->unfold && (a->dil != 1 || a->T < a->K)) return fail(-1, "im2col1d: unfold needs dilation 1 and T >= K");
   if ((int64_t)a->C * a->K > 65535) return fail(-2, "im2col1d: too many gathered rows for one launch");
-  if (a->ldx < a->T || a->ldc < a->T || a->bsc < (int64_t)a->C * a->K * a->ldc) return fail(-1, "im2col1d: strides");
+  const int tout_ = a->unfold ? (a->T - a->K) / (a->stride > 0 ? a->stride : 1) + 1 : a->T;
+  if (a->ldx < a->T || a->ldc < tout_ || a->bsc < (int64_t)a->C * a->K * a->ldc) return fail(-1, "im2col1d: strides");
   return 0;
 }
 extern "C" int wesep_b200_im2col1d_fwd(const WesepIm2col1dArgs* a, void* stream) {
   if (int rc = check_i1(a)) return rc;
   if (!a->x || !a->col) return fail(-1, "im2col1d: pointers");
-  im2col1d_kernel<<<dim3(cdiv(a->T, 1024), a->C * a->K, a->n), 256, 0, (cudaStream_t)stream>>>(*a);
+  im2col1d_kernel<<<dim3(cdiv(tout_of(a), 1024), a->C * a->K, a->n), 256, 0, (cudaStream_t)stream>>>(*a);
   WB_LAUNCH_CHECK("im2col1d_fwd");
   return 0;
 }

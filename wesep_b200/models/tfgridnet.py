@@ -8,7 +8,8 @@ channels (cLN kernel) -> BLSTM on the persistent cluster recurrence kernel -> Li
 1x1 convolutions, PReLU + head LayerNorm (csrc/tfgridnet.cu), both attention products on the pointwise GEMMs with the row
 softmax kernel in between.  The nn.* members only hold parameters.  There is no CPU path.
 
-Built: emb_ks == emb_hs == 1 (tfgridnet.yaml:52-53), n_srcs == 1, n_imics == 1, multiply fusion.
+Built: emb_ks == emb_hs == 1 (tfgridnet.yaml:52-53) and emb_ks != emb_hs (the class default 4 / 1: unfold + ConvTranspose1d),
+n_srcs == 1, n_imics == 1, multiply fusion.
 """
 import math
 
@@ -72,16 +73,23 @@ class GridNetBlock(nn.Module):
                  eps=1e-5):
         super().__init__()
         assert activation == "prelu"
-        if emb_ks != 1 or emb_hs != 1:
-            raise NotImplementedError("TF-GridNet: emb_ks == emb_hs == 1 (tfgridnet.yaml:52-53) is built; the unfold / "
-                                      "ConvTranspose1d path of gridnet_block.py:147-160 is not")
+        if emb_ks == emb_hs and emb_ks != 1:
+            raise NotImplementedError("TF-GridNet: emb_ks == emb_hs > 1 (the reshaping Linear path of gridnet_block.py:139-146 with "
+                                      "several frames per step) is not built; emb_ks == emb_hs == 1 (tfgridnet.yaml:52-53) and "
+                                      "emb_ks != emb_hs (the class default 4 / 1) are")
         in_channels = emb_dim * emb_ks
         self.intra_norm = nn.LayerNorm(emb_dim, eps=eps)
         self.intra_rnn = nn.LSTM(in_channels, hidden_channels, 1, batch_first=True, bidirectional=True)
-        self.intra_linear = nn.Linear(hidden_channels * 2, in_channels)
+        if emb_ks == emb_hs:
+            self.intra_linear = nn.Linear(hidden_channels * 2, in_channels)
+        else:
+            self.intra_linear = nn.ConvTranspose1d(hidden_channels * 2, emb_dim, emb_ks, stride=emb_hs)
         self.inter_norm = nn.LayerNorm(emb_dim, eps=eps)
         self.inter_rnn = nn.LSTM(in_channels, hidden_channels, 1, batch_first=True, bidirectional=True)
-        self.inter_linear = nn.Linear(hidden_channels * 2, in_channels)
+        if emb_ks == emb_hs:
+            self.inter_linear = nn.Linear(hidden_channels * 2, in_channels)
+        else:
+            self.inter_linear = nn.ConvTranspose1d(hidden_channels * 2, emb_dim, emb_ks, stride=emb_hs)
         E = math.ceil(approx_qk_dim * 1.0 / n_freqs)
         assert emb_dim % n_head == 0
         self.add_module("attn_conv_Q", nn.Conv2d(emb_dim, n_head * E, 1))
@@ -98,18 +106,32 @@ class GridNetBlock(nn.Module):
         y = ops.Conv1x1Fn.apply(x, conv.weight.reshape(conv.weight.shape[0], -1), conv.bias, False, None)
         return ops.HeadLnFn.apply(y, norm.act.weight, norm.gamma, norm.beta, self.n_head, T, F, norm.eps)
 
+    def _path(self, x, norm, rnn, lin):
+        if self.emb_ks == self.emb_hs:
+            return ops.res_rnn(x, norm.weight, norm.bias, _lstm_args(rnn), lin.weight, lin.bias, layer_norm_eps=self.eps)
+        return ops.res_rnn_unfold(x, norm.weight, norm.bias, _lstm_args(rnn), lin.weight, lin.bias, self.emb_ks, self.emb_hs, self.eps)
+
     def run(self, x, B, T, F):
         """x act [B, C, T*F] -> act [B, C, T*F]."""
         C, H = self.emb_dim, self.n_head
-        # intra (along frequency): rows (b, t), steps f — gridnet_block.py:139-146,161
-        xi = ops.as_act(x.unflatten(2, (T, F)).permute(0, 2, 1, 3).reshape(B * T, C, F))
-        yi = ops.res_rnn(xi, self.intra_norm.weight, self.intra_norm.bias, _lstm_args(self.intra_rnn), self.intra_linear.weight,
-                         self.intra_linear.bias, layer_norm_eps=self.eps)
-        # inter (along time): rows (b, f), steps t — gridnet_block.py:163-172,187
+        old_T, old_F = T, F
+        olp = self.emb_ks - self.emb_hs
+        x4 = x.unflatten(2, (T, F))
+        if self.emb_ks != 1:                                       # gridnet_block.py:124-133: zero padding to whole windows
+            T = math.ceil((old_T + 2 * olp - self.emb_ks) / self.emb_hs) * self.emb_hs + self.emb_ks
+            F = math.ceil((old_F + 2 * olp - self.emb_ks) / self.emb_hs) * self.emb_hs + self.emb_ks
+            x4 = torch.nn.functional.pad(x4, (olp, F - old_F - olp, olp, T - old_T - olp))
+        # intra (along frequency): rows (b, t), steps f — gridnet_block.py:135-161
+        xi = ops.as_act(x4.permute(0, 2, 1, 3).reshape(B * T, C, F))
+        yi = self._path(xi, self.intra_norm, self.intra_rnn, self.intra_linear)
+        # inter (along time): rows (b, f), steps t — gridnet_block.py:163-187
         xe = ops.SwapOIFn.apply(yi, B, None)                                             # [B*F, C, T]
-        ye = ops.res_rnn(xe, self.inter_norm.weight, self.inter_norm.bias, _lstm_args(self.inter_rnn), self.inter_linear.weight,
-                         self.inter_linear.bias, layer_norm_eps=self.eps)
-        x1 = ops.as_act(ye.unflatten(0, (B, F)).permute(0, 2, 3, 1).reshape(B, C, T * F))    # [B, F, C, T] -> [B, C, T, F]
+        ye = self._path(xe, self.inter_norm, self.inter_rnn, self.inter_linear)
+        x1 = ye.unflatten(0, (B, F)).permute(0, 2, 3, 1)                                 # [B, F, C, T] -> [B, C, T, F]
+        if self.emb_ks != 1:
+            x1 = x1[..., olp:olp + old_T, olp:olp + old_F]                               # gridnet_block.py:190
+            T, F = old_T, old_F
+        x1 = ops.as_act(x1.reshape(B, C, T * F))
         # full-band self-attention over frames — gridnet_block.py:192-224
         Qc = self._qkv(x1, self["attn_conv_Q"], self["attn_norm_Q"], T, F)               # [B, H*E, T*F]
         Kc = self._qkv(x1, self["attn_conv_K"], self["attn_norm_K"], T, F)

@@ -1022,6 +1022,21 @@ def res_rnn(x, norm_w, norm_b, lstm, proj_w, proj_b, layer_norm_eps=None):
     return SwapOIFn.apply(p, 1, x)                                      # [Q, C, S] + residual
 
 
+def res_rnn_unfold(x, norm_w, norm_b, lstm, ct_w, ct_b, ks, hs, eps):
+    """The intra / inter path of a TF-GridNet block with emb_ks != emb_hs (gridnet_block.py:147-161,173-187) on an act tensor
+    x [rows, C, S]: LayerNorm(C) -> F.unfold (ks taps, stride hs) -> BLSTM over the (S - ks) / hs + 1 windows ->
+    nn.ConvTranspose1d(2 Hd, C, ks, stride hs) = transposed pointwise product + overlap-add -> + x."""
+    rows, C, S = x.shape
+    xh = cln(x, norm_w, norm_b, eps)
+    col = Unfold1dFn.apply(xh, ks, hs)                                  # [rows, C*ks, L]
+    xn = SwapOIFn.apply(col, 1, None)                                   # [L, C*ks, rows]
+    h = LstmTmFn.apply(xn, *lstm)                                       # [L, 2Hd, rows]
+    d = Conv1x1Fn.apply(h, ct_w.reshape(ct_w.shape[0], C * ks), None, True, None)     # [L, C*ks, rows]
+    y = Fold1dFn.apply(SwapOIFn.apply(d, 1, None), C, S, ks, hs)        # [rows, C, S]
+    y = RowAffineFn.apply(y, None, ct_b[None].expand(rows, C))
+    return AddFn.apply(y, x)
+
+
 def bsnet(x, nband, band_rnn, band_comm):
     """BSNet.forward (bsrnn.py:70-83) on an act tensor x [B, nband*N, T].  band_rnn / band_comm = argument tuples of
     res_rnn (norm_w, norm_b, lstm[8], proj_w, proj_b)."""
@@ -1808,6 +1823,56 @@ class Im2Col1dFn(torch.autograd.Function):
         _lib.call("wesep_b200_im2col1d_bwd", _args("WesepIm2col1dArgs", n=n, C=C, T=T, K=K, dil=dil, ldx=gx.stride(1),
                                                    ldc=gcol.stride(1), bsc=gcol.stride(0), gcol=gcol, gx=gx), _stream())
         return gx, None, None
+
+
+class Unfold1dFn(torch.autograd.Function):
+    """F.unfold(x[..., None], (K, 1), stride=(hs, 1)) on an act tensor [n, C, T] -> [n, C*K, (T - K) // hs + 1] (rows (c, k))."""
+
+    @staticmethod
+    def forward(ctx, x, K, hs):
+        x = as_act(x)
+        n, C, T = x.shape
+        L = (T - K) // hs + 1
+        col = new_act(n, C * K, L, x.device)
+        _lib.call("wesep_b200_im2col1d_fwd", _args("WesepIm2col1dArgs", n=n, C=C, T=T, K=int(K), dil=1, ldx=x.stride(1),
+                                                   ldc=col.stride(1), bsc=col.stride(0), x=x, col=col, unfold=1, stride=int(hs)), _stream())
+        ctx.meta = (n, C, T, int(K), int(hs))
+        return col
+
+    @staticmethod
+    def backward(ctx, gcol):
+        n, C, T, K, hs = ctx.meta
+        return _fold1d(as_act(gcol), n, C, T, K, hs), None, None
+
+
+def _fold1d(col, n, C, T, K, hs):
+    y = new_act(n, C, T, col.device)
+    _lib.call("wesep_b200_im2col1d_bwd", _args("WesepIm2col1dArgs", n=n, C=C, T=T, K=K, dil=1, ldx=y.stride(1), ldc=col.stride(1),
+                                               bsc=col.stride(0), gcol=col, gx=y, unfold=1, stride=hs), _stream())
+    return y
+
+
+class Fold1dFn(torch.autograd.Function):
+    """The adjoint of Unfold1dFn as a forward op: [n, C*K, L] -> [n, C, T] overlap-add (the data movement of
+    nn.ConvTranspose1d(kernel K, stride hs) after its pointwise product)."""
+
+    @staticmethod
+    def forward(ctx, col, C, T, K, hs):
+        col = as_act(col)
+        n = col.shape[0]
+        if col.shape[1] != C * K or col.shape[2] != (T - K) // hs + 1:
+            raise RuntimeError("fold1d: shape mismatch")
+        ctx.meta = (n, C, T, int(K), int(hs))
+        return _fold1d(col, n, C, T, int(K), int(hs))
+
+    @staticmethod
+    def backward(ctx, gy):
+        n, C, T, K, hs = ctx.meta
+        gy = as_act(gy)
+        gcol = new_act(n, C * K, (T - K) // hs + 1, gy.device)
+        _lib.call("wesep_b200_im2col1d_fwd", _args("WesepIm2col1dArgs", n=n, C=C, T=T, K=K, dil=1, ldx=gy.stride(1),
+                                                   ldc=gcol.stride(1), bsc=gcol.stride(0), x=gy, col=gcol, unfold=1, stride=hs), _stream())
+        return gcol, None, None, None, None
 
 
 def conv1d_k(x, weight, bias, dil=1, act=None):
