@@ -8,7 +8,7 @@ gradient summaries of the REAL reference module (tests/golden/make_golden_tfgrid
 compares this file with them.
 
 Scope: ``joint_training=False`` (a given speaker embedding), ``emb_ks == emb_hs == 1`` (tfgridnet.yaml:52-53) or
-``emb_ks != emb_hs`` (the class default 4 / 1), one source, one microphone, ``multiply`` fusion.
+``emb_ks != emb_hs`` (the class default 4 / 1) or ``emb_ks == emb_hs > 1``, one source, one microphone, ``multiply`` fusion.
 """
 import math
 
@@ -61,9 +61,10 @@ def _rnn_path(v, sd, pre, name, ks, hs, eps):
     Linear or ConvTranspose1d -> + v (gridnet_block.py:135-161 / 163-187)."""
     B, A, S, C = v.shape
     y = layer_norm_c(v, sd[pre + name + "_norm.weight"], sd[pre + name + "_norm.bias"], eps).reshape(B * A, S, C)
-    if ks == hs:
+    if ks == hs:                                                       # ks consecutive positions per step, features (k, c)
+        y = y.reshape(B * A, S // ks, ks * C)
         y = blstm(y, sd, pre + name + "_rnn.") @ sd[pre + name + "_linear.weight"].t() + sd[pre + name + "_linear.bias"]
-        return y.view(B, A, S, C) + v
+        return y.reshape(B, A, S, C) + v
     y = F.unfold(y.transpose(1, 2)[..., None], (ks, 1), stride=(hs, 1)).transpose(1, 2)       # [BA, L, C*ks]
     y = blstm(y, sd, pre + name + "_rnn.").transpose(1, 2)                                    # [BA, 2H, L]
     y = F.conv_transpose1d(y, sd[pre + name + "_linear.weight"], sd[pre + name + "_linear.bias"], stride=hs)   # [BA, C, S]
@@ -151,8 +152,8 @@ def make_state_dict(n_layers=6, emb_dim=128, hidden=192, n_head=4, approx_qk_dim
                 sd[pre + path + "_rnn.weight_hh_l0" + suf] = t(4 * hidden, hidden)
                 sd[pre + path + "_rnn.bias_ih_l0" + suf] = t(4 * hidden)
                 sd[pre + path + "_rnn.bias_hh_l0" + suf] = t(4 * hidden)
-            sd[pre + path + "_linear.weight"] = t(emb_dim, 2 * hidden) if emb_ks == emb_hs else t(2 * hidden, emb_dim, emb_ks)
-            sd[pre + path + "_linear.bias"] = t(emb_dim)
+            sd[pre + path + "_linear.weight"] = t(emb_dim * emb_ks, 2 * hidden) if emb_ks == emb_hs else t(2 * hidden, emb_dim, emb_ks)
+            sd[pre + path + "_linear.bias"] = t(emb_dim * emb_ks if emb_ks == emb_hs else emb_dim)
         for name, co, e in (("Q", n_head * E, E), ("K", n_head * E, E), ("V", emb_dim, emb_dim // n_head)):
             sd[pre + f"attn_conv_{name}.weight"] = t(co, emb_dim, 1, 1)
             sd[pre + f"attn_conv_{name}.bias"] = t(co)

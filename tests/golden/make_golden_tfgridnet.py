@@ -27,6 +27,9 @@ def main():
     # the class default window: emb_ks 4 / emb_hs 1 (unfold + ConvTranspose1d paths), 1 block
     run_case(TFGridNet, "tfgridnet_small_ks4", dict(base, n_layers=1, emb_dim=16, lstm_hidden_units=32, attn_n_head=2,
                                                     attn_approx_qk_dim=260, emb_ks=4, emb_hs=1), 2, 1500, 73, 83)
+    # ks == hs == 2: two positions packed per recurrent step (the reshaping Linear path)
+    run_case(TFGridNet, "tfgridnet_small_ks2", dict(base, n_layers=1, emb_dim=16, lstm_hidden_units=32, attn_n_head=2,
+                                                    attn_approx_qk_dim=260, emb_ks=2, emb_hs=2), 2, 1500, 74, 84)
     # the recipe network (tfgridnet.yaml:44-55: 6 blocks, 128 channels, hidden 192, 4 heads, qk 512) on 0.5 s, one row
     run_case(TFGridNet, "tfgridnet_full_train_05s", dict(base, n_layers=6, emb_dim=128, lstm_hidden_units=192, attn_n_head=4,
                                                          attn_approx_qk_dim=512), 1, 8000, 72, 82, subsample=2)

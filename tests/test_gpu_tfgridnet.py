@@ -186,6 +186,11 @@ def test_tfgridnet_golden_unfold_path():
     _golden_case("tfgridnet_small_ks4")
 
 
+def test_tfgridnet_golden_packed_path():
+    """emb_ks == emb_hs == 2: two positions per recurrent step (gridnet_block.py:139-146); vs the real reference."""
+    _golden_case("tfgridnet_small_ks2")
+
+
 @pytest.mark.parametrize("K,hs,T", [(4, 1, 71), (3, 2, 40), (4, 2, 10)])
 def test_unfold_fold_1d(K, hs, T):
     """Unfold1dFn == F.unfold(x[..., None], (K, 1), stride=(hs, 1)); Fold1dFn == its adjoint (F.fold); both gradients."""

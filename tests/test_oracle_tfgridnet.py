@@ -20,7 +20,7 @@ def state_dict(meta):
 import pytest  # noqa: E402
 
 
-@pytest.mark.parametrize("name", ["tfgridnet_small_train", "tfgridnet_small_ks4"])
+@pytest.mark.parametrize("name", ["tfgridnet_small_train", "tfgridnet_small_ks4", "tfgridnet_small_ks2"])
 def test_tfgridnet_small_golden(name):
     """forward, per-row SI-SDR, loss and every gradient norm of the small cases (emb_ks 1 and the unfold path emb_ks 4 / emb_hs 1),
     oracle in fp64 vs the fp32 reference run."""

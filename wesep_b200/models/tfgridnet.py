@@ -8,7 +8,8 @@ channels (cLN kernel) -> BLSTM on the persistent cluster recurrence kernel -> Li
 1x1 convolutions, PReLU + head LayerNorm (csrc/tfgridnet.cu), both attention products on the pointwise GEMMs with the row
 softmax kernel in between.  The nn.* members only hold parameters.  There is no CPU path.
 
-Built: emb_ks == emb_hs == 1 (tfgridnet.yaml:52-53) and emb_ks != emb_hs (the class default 4 / 1: unfold + ConvTranspose1d),
+Built: every (emb_ks, emb_hs) the reference accepts — 1 / 1 (tfgridnet.yaml:52-53), ks != hs (the class default 4 / 1: unfold +
+ConvTranspose1d) and ks == hs > 1 (ks positions packed per step) —,
 n_srcs == 1, n_imics == 1, multiply fusion.
 """
 import math
@@ -73,10 +74,6 @@ class GridNetBlock(nn.Module):
                  eps=1e-5):
         super().__init__()
         assert activation == "prelu"
-        if emb_ks == emb_hs and emb_ks != 1:
-            raise NotImplementedError("TF-GridNet: emb_ks == emb_hs > 1 (the reshaping Linear path of gridnet_block.py:139-146 with "
-                                      "several frames per step) is not built; emb_ks == emb_hs == 1 (tfgridnet.yaml:52-53) and "
-                                      "emb_ks != emb_hs (the class default 4 / 1) are")
         in_channels = emb_dim * emb_ks
         self.intra_norm = nn.LayerNorm(emb_dim, eps=eps)
         self.intra_rnn = nn.LSTM(in_channels, hidden_channels, 1, batch_first=True, bidirectional=True)
@@ -107,9 +104,23 @@ class GridNetBlock(nn.Module):
         return ops.HeadLnFn.apply(y, norm.act.weight, norm.gamma, norm.beta, self.n_head, T, F, norm.eps)
 
     def _path(self, x, norm, rnn, lin):
-        if self.emb_ks == self.emb_hs:
+        ks, hs, C = self.emb_ks, self.emb_hs, self.emb_dim
+        if ks == 1:
             return ops.res_rnn(x, norm.weight, norm.bias, _lstm_args(rnn), lin.weight, lin.bias, layer_norm_eps=self.eps)
-        return ops.res_rnn_unfold(x, norm.weight, norm.bias, _lstm_args(rnn), lin.weight, lin.bias, self.emb_ks, self.emb_hs, self.eps)
+        if ks != hs:
+            return ops.res_rnn_unfold(x, norm.weight, norm.bias, _lstm_args(rnn), lin.weight, lin.bias, ks, hs, self.eps)
+        # ks == hs > 1 (gridnet_block.py:139-146): `view([B*T, -1, ks*C])` packs ks consecutive positions into the feature axis in
+        # (k, c) order; the unfold kernel produces (c, k) rows, so the LSTM input columns / Linear output rows are permuted to match
+        perm = (torch.arange(ks, device=x.device)[None, :] * C + torch.arange(C, device=x.device)[:, None]).reshape(-1)   # [c*ks+k] -> k*C+c
+        lstm = _lstm_args(rnn)
+        lstm[0], lstm[4] = lstm[0][:, perm], lstm[4][:, perm]
+        rows, _, S = x.shape
+        xh = ops.cln(x, norm.weight, norm.bias, self.eps)
+        xn = ops.SwapOIFn.apply(ops.Unfold1dFn.apply(xh, ks, ks), 1, None)                # [S/ks, C*ks, rows]
+        h = ops.LstmTmFn.apply(xn, *lstm)
+        p = ops.Conv1x1Fn.apply(h, lin.weight[perm], lin.bias[perm], False, None)        # [S/ks, C*ks, rows]
+        y = ops.Fold1dFn.apply(ops.SwapOIFn.apply(p, 1, None), C, S, ks, ks)
+        return ops.AddFn.apply(y, x)
 
     def run(self, x, B, T, F):
         """x act [B, C, T*F] -> act [B, C, T*F]."""
